@@ -1,0 +1,15 @@
+"""b200clip: B200-native CLIP head behind the reference's nn.Module / loss-function surface.
+
+Public names mirror cjycarrie/CLIP-FOR-DL (0426/train.py, disease_analysis.py): ImageProjection, TextProjection,
+contrastive_loss, multilabel_contrastive_loss, predict_multilabel, predict_zero_shot; plus ClassificationAdapter
+(the notebook's "C-Adapter"), the fused ClipHead and install() which patches a reference module in place.
+"""
+from .modules import MODEL_CONFIG, ClassificationAdapter, ImageProjection, TextProjection  # noqa: F401
+from .losses import contrastive_loss, fc_adapter_bce, multilabel_contrastive_loss, predict_multilabel  # noqa: F401
+from .zero_shot import (predict_zero_shot, unpack_mask, zero_shot_posneg, zero_shot_threshold,  # noqa: F401
+                        zero_shot_topk)
+from .head import ClipHead, ClipHeadFn  # noqa: F401
+from .ops import normalize  # noqa: F401
+from .install import install  # noqa: F401
+
+__version__ = "0.1.0"

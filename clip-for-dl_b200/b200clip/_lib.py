@@ -1,0 +1,86 @@
+"""ctypes binding of libb200clip.so (the C ABI declared in include/b200clip.h).
+
+There is no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libb200clip.so")
+
+vp, ll, i32, f32, f64, sz = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_double, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/b200clip.h one to one
+SIGNATURES = {
+    "b200clip_version": (i32, []),
+    "b200clip_last_error_string": (C.c_char_p, []),
+    "b200clip_gemm_bf16": (i32, [vp, vp, i32, i32, i32, i32, i32, ll, ll, i32, f32, vp, ll, vp, ll, vp, vp, ll, vp, ll, i32, vp]),
+    "b200clip_l2norm_fwd": (i32, [vp, i32, ll, vp, vp, vp, ll, i32, f32, vp]),
+    "b200clip_l2norm_bwd": (i32, [vp, vp, i32, ll, vp, vp, i32, ll, i32, f32, vp]),
+    "b200clip_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, ll, i32, f32, f32, vp]),
+    "b200clip_layernorm_bwd_workspace_bytes": (sz, [ll, i32]),
+    "b200clip_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, ll, i32, vp, sz, vp]),
+    "b200clip_colsum_workspace_bytes": (sz, [ll, i32]),
+    "b200clip_colsum": (i32, [vp, i32, ll, ll, i32, vp, i32, vp, sz, vp]),
+    "b200clip_cast_f32_bf16": (i32, [vp, vp, ll, vp]),
+    "b200clip_sum_f32": (i32, [vp, ll, vp, vp]),
+    "b200clip_proj_fwd": (i32, [vp, ll, i32, i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "b200clip_proj_bwd_workspace_bytes": (sz, [ll, i32, i32]),
+    "b200clip_proj_bwd": (i32, [vp, vp, ll, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "b200clip_infonce_workspace_bytes": (sz, [ll, ll]),
+    "b200clip_infonce_fwd_stats": (i32, [vp, vp, i32, ll, ll, f32, vp, vp, vp, sz, vp]),
+    "b200clip_infonce_loss": (i32, [vp, vp, i32, ll, ll, ll, f32, vp, vp, ll, ll, vp, vp, vp, vp, vp, sz, vp]),
+    "b200clip_infonce_bwd": (i32, [vp, vp, i32, ll, ll, ll, f32, vp, vp, vp, vp, vp, vp]),
+    "b200clip_smallc_workspace_bytes": (sz, [ll, i32, i32]),
+    "b200clip_mlbce_fwd_bwd": (i32, [vp, ll, vp, vp, i32, ll, ll, i32, i32, f32, vp, f64, vp, vp, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "b200clip_fc_bce_fwd_bwd": (i32, [vp, ll, vp, vp, vp, ll, ll, i32, i32, f64, f32, vp, vp, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "b200clip_skinny_outer": (i32, [vp, i32, vp, ll, vp, ll, i32, vp, vp, i32, vp, sz, vp]),
+    "b200clip_predict_multilabel": (i32, [vp, ll, vp, ll, i32, i32, f32, f32, vp, vp]),
+    "b200clip_zeroshot_score": (i32, [vp, ll, ll, vp, i32, i32, i32, i32, f32, C.POINTER(f32), i32, f32, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building is __graft_entry__.build()'s job; a missing .so is a hard error)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"b200clip: CUDA library not built ({LIB_PATH}); run `python clip-for-dl_b200/build.py`. "
+                "There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().b200clip_last_error_string()
+        raise RuntimeError(f"b200clip.{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("b200clip: tensors must live on a CUDA device (B200); there is no CPU path")

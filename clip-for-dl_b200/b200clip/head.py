@@ -1,0 +1,146 @@
+"""The fused CLIP head: projections -> (LayerNorm + L2-norm) -> symmetric InfoNCE + multi-label BCE + FC-adapter BCE,
+forward and backward, single- or multi-GPU (data-parallel over the batch).
+
+This is the path bench.py times (BASELINE.json: "contrastive head fwd+bwd").  It composes the same C-ABI entry points
+as the stand-alone modules/losses, but as ONE autograd node so that no fp32 copies of the normalised embeddings are
+materialised between kernels and every collective has a fixed place:
+
+  rank r owns rows [r*B/W, (r+1)*B/W) of images and texts (its local pairs)
+  fwd : all_gather(T_hat bf16)  ->  local row block of logits against all columns (never materialised)
+        all_reduce(column sum-exp partials [B])      all_reduce(3 loss scalars)
+  bwd : dI_hat complete locally;  dT_hat partial [B, D]  ->  reduce_scatter(SUM)
+        all_reduce(head parameter gradients)                          
+Only T_hat is gathered: the local I rows are the stationary operand of direction 0 and the streamed operand of
+direction 1, so I_hat never leaves its rank.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops
+from .modules import MODEL_CONFIG, ClassificationAdapter, ImageProjection, TextProjection
+
+PARAM_ORDER = ("iw1", "ib1", "iw2", "ib2", "ig", "ibeta", "tw1", "tb1", "tw2", "tb2", "tg", "tbeta", "fw", "fb")
+
+
+def _world(group) -> int:
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def _rank(group) -> int:
+    return dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
+
+
+class ClipHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, *params):
+        (iw1, ib1, iw2, ib2, ig, ibeta, tw1, tb1, tw2, tb2, tg, tbeta, fw, fb) = params
+        ops.require_cuda(x_img, x_txt, class_text, labels, iw1)
+        W, rank = _world(group), _rank(group)
+        b_loc = x_img.shape[0]
+        b_glob = b_loc * W
+        row0 = rank * b_loc
+        xi, xt = ops.cast_bf16(x_img), ops.cast_bf16(x_txt)
+        iw1b, iw2b, tw1b, tw2b = (ops.cast_bf16(w) for w in (iw1, iw2, tw1, tw2))
+        f = ops._f32c
+        # text first so its all-gather can overlap the image projection
+        y_txt, that_loc, inv_txt, saved_t = ops.proj_fwd(xt, tw1b, f(tb1), tw2b, f(tb2), f(tg), f(tbeta), want_yhat=True)
+        if W > 1:
+            that_all = torch.empty((b_glob, that_loc.shape[1]), dtype=torch.bfloat16, device=that_loc.device)
+            work = dist.all_gather_into_tensor(that_all, that_loc, group=group, async_op=True)
+        else:
+            that_all, work = that_loc, None
+        y_img, ihat, inv_img, saved_i = ops.proj_fwd(xi, iw1b, f(ib1), iw2b, f(ib2), f(ig), f(ibeta), want_yhat=True)
+        labels_f = f(labels)
+        lsum = ops._label_sum(labels_f)
+        if W > 1:
+            dist.all_reduce(lsum, group=group)
+            work.wait()
+        l_nce, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, group=group if W > 1 else None)
+        C = class_text.shape[0]
+        l_bce, status, bsums, *_ = ops.mlbce(y_img, class_text, labels_f, tau_bce, label_sum=lsum,
+                                             total_elems=float(b_glob) * C, finalize=(W == 1))
+        l_fc, fsums, *_ = ops.fc_bce(y_img, fw, fb, labels_f, total_elems=float(b_glob) * C, finalize=(W == 1))
+        if W > 1:
+            both = torch.stack([bsums[0], bsums[1], fsums[0]])
+            dist.all_reduce(both, group=group)
+            P = lsum.double()
+            N = float(b_glob) * C - P
+            l_bce = (0.5 * (-both[0] / (P + 1e-8) - both[1] / (N + 1e-8))).float()
+            l_fc = (both[2] / (float(b_glob) * C)).float()
+        loss = l_nce + l_bce + l_fc
+        ctx.save_for_backward(xi, xt, iw1b, iw2b, tw1b, tw2b, f(ig), f(tg), f(class_text), labels_f, lsum, y_img, y_txt, ihat,
+                              that_all, inv_img, inv_txt, rinvh, cinvh, f(fw), f(fb) if fb is not None else None,
+                              *saved_i, *saved_t)
+        ctx.meta = (tau_nce, tau_bce, group, W, row0, b_loc, b_glob, x_img.requires_grad, x_txt.requires_grad)
+        ctx.parts = (l_nce.detach(), l_bce.detach(), l_fc.detach())
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (xi, xt, iw1b, iw2b, tw1b, tw2b, ig, tg, class_text, labels_f, lsum, y_img, y_txt, ihat, that_all, inv_img, inv_txt,
+         rinvh, cinvh, fw, fb, *rest) = ctx.saved_tensors
+        saved_i, saved_t = tuple(rest[:5]), tuple(rest[5:])
+        tau_nce, tau_bce, group, W, row0, b_loc, b_glob, need_dxi, need_dxt = ctx.meta
+        C = class_text.shape[0]
+        g = ops._f32c(g)
+        d_ihat, d_that = ops.infonce_backward(ihat, that_all, tau_nce, rinvh, cinvh, g, row0=row0)
+        if W > 1:
+            d_that_loc = torch.empty((b_loc, d_that.shape[1]), dtype=torch.float32, device=d_that.device)
+            work = dist.reduce_scatter_tensor(d_that_loc, d_that, group=group, async_op=True)
+        else:
+            d_that_loc, work = d_that, None
+        # image side: through the L2 normalisation, then add the two BCE heads' gradients (they act on y_img itself)
+        dy_img = ops.l2norm_bwd(d_ihat, y_img, inv_img)
+        ops.mlbce(y_img, class_text, labels_f, tau_bce, grad_scale=g, label_sum=lsum, total_elems=float(b_glob) * C,
+                  finalize=False, dx_accum=dy_img)
+        _, _, _, coef, _, _ = ops.fc_bce(y_img, fw, fb, labels_f, grad_scale=g, total_elems=float(b_glob) * C, want_coef=True,
+                                         finalize=False, dx_accum=dy_img)
+        dfw, dfb = ops.skinny_outer(coef, y_img, want_bias=True)
+        gi = ops.proj_bwd(dy_img, xi, iw1b, iw2b, ig, saved_i, need_dxi)
+        if work is not None:
+            work.wait()
+        dy_txt = ops.l2norm_bwd(d_that_loc, y_txt, inv_txt)
+        gt = ops.proj_bwd(dy_txt, xt, tw1b, tw2b, tg, saved_t, need_dxt)
+        grads = [gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], gt[1], gt[2], gt[3], gt[4], gt[5], gt[6], dfw, dfb]
+        if W > 1:
+            # DDP-style: average is NOT taken -- the losses are already normalised by the GLOBAL batch, so SUM is exact
+            flat = torch.cat([t.reshape(-1) for t in grads])
+            dist.all_reduce(flat, group=group)
+            out, o = [], 0
+            for t in grads:
+                out.append(flat[o:o + t.numel()].view_as(t))
+                o += t.numel()
+            grads = out
+        return (gi[0], gt[0], None, None, None, None, None, *grads)
+
+
+class ClipHead(nn.Module):
+    """ImageProjection + TextProjection + ClassificationAdapter with the fused step.  Sub-modules keep the reference's
+    state_dict keys (image_projector.*, text_projector.* as in the reference's `models` dict, 0426/train.py:888-928)."""
+
+    def __init__(self, image_embedding_size=MODEL_CONFIG["image_embedding_size"],
+                 text_embedding_size=MODEL_CONFIG["text_embedding_size"],
+                 shared_embedding_size=MODEL_CONFIG["shared_embedding_size"], num_labels=MODEL_CONFIG["num_labels"],
+                 tau_nce: float = MODEL_CONFIG["temperature"], tau_bce: float = 1.0, group=None):
+        super().__init__()
+        self.image_projector = ImageProjection(image_embedding_size, shared_embedding_size, dropout_rate=0.0)
+        self.text_projector = TextProjection(text_embedding_size, shared_embedding_size, dropout_rate=0.0)
+        self.classifier = ClassificationAdapter(shared_embedding_size, num_labels)
+        self.tau_nce, self.tau_bce, self.group = tau_nce, tau_bce, group
+
+    def params(self):
+        ip, tp, c = self.image_projector, self.text_projector, self.classifier
+        return (ip.image_projection.weight, ip.image_projection.bias, ip.fc.weight, ip.fc.bias, ip.layer_norm.weight,
+                ip.layer_norm.bias, tp.text_projection.weight, tp.text_projection.bias, tp.fc.weight, tp.fc.bias,
+                tp.layer_norm.weight, tp.layer_norm.bias, c.weight, c.bias)
+
+    def forward(self, image_embeddings, text_embeddings, class_text_features, labels):
+        """One head step on this rank's local pairs; returns the global loss
+        contrastive_loss(tau_nce) + multilabel_contrastive_loss(tau_bce) + BCEWithLogits(classifier)."""
+        return ClipHeadFn.apply(image_embeddings, text_embeddings, class_text_features, labels, self.tau_nce, self.tau_bce,
+                                self.group, *self.params())

@@ -1,0 +1,48 @@
+"""Loss / prediction functions with the reference's names and signatures."""
+from __future__ import annotations
+
+import logging
+
+import torch
+
+from . import ops
+from .modules import MODEL_CONFIG
+
+
+def contrastive_loss(image_features, text_features, temperature=1.0):
+    """0426/train.py:154-176.  image_features/text_features [B, D] L2-normalised (as at the only call site, :228)."""
+    if image_features.shape != text_features.shape:
+        # F.cross_entropy(logits[B,C], arange(B)) raises for C < B in the reference too
+        raise RuntimeError(f"contrastive_loss: logits must be square, got {tuple(image_features.shape)} x "
+                           f"{tuple(text_features.shape)}")
+    return ops.InfoNCEFn.apply(image_features, text_features, float(temperature))
+
+
+def multilabel_contrastive_loss(image_features, text_features, labels, temperature=1.0, strict_guard=False):
+    """0426/train.py:178-230.  The NaN/Inf/>1000 guard (:224) is evaluated on the device; with strict_guard=True the
+    flag is read back (one host sync, like the reference's two) and the reference's fallback is taken."""
+    num_classes = text_features.size(0)
+    if labels.size(1) != num_classes:                                     # :205-210 (kernel zero-pads)
+        logging.error(f"标签格式不正确: shape={labels.shape}, 期望shape=[{labels.size(0)}, {num_classes}]")
+        if labels.size(1) > num_classes:
+            raise RuntimeError("multilabel_contrastive_loss: more label columns than classes")
+    loss, status = ops.MultilabelContrastiveFn.apply(image_features, text_features, labels, float(temperature))
+    multilabel_contrastive_loss.last_status = status
+    if strict_guard and int(status.item()) != 0:
+        logging.error(f"多标签对比损失异常: {loss}")
+        return contrastive_loss(ops.normalize(image_features), ops.normalize(text_features), temperature)
+    return loss
+
+
+multilabel_contrastive_loss.last_status = None
+
+
+def fc_adapter_bce(x, weight, bias, labels):
+    """BCEWithLogitsLoss()(F.linear(x, weight, bias), labels) -- NB02 c29:23-25."""
+    return ops.FcBceFn.apply(x, weight, bias, labels)
+
+
+@torch.no_grad()
+def predict_multilabel(image_features, text_features, threshold=0.5):
+    """0426/train.py:869-886 (temperature bound from MODEL_CONFIG like the reference)."""
+    return ops.predict_multilabel_raw(image_features, text_features, threshold, MODEL_CONFIG["temperature"])

@@ -1,0 +1,81 @@
+"""nn.Module surface of the reference head, same constructor signatures and state_dict keys
+ so checkpoints written by the reference's save_checkpoint (0426/train.py:846-860) load.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+# 0426/config.py:19-37 (the values the reference binds at import time)
+MODEL_CONFIG = {
+    "temperature": 0.07,
+    "dropout_rate": 0.1,
+    "image_embedding_size": 2048,
+    "text_embedding_size": 768,
+    "shared_embedding_size": 512,
+    "num_labels": 16,
+}
+
+
+class _ProjectionBase(nn.Module):
+    """Linear(E,D) -> GELU -> Linear(D,D) -> Dropout -> +residual -> LayerNorm (0426/train.py:84-96)."""
+
+    _first = "proj"
+
+    def __init__(self, in_features: int, shared_embedding_size: int, dropout_rate: float = MODEL_CONFIG["dropout_rate"]):
+        super().__init__()
+        setattr(self, self._first, nn.Linear(in_features, shared_embedding_size))
+        self.gelu = nn.GELU()
+        self.fc = nn.Linear(shared_embedding_size, shared_embedding_size)
+        self.dropout = nn.Dropout(dropout_rate)
+        self.layer_norm = nn.LayerNorm(shared_embedding_size)
+
+    def forward(self, embeddings: torch.Tensor) -> torch.Tensor:
+        if embeddings.dim() > 2:                                   # 0426/train.py:86-88
+            embeddings = embeddings.reshape(embeddings.size(0), -1)
+        if self.training and self.dropout.p > 0:
+            raise RuntimeError(
+                "b200clip projection: train-mode dropout p>0 is not implemented by the fused kernels yet; call "
+                ".eval() or construct with dropout_rate=0 (parity with the reference is defined with dropout off)")
+        first = getattr(self, self._first)
+        return ops.ProjectionFn.apply(embeddings, first.weight, first.bias, self.fc.weight, self.fc.bias,
+                                      self.layer_norm.weight, self.layer_norm.bias)
+
+
+class ImageProjection(_ProjectionBase):
+    """Drop-in for 0426/train.py:73-96 (keys image_projection.*, fc.*, layer_norm.*)."""
+    _first = "image_projection"
+
+    def __init__(self, image_embedding_size, shared_embedding_size, dropout_rate: float = MODEL_CONFIG["dropout_rate"]):
+        super().__init__(image_embedding_size, shared_embedding_size, dropout_rate)
+
+
+class TextProjection(_ProjectionBase):
+    """Drop-in for 0426/train.py:98-116 (keys text_projection.*, fc.*, layer_norm.*)."""
+    _first = "text_projection"
+
+    def __init__(self, text_embedding_size, shared_embedding_size, dropout_rate: float = MODEL_CONFIG["dropout_rate"]):
+        super().__init__(text_embedding_size, shared_embedding_size, dropout_rate)
+
+
+class ClassificationAdapter(nn.Module):
+    """The "C-Adapter": nn.Linear(512,16) + BCEWithLogitsLoss (NB02 c28:50-52).  `forward` = logits (as nn.Linear),
+    `loss` = fused Linear+BCE, `predict` = sigmoid(logits) > threshold (NB02 c30:42-43).  state_dict keys weight/bias."""
+
+    def __init__(self, in_features: int = 512, num_labels: int = 16):
+        super().__init__()
+        lin = nn.Linear(in_features, num_labels)
+        self.weight = lin.weight
+        self.bias = lin.bias
+
+    def forward(self, x):
+        return ops.LinearSmallFn.apply(x, self.weight, self.bias)
+
+    def loss(self, x, labels):
+        return ops.FcBceFn.apply(x, self.weight, self.bias, labels)
+
+    @torch.no_grad()
+    def predict(self, x, threshold: float = 0.5):
+        return ops.fc_bce(x, self.weight, self.bias, None, want_pred=True, threshold=threshold)[4]

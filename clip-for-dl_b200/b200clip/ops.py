@@ -1,0 +1,473 @@
+"""Thin functional layer over the C ABI: tensor allocation + argument marshalling, and the autograd Functions
+that give the reference's modules/losses their backward passes.  PyTorch is used for device memory, streams
+and autograd bookkeeping only; all arithmetic happens in libb200clip.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, load, ptr, require_cuda, stream_ptr
+
+LN_EPS = 1e-5          # nn.LayerNorm default (0426/train.py:82)
+L2_EPS = 1e-12         # F.normalize default
+
+EPI_STORE_F32, EPI_STORE_BF16, EPI_BIAS_GELU, EPI_BIAS_RESID_F32, EPI_ATOMIC_F32, EPI_GELU_BWD, EPI_RELU_BF16 = range(7)
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 copy through b200clip_cast_f32_bf16 (bf16 inputs pass through)."""
+    require_cuda(x)
+    if x.dtype == torch.bfloat16:
+        return x.contiguous()
+    x = _f32c(x)
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    n = x.numel()
+    if n % 4 == 0:
+        check(load().b200clip_cast_f32_bf16(ptr(x), ptr(out), n, stream_ptr()), "cast_f32_bf16")
+    else:                                    # ragged tail: pad to a multiple of 4 in a scratch copy
+        pad = (-n) % 4
+        xin = torch.zeros(n + pad, dtype=torch.float32, device=x.device)
+        xin[:n] = x.reshape(-1)
+        o = torch.empty(n + pad, dtype=torch.bfloat16, device=x.device)
+        check(load().b200clip_cast_f32_bf16(ptr(xin), ptr(o), n + pad, stream_ptr()), "cast_f32_bf16")
+        out = o[:n].reshape(x.shape).contiguous()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# generic GEMM (tests + projection internals)
+# --------------------------------------------------------------------------------------------------------------
+def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, epilogue: int = EPI_STORE_F32,
+              alpha: float = 1.0, bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+              aux: Optional[torch.Tensor] = None, split_k: int = 1, out: Optional[torch.Tensor] = None):
+    require_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
+    a, b = a.contiguous(), b.contiguous()
+    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
+    N = b.shape[1] if b_mn else b.shape[0]
+    assert (b.shape[0] if b_mn else b.shape[1]) == K, "inner dimensions differ"
+    out1 = None
+    if epilogue in (EPI_STORE_F32, EPI_BIAS_RESID_F32, EPI_ATOMIC_F32):
+        if out is None:
+            out = (torch.zeros if epilogue == EPI_ATOMIC_F32 else torch.empty)((M, N), dtype=torch.float32, device=a.device)
+    else:
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+        if epilogue == EPI_BIAS_GELU:
+            out1 = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    rc = load().b200clip_gemm_bf16(ptr(a), ptr(b), int(a_mn), int(b_mn), M, N, K, a.shape[1], b.shape[1], epilogue, alpha,
+                                   ptr(out), N, ptr(out1), N, ptr(bias), ptr(resid), N, ptr(aux), N, split_k, stream_ptr())
+    check(rc, "gemm_bf16")
+    return (out, out1) if out1 is not None else out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a-L2
+# --------------------------------------------------------------------------------------------------------------
+def l2norm_fwd(x: torch.Tensor, want_bf16: bool = True, want_f32: bool = False, eps: float = L2_EPS):
+    require_cuda(x)
+    assert x.dim() == 2
+    if x.dtype != torch.bfloat16:
+        x = _f32c(x)
+    x = x.contiguous()
+    rows, D = x.shape
+    yb = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    yf = torch.empty((rows, D), dtype=torch.float32, device=x.device) if want_f32 else None
+    inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    check(load().b200clip_l2norm_fwd(ptr(x), int(x.dtype == torch.bfloat16), D, ptr(yb), ptr(yf), ptr(inv), rows, D, eps,
+                                     stream_ptr()), "l2norm_fwd")
+    return yb, yf, inv
+
+
+def l2norm_bwd(dy: torch.Tensor, x: torch.Tensor, inv: torch.Tensor, eps: float = L2_EPS, out: Optional[torch.Tensor] = None,
+               accumulate: bool = False) -> torch.Tensor:
+    dy = _f32c(dy)
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty((rows, D), dtype=torch.float32, device=x.device)
+    check(load().b200clip_l2norm_bwd(ptr(dy), ptr(x), int(x.dtype == torch.bfloat16), D, ptr(inv), ptr(out), int(accumulate),
+                                     rows, D, eps, stream_ptr()), "l2norm_bwd")
+    return out
+
+
+class L2NormalizeFn(torch.autograd.Function):
+    """F.normalize(x, dim=-1) on [rows, D] (0426/train.py:191-192)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xc = _f32c(x)
+        _, yf, inv = l2norm_fwd(xc, want_bf16=False, want_f32=True)
+        ctx.save_for_backward(xc, inv)
+        return yf
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, inv = ctx.saved_tensors
+        return l2norm_bwd(dy, xc, inv)
+
+
+def normalize(x: torch.Tensor, dim: int = -1) -> torch.Tensor:
+    if dim not in (-1, x.dim() - 1):
+        raise ValueError("b200clip.normalize: only the last dimension is supported")
+    shp = x.shape
+    return L2NormalizeFn.apply(x.reshape(-1, shp[-1])).reshape(shp)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a-P1 / a-P2 projection block
+# --------------------------------------------------------------------------------------------------------------
+def proj_fwd(x_bf16, w1_bf16, b1, w2_bf16, b2, gamma, beta, want_yhat: bool):
+    B, E = x_bf16.shape
+    D = w1_bf16.shape[0]
+    dev = x_bf16.device
+    p = torch.empty((B, D), dtype=torch.bfloat16, device=dev)
+    h = torch.empty((B, D), dtype=torch.bfloat16, device=dev)
+    z = torch.empty((B, D), dtype=torch.float32, device=dev)
+    y = torch.empty((B, D), dtype=torch.float32, device=dev)
+    mean = torch.empty((B,), dtype=torch.float32, device=dev)
+    rstd = torch.empty((B,), dtype=torch.float32, device=dev)
+    yhat = torch.empty((B, D), dtype=torch.bfloat16, device=dev) if want_yhat else None
+    inv = torch.empty((B,), dtype=torch.float32, device=dev) if want_yhat else None
+    check(load().b200clip_proj_fwd(ptr(x_bf16), B, E, D, ptr(w1_bf16), ptr(b1), ptr(w2_bf16), ptr(b2), ptr(gamma), ptr(beta),
+                                   LN_EPS, ptr(p), ptr(h), ptr(z), ptr(y), ptr(yhat), ptr(mean), ptr(rstd), ptr(inv),
+                                   stream_ptr()), "proj_fwd")
+    return y, yhat, inv, (p, h, z, mean, rstd)
+
+
+def proj_bwd(dy, x_bf16, w1_bf16, w2_bf16, gamma, saved, need_dx: bool):
+    p, h, z, mean, rstd = saved
+    B, E = x_bf16.shape
+    D = w1_bf16.shape[0]
+    dev = x_bf16.device
+    dy = _f32c(dy)
+    dx = torch.empty((B, E), dtype=torch.float32, device=dev) if need_dx else None
+    dw1 = torch.empty((D, E), dtype=torch.float32, device=dev)
+    dw2 = torch.empty((D, D), dtype=torch.float32, device=dev)
+    db1, db2, dg, dbeta = (torch.empty((D,), dtype=torch.float32, device=dev) for _ in range(4))
+    nb = load().b200clip_proj_bwd_workspace_bytes(B, E, D)
+    ws = _ws(nb, dev)
+    check(load().b200clip_proj_bwd(ptr(dy), ptr(x_bf16), B, E, D, ptr(w1_bf16), ptr(w2_bf16), ptr(gamma), ptr(p), ptr(h), ptr(z),
+                                   ptr(mean), ptr(rstd), ptr(dx), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dg), ptr(dbeta),
+                                   ptr(ws), ws.numel(), stream_ptr()), "proj_bwd")
+    return dx, dw1, db1, dw2, db2, dg, dbeta
+
+
+class ProjectionFn(torch.autograd.Function):
+    """ImageProjection/TextProjection forward+backward (0426/train.py:84-96) with dropout off."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, gamma, beta):
+        require_cuda(x, w1)
+        xb = cast_bf16(x)
+        w1b, w2b = cast_bf16(w1), cast_bf16(w2)
+        b1, b2, gamma, beta = _f32c(b1), _f32c(b2), _f32c(gamma), _f32c(beta)
+        y, _, _, saved = proj_fwd(xb, w1b, b1, w2b, b2, gamma, beta, want_yhat=False)
+        ctx.save_for_backward(xb, w1b, w2b, gamma, *saved)
+        ctx.need_dx = x.requires_grad
+        ctx.x_dtype = x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, w1b, w2b, gamma, p, h, z, mean, rstd = ctx.saved_tensors
+        dx, dw1, db1, dw2, db2, dg, dbeta = proj_bwd(dy, xb, w1b, w2b, gamma, (p, h, z, mean, rstd), ctx.need_dx)
+        if dx is not None and ctx.x_dtype != torch.float32:
+            dx = dx.to(ctx.x_dtype)
+        return dx, dw1, db1, dw2, db2, dg, dbeta
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a-N symmetric InfoNCE
+# --------------------------------------------------------------------------------------------------------------
+def infonce_forward(i_hat: torch.Tensor, t_hat: torch.Tensor, temperature: float, row0: int = 0, group=None):
+    """i_hat: local rows [b_loc, D] bf16; t_hat: all rows [b_glob, D] bf16.  Returns (loss, rinvh, cinvh)."""
+    lib = load()
+    b_loc, D = i_hat.shape
+    b_glob = t_hat.shape[0]
+    dev = i_hat.device
+    nb = lib.b200clip_infonce_workspace_bytes(b_loc, b_glob)
+    ws = _ws(nb, dev)
+    r = torch.empty((b_loc,), dtype=torch.float32, device=dev)
+    c = torch.empty((b_glob,), dtype=torch.float32, device=dev)
+    check(lib.b200clip_infonce_fwd_stats(ptr(i_hat), ptr(t_hat), D, b_loc, b_glob, temperature, ptr(r), ptr(c), ptr(ws),
+                                         ws.numel(), stream_ptr()), "infonce_fwd_stats")
+    world = 1
+    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized() and b_loc != b_glob):
+        world = torch.distributed.get_world_size(group)
+    if world > 1:
+        torch.distributed.all_reduce(c, group=group)          # partial column sums -> global
+    rinvh = torch.empty_like(r)
+    cinvh = torch.empty_like(c)
+    sums = torch.empty((3,), dtype=torch.float64, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    c_lo, c_hi = (row0, row0 + b_loc) if world > 1 else (0, b_glob)
+    check(lib.b200clip_infonce_loss(ptr(i_hat), ptr(t_hat), D, b_loc, b_glob, row0, temperature, ptr(r), ptr(c), c_lo, c_hi,
+                                    ptr(rinvh), ptr(cinvh), ptr(sums), ptr(loss) if world == 1 else None, ptr(ws), ws.numel(),
+                                    stream_ptr()), "infonce_loss")
+    if world > 1:
+        torch.distributed.all_reduce(sums, group=group)
+        loss = (1.0 / temperature + (sums[0] + sums[1]) / (2.0 * b_glob) - sums[2] / b_glob).to(torch.float32)
+    return loss, rinvh, cinvh
+
+
+def infonce_backward(i_hat, t_hat, temperature, rinvh, cinvh, grad_scale: Optional[torch.Tensor], row0: int = 0):
+    """Returns d_i [b_loc, D] f32 and d_t_partial [b_glob, D] f32 (this rank's contribution)."""
+    b_loc, D = i_hat.shape
+    b_glob = t_hat.shape[0]
+    dev = i_hat.device
+    d_i = torch.empty((b_loc, D), dtype=torch.float32, device=dev)
+    d_t = torch.empty((b_glob, D), dtype=torch.float32, device=dev)
+    gs = None
+    if grad_scale is not None:
+        gs = _f32c(grad_scale.reshape(()))
+    check(load().b200clip_infonce_bwd(ptr(i_hat), ptr(t_hat), D, b_loc, b_glob, row0, temperature, ptr(rinvh), ptr(cinvh),
+                                      ptr(gs), ptr(d_i), ptr(d_t), stream_ptr()), "infonce_bwd")
+    return d_i, d_t
+
+
+class InfoNCEFn(torch.autograd.Function):
+    """contrastive_loss(image_features, text_features, temperature) -- 0426/train.py:154-176, single device.
+    Inputs must be L2-normalised (the only call sites pass F.normalize outputs); they are rounded to bf16."""
+
+    @staticmethod
+    def forward(ctx, image_features, text_features, temperature):
+        require_cuda(image_features, text_features)
+        ib, tb = cast_bf16(image_features), cast_bf16(text_features)
+        loss, rinvh, cinvh = infonce_forward(ib, tb, float(temperature))
+        ctx.save_for_backward(ib, tb, rinvh, cinvh)
+        ctx.temperature = float(temperature)
+        ctx.dtypes = (image_features.dtype, text_features.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ib, tb, rinvh, cinvh = ctx.saved_tensors
+        d_i, d_t = infonce_backward(ib, tb, ctx.temperature, rinvh, cinvh, grad_out)
+        return d_i.to(ctx.dtypes[0]), d_t.to(ctx.dtypes[1]), None
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a-B multi-label BCE on sigmoid(cos/tau)
+# --------------------------------------------------------------------------------------------------------------
+def _label_sum(labels: torch.Tensor) -> torch.Tensor:
+    out = torch.empty((), dtype=torch.float32, device=labels.device)
+    check(load().b200clip_sum_f32(ptr(labels), labels.numel(), ptr(out), stream_ptr()), "sum_f32")
+    return out
+
+
+def mlbce(image_features, text_features, labels, temperature, *, grad_scale=None, want_dx=False, want_coef=False,
+          label_sum=None, total_elems=None, finalize=True, dx_accum: Optional[torch.Tensor] = None):
+    lib = load()
+    x = _f32c(image_features)
+    t = _f32c(text_features)
+    y = _f32c(labels)
+    B, D = x.shape
+    Cn = t.shape[0]
+    dev = x.device
+    if label_sum is None:
+        label_sum = _label_sum(y)
+    if total_elems is None:
+        total_elems = float(B) * Cn
+    dx = dx_accum if dx_accum is not None else (torch.empty((B, D), dtype=torch.float32, device=dev) if want_dx else None)
+    coef = torch.empty((B, Cn), dtype=torch.float32, device=dev) if want_coef else None
+    xinv = torch.empty((B,), dtype=torch.float32, device=dev) if want_coef else None
+    sums = torch.empty((2,), dtype=torch.float64, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev) if finalize else None
+    status = torch.zeros((), dtype=torch.int32, device=dev) if finalize else None
+    ws = _ws(lib.b200clip_smallc_workspace_bytes(B, Cn, D), dev)
+    gs = _f32c(grad_scale.reshape(())) if grad_scale is not None else None
+    check(lib.b200clip_mlbce_fwd_bwd(ptr(x), D, ptr(t), ptr(y), y.shape[1], y.shape[1], B, Cn, D, float(temperature),
+                                     ptr(label_sum), float(total_elems), ptr(gs), ptr(dx), int(dx_accum is not None), ptr(coef), ptr(xinv), ptr(sums),
+                                     ptr(loss), ptr(status), ptr(ws), ws.numel(), stream_ptr()), "mlbce_fwd_bwd")
+    return loss, status, sums, dx, coef, xinv, label_sum
+
+
+def skinny_outer(coef, x, row_scale=None, want_bias=False):
+    lib = load()
+    B, Cn = coef.shape
+    D = x.shape[1]
+    dev = x.device
+    out_w = torch.empty((Cn, D), dtype=torch.float32, device=dev)
+    out_b = torch.empty((Cn,), dtype=torch.float32, device=dev) if want_bias else None
+    ws = _ws(lib.b200clip_smallc_workspace_bytes(B, Cn, D), dev)
+    check(lib.b200clip_skinny_outer(ptr(coef), Cn, ptr(x), x.stride(0), ptr(row_scale), B, D, ptr(out_w), ptr(out_b), 0, ptr(ws),
+                                    ws.numel(), stream_ptr()), "skinny_outer")
+    return out_w, out_b
+
+
+class MultilabelContrastiveFn(torch.autograd.Function):
+    """multilabel_contrastive_loss (0426/train.py:178-230), non-fallback branch; the guard flag is returned."""
+
+    @staticmethod
+    def forward(ctx, image_features, text_features, labels, temperature):
+        require_cuda(image_features, text_features, labels)
+        loss, status, _, _, _, _, lsum = mlbce(image_features, text_features, labels, temperature)
+        ctx.save_for_backward(image_features, text_features, labels, lsum)
+        ctx.temperature = float(temperature)
+        ctx.mark_non_differentiable(status)
+        return loss, status
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_status):
+        image_features, text_features, labels, lsum = ctx.saved_tensors
+        need_t = ctx.needs_input_grad[1]
+        _, _, _, dx, coef, xinv, _ = mlbce(image_features, text_features, labels, ctx.temperature, grad_scale=grad_out,
+                                           want_dx=ctx.needs_input_grad[0], want_coef=need_t, label_sum=lsum)
+        dt = None
+        if need_t:
+            # d t_hat[c] = sum_i coef[i,c] * x_hat[i] / tau, then back through the text normalisation
+            x = _f32c(image_features)
+            t = _f32c(text_features)
+            dth, _ = skinny_outer(coef, x, row_scale=xinv)
+            dth = dth * (1.0 / ctx.temperature)
+            _, _, tinv = l2norm_fwd(t, want_bf16=False, want_f32=False)
+            dt = l2norm_bwd(dth, t, tinv).to(text_features.dtype)
+        if dx is not None:
+            dx = dx.to(image_features.dtype)
+        return dx, dt, None, None
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a-A FC adapter + BCEWithLogits
+# --------------------------------------------------------------------------------------------------------------
+def fc_bce(x, weight, bias, labels=None, *, grad_scale=None, want_dx=False, want_coef=False, want_pred=False,
+           want_logits=False, total_elems=None, threshold=0.5, finalize=True, dx_accum: Optional[torch.Tensor] = None):
+    lib = load()
+    x, weight = _f32c(x), _f32c(weight)
+    bias = _f32c(bias) if bias is not None else None
+    B, D = x.shape
+    Cn = weight.shape[0]
+    dev = x.device
+    y = _f32c(labels) if labels is not None else torch.zeros((B, Cn), dtype=torch.float32, device=dev)
+    if total_elems is None:
+        total_elems = float(B) * Cn
+    dx = dx_accum if dx_accum is not None else (torch.empty((B, D), dtype=torch.float32, device=dev) if want_dx else None)
+    coef = torch.empty((B, Cn), dtype=torch.float32, device=dev) if want_coef else None
+    pred = torch.empty((B, Cn), dtype=torch.float32, device=dev) if want_pred else None
+    logits = torch.empty((B, Cn), dtype=torch.float32, device=dev) if want_logits else None
+    sums = torch.empty((2,), dtype=torch.float64, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev) if finalize else None
+    ws = _ws(lib.b200clip_smallc_workspace_bytes(B, Cn, D), dev)
+    gs = _f32c(grad_scale.reshape(())) if grad_scale is not None else None
+    check(lib.b200clip_fc_bce_fwd_bwd(ptr(x), x.stride(0), ptr(weight), ptr(bias), ptr(y), y.stride(0), B, Cn, D,
+                                      float(total_elems), float(threshold), ptr(gs), ptr(dx), int(dx_accum is not None), ptr(coef), ptr(pred),
+                                      ptr(logits), ptr(sums), ptr(loss), ptr(ws), ws.numel(), stream_ptr()), "fc_bce_fwd_bwd")
+    return loss, sums, dx, coef, pred, logits
+
+
+class FcBceFn(torch.autograd.Function):
+    """BCEWithLogitsLoss()(Linear(512,16)(x), labels) fused (NB02 c28:50-52, c29:23-25)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, labels):
+        require_cuda(x, weight, labels)
+        loss, *_ = fc_bce(x, weight, bias, labels)
+        ctx.save_for_backward(x, weight, bias, labels)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, weight, bias, labels = ctx.saved_tensors
+        _, _, dx, coef, _, _ = fc_bce(x, weight, bias, labels, grad_scale=grad_out, want_dx=ctx.needs_input_grad[0],
+                                      want_coef=True)
+        dw, db = skinny_outer(coef, _f32c(x), want_bias=True)
+        return dx, dw.to(weight.dtype), (db.to(bias.dtype) if bias is not None else None), None
+
+
+class LinearSmallFn(torch.autograd.Function):
+    """nn.Linear(D, C<=32) forward (logits) with backward -- the adapter used stand-alone (NB02 c30:42)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        require_cuda(x, weight)
+        *_, logits = fc_bce(x, weight, bias, None, want_logits=True)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return logits
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, weight = ctx.saved_tensors
+        dz = _f32c(dz)
+        dw, db = skinny_outer(dz, _f32c(x), want_bias=True)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("b200clip: input gradient of the stand-alone adapter Linear is not implemented; "
+                               "use fc_adapter_bce (fused) or freeze the encoder as NB02 c28:54-62 does")
+        return dx, dw, (db if ctx.has_bias else None)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a-M
+# --------------------------------------------------------------------------------------------------------------
+def predict_multilabel_raw(image_features, text_features, threshold: float, temperature: float) -> torch.Tensor:
+    require_cuda(image_features, text_features)
+    x, t = _f32c(image_features), _f32c(text_features)
+    B, D = x.shape
+    Cn = t.shape[0]
+    pred = torch.empty((B, Cn), dtype=torch.float32, device=x.device)
+    check(load().b200clip_predict_multilabel(ptr(x), x.stride(0), ptr(t), B, Cn, D, float(temperature), float(threshold),
+                                             ptr(pred), stream_ptr()), "predict_multilabel")
+    return pred
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a-Z
+# --------------------------------------------------------------------------------------------------------------
+def _logit(p: float) -> float:
+    if p <= 0.0:
+        return -math.inf
+    if p >= 1.0:
+        return math.inf
+    return math.log(p / (1.0 - p))
+
+
+def zeroshot_score(x_bf16: torch.Tensor, prompts_bf16: torch.Tensor, *, pair_mode: bool, temperature: float,
+                   thresholds: Optional[Sequence[float]] = None, thr_inclusive: bool = False, normalize_x: bool = True,
+                   topk: int = 0, value_mode: int = 0, want_argmax: bool = True, want_mask: bool = True,
+                   want_scores: bool = False, guard: Optional[float] = None, count_guard: bool = False):
+    """Scores N embeddings against <=32 prompts.  thresholds are PROBABILITY thresholds (one per label or a scalar
+    list); a label passes when sigmoid(score) (>|>=) thr, evaluated exactly as score (>|>=) logit(thr)."""
+    require_cuda(x_bf16, prompts_bf16)
+    assert x_bf16.dtype == torch.bfloat16 and prompts_bf16.dtype == torch.bfloat16
+    x_bf16, prompts_bf16 = x_bf16.contiguous(), prompts_bf16.contiguous()
+    n, D = x_bf16.shape
+    np_ = prompts_bf16.shape[0]
+    L = np_ // 2 if pair_mode else np_
+    dev = x_bf16.device
+    if guard is None:
+        guard = 1e-4 / temperature
+    thr_arr = None
+    if want_mask:
+        if thresholds is None:
+            thresholds = [0.5] * L
+        thresholds = list(thresholds)
+        if len(thresholds) == 1:
+            thresholds = thresholds * L
+        assert len(thresholds) == L
+        thr_arr = (C.c_float * L)(*[_logit(float(t)) for t in thresholds])
+    argmax = torch.empty((n,), dtype=torch.uint8, device=dev) if want_argmax else None
+    mask_u32 = L > 16
+    mask = torch.empty((n,), dtype=torch.int32 if mask_u32 else torch.int16, device=dev) if want_mask else None
+    tk_idx = torch.empty((n, topk), dtype=torch.uint8, device=dev) if topk > 0 else None
+    tk_val = torch.empty((n, topk), dtype=torch.float32, device=dev) if topk > 0 else None
+    scores = torch.empty((n, L), dtype=torch.float32, device=dev) if want_scores else None
+    gcount = torch.zeros((1,), dtype=torch.int64, device=dev) if count_guard else None
+    check(load().b200clip_zeroshot_score(ptr(x_bf16), D, n, ptr(prompts_bf16), np_, D, int(pair_mode), int(normalize_x),
+                                         float(temperature), thr_arr, int(thr_inclusive), float(guard), topk, value_mode,
+                                         ptr(argmax), ptr(mask), int(mask_u32), ptr(tk_idx), ptr(tk_val), ptr(scores),
+                                         ptr(gcount), stream_ptr()), "zeroshot_score")
+    return {"argmax": argmax, "mask": mask, "topk_idx": tk_idx, "topk_val": tk_val, "scores": scores, "guard_rows": gcount}

@@ -1,0 +1,78 @@
+"""Zero-shot scoring cores.  The reference's predict_zero_shot (0426/disease_analysis.py:291-364)
+runs encoders, then scores; these functions replace everything after the projector (normalise, similarities,
+softmax/sigmoid, top-k / threshold) and return tensors instead of per-row python lists."""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Union
+
+import torch
+
+from . import ops
+from .modules import MODEL_CONFIG
+
+
+def _prep(image_features, text_features):
+    x = ops.cast_bf16(image_features.reshape(image_features.shape[0], -1))
+    p = ops.cast_bf16(text_features.reshape(-1, text_features.shape[-1]))
+    return x, p
+
+
+@torch.no_grad()
+def zero_shot_topk(image_features, text_features, top_k: int = 3, temperature: float = MODEL_CONFIG["temperature"]):
+    """Z1: softmax(normalize(I) T^T / tau).topk(k) -- 0426/disease_analysis.py:332-351.  Returns (idx uint8 [N,k], prob)."""
+    x, p = _prep(image_features, text_features)
+    k = min(top_k, p.shape[0])
+    out = ops.zeroshot_score(x, p, pair_mode=False, temperature=temperature, topk=k, value_mode=1, want_mask=False)
+    return out["topk_idx"], out["topk_val"]
+
+
+@torch.no_grad()
+def zero_shot_threshold(image_features, text_features, threshold: Union[float, Sequence[float]] = 0.5,
+                        temperature: float = 0.5, inclusive: bool = True):
+    """Z2: sigmoid(normalize(I) T^T / 0.5) >= thr (scalar or per-class) -- multimodal_attention/disease_analysis.py:350-378.
+    Returns (mask bits [N] int, argmax uint8 [N])."""
+    x, p = _prep(image_features, text_features)
+    thr = [float(threshold)] if isinstance(threshold, (int, float)) else [float(t) for t in threshold]
+    out = ops.zeroshot_score(x, p, pair_mode=False, temperature=temperature, thresholds=thr, thr_inclusive=inclusive)
+    return out["mask"], out["argmax"]
+
+
+@torch.no_grad()
+def zero_shot_posneg(image_features, prompts, temperature: float = MODEL_CONFIG["temperature"], threshold: float = 0.5):
+    """north-star shape: prompts [L,2,D] (positive, negative), q_l = softmax([l+, l-])[0]; returns
+    (argmax uint8 [N], mask int16 [N] with bit l = q_l > thr)."""
+    L = prompts.shape[0]
+    x, p = _prep(image_features, prompts.reshape(2 * L, -1))
+    out = ops.zeroshot_score(x, p, pair_mode=True, temperature=temperature, thresholds=[threshold])
+    return out["argmax"], out["mask"]
+
+
+def unpack_mask(mask: torch.Tensor, num_labels: int) -> torch.Tensor:
+    """bit-packed label set -> bool [N, L]"""
+    bits = torch.arange(num_labels, device=mask.device, dtype=torch.int32)
+    return ((mask.to(torch.int32).unsqueeze(-1) >> bits) & 1).bool()
+
+
+@torch.no_grad()
+def predict_zero_shot(images, models: Dict, disease_list: List[str], top_k: int = 3, prompts=None,
+                      use_enhanced_prompts: bool = False, text_features: torch.Tensor = None):
+    """Drop-in for 0426/disease_analysis.py:291-364.  Encoders stay stock PyTorch (models['resnet']); the projector and
+    everything after it run on the B200 kernels.  `text_features` [C,D] (normalised) replaces the reference's
+    per-call BERT pass (get_prediction_text_features, :335-340) when given; otherwise models['text_features'] is used."""
+    for m in models.values():
+        if hasattr(m, "eval"):
+            m.eval()
+    is_batch = isinstance(images, torch.Tensor) and images.dim() == 4
+    if not is_batch:
+        if isinstance(images, list):
+            images = images[0]
+        images = images.unsqueeze(0)
+    dev = next(models["image_projector"].parameters()).device
+    emb = models["resnet"](images.to(dev))
+    feats = models["image_projector"](emb.reshape(emb.size(0), -1))
+    tf = text_features if text_features is not None else models["text_features"]
+    idx, val = zero_shot_topk(feats, tf, top_k)
+    idx_c, val_c = idx.cpu().numpy(), val.cpu().numpy()            # one D2H for the batch (reference: one per row)
+    if is_batch:
+        return [[disease_list[j] for j in row] for row in idx_c], [row for row in val_c]
+    return [{"disease": disease_list[j], "confidence": float(s)} for j, s in zip(idx_c[0], val_c[0])]

@@ -1,0 +1,82 @@
+// b200clip: C-ABI entry point for the tcgen05 GEMM (used by the projection block and by the parity tests).
+#include "gemm.cuh"
+#include "host.cuh"
+#include "../../include/b200clip.h"
+
+namespace b200 {
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits,
+                       cudaStream_t stream) {
+  auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN, EPI>;
+  constexpr int smem = gemm_smem_bytes<BN, STAGES>();
+  static bool configured = false;   // per-instantiation; idempotent, so a benign race
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((p.M + GEMM_BM - 1) / GEMM_BM, (p.N + BN - 1) / BN, splits);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, int K, long long lda, long long ldb,
+              int epi, float alpha, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
+              const void* resid, long long ld_res, const float* aux, long long ld_aux, int split_k,
+              cudaStream_t stream) {
+  B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  B200_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
+  B200_REQUIRE(out0 != nullptr && aligned16(out0), "gemm: out0 must be non-null and 16-byte aligned");
+  B200_REQUIRE(ld0 % 8 == 0, "gemm: ld0 must be a multiple of 8 elements");
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.k_chunks = (K + GEMM_BK - 1) / GEMM_BK;
+  if (split_k < 1) split_k = 1;
+  if (split_k > p.k_chunks) split_k = p.k_chunks;
+  B200_REQUIRE(split_k == 1 || epi == EPI_ATOMIC_F32, "gemm: split-K needs the atomic epilogue");
+  p.k_chunks_per_split = (p.k_chunks + split_k - 1) / split_k;
+  const int splits = (p.k_chunks + p.k_chunks_per_split - 1) / p.k_chunks_per_split;
+  p.alpha = alpha;
+  p.out0 = out0; p.ld0 = ld0; p.out1 = out1; p.ld1 = ld1; p.bias = bias;
+  p.resid = reinterpret_cast<const __nv_bfloat16*>(resid); p.ld_res = ld_res; p.aux = aux; p.ld_aux = ld_aux;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = make_tmap_bf16_2d(&ta, a, M, K, lda, 64, GEMM_BM);       // a[M][K], box 128 rows x 64 k
+  else       rc = make_tmap_bf16_2d(&ta, a, K, M, lda, 64, 64);            // a[K][M], box 64 k-rows x 64 m
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap_bf16_2d(&tb, b, N, K, ldb, 64, BN);            // b[N][K]
+  else       rc = make_tmap_bf16_2d(&tb, b, K, N, ldb, 64, 64);            // b[K][N]
+  if (rc) return rc;
+
+#define B200_GEMM_CASE(AMN, BMN, E)                                                                     \
+  if (a_mn == AMN && b_mn == BMN && epi == E) {                                                         \
+    return BN == 256 ? launch_gemm<256, 4, AMN, BMN, E>(ta, tb, p, splits, stream)                      \
+                     : launch_gemm<128, 6, AMN, BMN, E>(ta, tb, p, splits, stream);                     \
+  }
+  B200_GEMM_CASE(0, 0, EPI_STORE_F32)
+  B200_GEMM_CASE(0, 0, EPI_STORE_BF16)
+  B200_GEMM_CASE(0, 0, EPI_BIAS_GELU)
+  B200_GEMM_CASE(0, 0, EPI_BIAS_RESID_F32)
+  B200_GEMM_CASE(0, 0, EPI_RELU_BF16)
+  B200_GEMM_CASE(0, 1, EPI_STORE_F32)
+  B200_GEMM_CASE(0, 1, EPI_STORE_BF16)
+  B200_GEMM_CASE(0, 1, EPI_GELU_BWD)
+  B200_GEMM_CASE(1, 1, EPI_STORE_F32)
+  B200_GEMM_CASE(1, 1, EPI_ATOMIC_F32)
+  B200_GEMM_CASE(1, 0, EPI_STORE_F32)
+#undef B200_GEMM_CASE
+  return fail(B200_ERR_UNSUPPORTED, "gemm: no kernel for a_mn=%d b_mn=%d epilogue=%d", a_mn, b_mn, epi);
+}
+
+}  // namespace b200
+
+extern "C" int b200clip_gemm_bf16(const void* a, const void* b, int a_mn_major, int b_mn_major, int M, int N, int K,
+                                  long long lda, long long ldb, int epilogue, float alpha, void* out0, long long ld0,
+                                  void* out1, long long ld1, const float* bias, const void* resid, long long ld_res,
+                                  const float* aux, long long ld_aux, int split_k, void* stream) {
+  return b200::gemm_bf16(a, b, a_mn_major, b_mn_major, M, N, K, lda, ldb, epilogue, alpha, out0, ld0, out1, ld1, bias,
+                         resid, ld_res, aux, ld_aux, split_k, static_cast<cudaStream_t>(stream));
+}

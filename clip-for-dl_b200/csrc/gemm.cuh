@@ -1,0 +1,242 @@
+// b200clip: tcgen05/TMEM GEMM with TMA-fed 128B-swizzled smem tiles and fused epilogues.
+//   D[M,N] = A * B  with bf16 operands, fp32 accumulation in TMEM.
+// Operand storage (row-major global matrices, bf16):
+//   A K-major : a[M][K]   (rows of A are contiguous in K)       A MN-major: a[K][M]  (i.e. A^T stored)
+//   B K-major : b[N][K]   ("NT" GEMM, y = x W^T)                B MN-major: b[K][N]  ("NN" GEMM, y = x W)
+// One CTA computes one 128 x BN output tile over a K range (split-K via gridDim.z).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (one elected thread), 2 = TMEM allocator, 4..7 = epilogue
+// (warp_idx % 4 selects the TMEM lane quadrant a warp may read).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+enum GemmEpilogue : int {
+  EPI_STORE_F32 = 0,        // out0 f32 [M,N]           = alpha * acc (+ bias[n])
+  EPI_STORE_BF16 = 1,       // out0 bf16 [M,N]          = alpha * acc (+ bias[n])
+  EPI_BIAS_GELU = 2,        // out0 bf16 = p = acc + bias ; out1 bf16 = gelu_erf(p)
+  EPI_BIAS_RESID_F32 = 3,   // out0 f32  = acc + bias + resid(bf16)
+  EPI_ATOMIC_F32 = 4,       // atomicAdd(out0 f32, alpha * acc)       (split-K reduction)
+  EPI_GELU_BWD = 5,         // out0 bf16 = acc * gelu'(resid=p bf16) + aux(f32 [M,N])   (dp = dh*gelu'(p) + dz)
+  EPI_RELU_BF16 = 6,        // out0 bf16 = relu(acc + bias)
+};
+
+struct GemmParams {
+  int M, N, K;              // logical problem size
+  int k_chunks;             // ceil(K / 64)
+  int k_chunks_per_split;   // chunks handled by one blockIdx.z
+  float alpha;
+  void* out0;  long long ld0;
+  void* out1;  long long ld1;
+  const float* bias;        // [N] or nullptr
+  const __nv_bfloat16* resid; long long ld_res;
+  const float* aux;         long long ld_aux;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+constexpr int gemm_stage_bytes() { return GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2; }
+template <int BN, int STAGES>
+constexpr int gemm_smem_bytes() { return STAGES * gemm_stage_bytes<BN>() + 1024 /*align*/ + 256 /*barriers*/; }
+
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad_f(float x) {
+  // d/dx [x * Phi(x)] = Phi(x) + x * phi(x)
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-B alignment for the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  constexpr int B_BYTES = BN * GEMM_BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * GEMM_BM;
+  const int n0 = blockIdx.y * BN;
+  const int kc0 = blockIdx.z * p.k_chunks_per_split;
+  const int kc1 = min(p.k_chunks, kc0 + p.k_chunks_per_split);
+  const int nk = kc1 - kc0;                        // >= 1 guaranteed by the host
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        const int k0 = (kc0 + i) * GEMM_BK;
+        if constexpr (!A_MN) {
+          tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0);                      // box {64 k, 128 m}
+        } else {
+#pragma unroll
+          for (int g = 0; g < GEMM_BM / 64; ++g)                                // box {64 m, 64 k}
+            tma_load_2d(sa + g * 8192, &tmap_a, &full_bar[s], m0 + g * 64, k0);
+        }
+        if constexpr (!B_MN) {
+          tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n0);                      // box {64 k, BN n}
+        } else {
+#pragma unroll
+          for (int g = 0; g < BN / 64; ++g)                                     // box {64 n, 64 k}
+            tma_load_2d(sb + g * 8192, &tmap_b, &full_bar[s], n0 + g * 64, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int j = 0; j < GEMM_BK / 16; ++j) {
+          const uint64_t da = A_MN ? desc_mnmajor_sw128(sa + j * 2048, 8192) : desc_kmajor_sw128(sa + j * 32);
+          const uint64_t db = B_MN ? desc_mnmajor_sw128(sb + j * 2048, 8192) : desc_kmajor_sw128(sb + j * 32);
+          mma_ss(tmem_base, da, db, idesc, (i | j) ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);                     // frees the smem stage once these MMAs have read it
+      }
+      tc_commit(accum_bar);                           // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;                           // TMEM lane quadrant of this warp
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const bool row_ok = row < p.M;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t v[32];
+      tmem_ld_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
+      tmem_ld_wait();
+      const int col = n0 + c;
+      if (!row_ok || col >= p.N) continue;            // N is a multiple of 32 (host-checked)
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col + i);
+          f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+        }
+      }
+      if constexpr (EPI == EPI_STORE_F32) {
+        float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+      } else if constexpr (EPI == EPI_ATOMIC_F32) {
+        float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(o + i, f[i]);
+      } else if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_RELU_BF16) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
+        if constexpr (EPI == EPI_RELU_BF16) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+          *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf16x2(f[i], f[i + 1]), pack_bf16x2(f[i + 2], f[i + 3]),
+                                                        pack_bf16x2(f[i + 4], f[i + 5]), pack_bf16x2(f[i + 6], f[i + 7]));
+      } else if constexpr (EPI == EPI_BIAS_GELU) {
+        __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
+        __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(p.out1) + static_cast<long long>(row) * p.ld1 + col;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          *reinterpret_cast<uint4*>(o0 + i) = make_uint4(pack_bf16x2(f[i], f[i + 1]), pack_bf16x2(f[i + 2], f[i + 3]),
+                                                         pack_bf16x2(f[i + 4], f[i + 5]), pack_bf16x2(f[i + 6], f[i + 7]));
+          float g[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            // GELU is applied to the bf16-rounded p so that backward (which only sees the stored p) is consistent
+            const float pr = __bfloat162float(__float2bfloat16_rn(f[i + t]));
+            g[t] = gelu_erf_f(pr);
+          }
+          *reinterpret_cast<uint4*>(o1 + i) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
+                                                         pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+        }
+      } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
+        const __nv_bfloat16* rs = p.resid + static_cast<long long>(row) * p.ld_res + col;
+        float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          const uint4 r4 = *reinterpret_cast<const uint4*>(rs + i);
+          f[i] += bf16_lo(r4.x); f[i + 1] += bf16_hi(r4.x); f[i + 2] += bf16_lo(r4.y); f[i + 3] += bf16_hi(r4.y);
+          f[i + 4] += bf16_lo(r4.z); f[i + 5] += bf16_hi(r4.z); f[i + 6] += bf16_lo(r4.w); f[i + 7] += bf16_hi(r4.w);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+      } else if constexpr (EPI == EPI_GELU_BWD) {
+        const __nv_bfloat16* rs = p.resid + static_cast<long long>(row) * p.ld_res + col;
+        const float* ax = p.aux + static_cast<long long>(row) * p.ld_aux + col;
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          const uint4 r4 = *reinterpret_cast<const uint4*>(rs + i);
+          const float pv[8] = {bf16_lo(r4.x), bf16_hi(r4.x), bf16_lo(r4.y), bf16_hi(r4.y),
+                               bf16_lo(r4.z), bf16_hi(r4.z), bf16_lo(r4.w), bf16_hi(r4.w)};
+          const float4 a0 = *reinterpret_cast<const float4*>(ax + i);
+          const float4 a1 = *reinterpret_cast<const float4*>(ax + i + 4);
+          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          float g[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) g[t] = f[i + t] * gelu_erf_grad_f(pv[t]) + av[t];
+          *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
+                                                        pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, BN);
+}
+
+}  // namespace b200

@@ -1,0 +1,100 @@
+// b200clip: host-side helpers shared by the C-ABI translation units (error reporting, TMA descriptor encoding).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <string>
+
+namespace b200 {
+
+// error codes returned across the C ABI (0 = ok)
+enum : int {
+  B200_OK = 0,
+  B200_ERR_INVALID = -1,     // shape / alignment / dtype contract violated (rejected before any launch)
+  B200_ERR_CUDA = -2,        // a CUDA runtime/driver call failed
+  B200_ERR_WORKSPACE = -3,   // caller's workspace is too small
+  B200_ERR_UNSUPPORTED = -4, // valid request the kernels do not cover (never a silent fallback)
+};
+
+inline std::string& last_error() {
+  static thread_local std::string s;
+  return s;
+}
+inline int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+inline int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+#define B200_CHECK_CUDA(expr)                                                                    \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return ::b200::fail(::b200::B200_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+#define B200_REQUIRE(cond, ...)                                            \
+  do {                                                                     \
+    if (!(cond)) return ::b200::fail(::b200::B200_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+#define B200_LAUNCH_CHECK() B200_CHECK_CUDA(cudaGetLastError())
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// cuTensorMapEncodeTiled is fetched through the runtime so the library has no link-time dependency on libcuda
+// (it must load on a CPU-only box for the symbol-export test).
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major matrix [rows x cols] with row pitch `ld` elements; box = [box_rows x box_cols], 128B swizzle
+// (box_cols * 2 bytes must be <= 128). Out-of-bounds elements read as zero.
+inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                             uint32_t box_cols, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+  if (!aligned16(base)) return fail(B200_ERR_INVALID, "TMA base pointer must be 16-byte aligned");
+  if ((ld * 2) % 16 != 0) return fail(B200_ERR_INVALID, "TMA row pitch (%llu elems) must be a multiple of 8", (unsigned long long)ld);
+  if (box_cols * 2 > 128 || box_rows > 256) return fail(B200_ERR_INVALID, "TMA box too large");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return B200_OK;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace b200

@@ -1,0 +1,375 @@
+// b200clip: HBM-bound row kernels of the CLIP head -- L2 normalisation (a-L2), LayerNorm (tail of a-P1/a-P2),
+// column sums for bias gradients, casts.  One warp owns one row: 128-bit coalesced loads, fp32 statistics,
+// warp-shuffle reductions.  Roofline: HBM bandwidth (bytes listed per kernel).
+#include "common.cuh"
+#include "host.cuh"
+#include "../../include/b200clip.h"
+
+namespace b200 {
+
+constexpr int ROW_THREADS = 256;          // 8 warps = 8 rows per block pass
+constexpr int MAX_D = 1024;               // per-lane register tile is MAX_V float4; kernels are templated on MAX_V
+#define B200_DISPATCH_V(D, ...)                                      \
+  do {                                                              \
+    if ((D) <= 512) { constexpr int MAX_V = 4; __VA_ARGS__; }       \
+    else            { constexpr int MAX_V = 8; __VA_ARGS__; }       \
+  } while (0)
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  const uint2 w = *reinterpret_cast<const uint2*>(p);
+  return make_float4(bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y));
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+// ------------------------------------------------------------------------------------------------
+// a-L2 forward: y = x / max(||x||, eps)        (0426/train.py:191-192; F.normalize, eps 1e-12)
+// bytes/row: D*sizeof(in) read + D*2 (bf16 out) [+ D*4 (f32 out)] + 4
+// ------------------------------------------------------------------------------------------------
+template <typename TIn, int MAX_V>
+__global__ void __launch_bounds__(ROW_THREADS) l2norm_fwd_kernel(const TIn* __restrict__ x, long long ldx,
+                                                                 __nv_bfloat16* __restrict__ y_bf16,
+                                                                 float* __restrict__ y_f32, float* __restrict__ inv_norm,
+                                                                 int rows, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nv = D >> 7;                                    // float4 per lane
+  for (long long row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); row < rows;
+       row += static_cast<long long>(gridDim.x) * (ROW_THREADS / 32)) {
+    const TIn* xr = x + row * ldx;
+    float4 v[MAX_V];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_V; ++i)
+      if (i < nv) {
+        v[i] = ld4(xr + i * 128 + lane * 4);
+        ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), eps);
+    if (lane == 0 && inv_norm) inv_norm[row] = inv;
+#pragma unroll
+    for (int i = 0; i < MAX_V; ++i)
+      if (i < nv) {
+        const float4 o = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+        if (y_bf16) st4(y_bf16 + row * D + i * 128 + lane * 4, o);
+        if (y_f32) st4(y_f32 + row * D + i * 128 + lane * 4, o);
+      }
+  }
+}
+
+// a-L2 backward: dx (+)= inv * (dy - yhat * (yhat . dy)),  yhat = x * inv.   If the norm was clamped (inv == 1/eps)
+// the clamp has zero gradient and dx = dy * inv.
+template <typename TIn, int MAX_V>
+__global__ void __launch_bounds__(ROW_THREADS) l2norm_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x,
+                                                                 long long ldx, const float* __restrict__ inv_norm,
+                                                                 float* __restrict__ dx, int accumulate, int rows, int D,
+                                                                 float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nv = D >> 7;
+  for (long long row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); row < rows;
+       row += static_cast<long long>(gridDim.x) * (ROW_THREADS / 32)) {
+    const float inv = inv_norm[row];
+    const bool clamped = inv >= 1.0f / eps;
+    float4 g[MAX_V], yh[MAX_V];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_V; ++i)
+      if (i < nv) {
+        g[i] = ld4(dy + row * D + i * 128 + lane * 4);
+        const float4 xv = ld4(x + row * ldx + i * 128 + lane * 4);
+        yh[i] = make_float4(xv.x * inv, xv.y * inv, xv.z * inv, xv.w * inv);
+        dot += g[i].x * yh[i].x + g[i].y * yh[i].y + g[i].z * yh[i].z + g[i].w * yh[i].w;
+      }
+    dot = clamped ? 0.f : warp_sum(dot);
+#pragma unroll
+    for (int i = 0; i < MAX_V; ++i)
+      if (i < nv) {
+        float4 o = make_float4(inv * (g[i].x - yh[i].x * dot), inv * (g[i].y - yh[i].y * dot),
+                               inv * (g[i].z - yh[i].z * dot), inv * (g[i].w - yh[i].w * dot));
+        float* d = dx + row * D + i * 128 + lane * 4;
+        if (accumulate) {
+          const float4 old = ld4(d);
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        st4(d, o);
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward (0426/train.py:95, eps 1e-5, biased variance) fused with the optional L2-normalised bf16 copy
+// that feeds the InfoNCE kernels.  bytes/row: D*4 read + D*4 (y f32) + D*2 (yhat bf16) + 12.
+// ------------------------------------------------------------------------------------------------
+template <int MAX_V>
+__global__ void __launch_bounds__(ROW_THREADS) layernorm_fwd_kernel(const float* __restrict__ z,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta,
+                                                                    float* __restrict__ y_f32,
+                                                                    __nv_bfloat16* __restrict__ yhat_bf16,
+                                                                    float* __restrict__ mean_out,
+                                                                    float* __restrict__ rstd_out,
+                                                                    float* __restrict__ inv_norm_out, int rows, int D,
+                                                                    float ln_eps, float l2_eps) {
+  const int lane = threadIdx.x & 31;
+  const int nv = D >> 7;
+  for (long long row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); row < rows;
+       row += static_cast<long long>(gridDim.x) * (ROW_THREADS / 32)) {
+    float4 v[MAX_V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_V; ++i)
+      if (i < nv) {
+        v[i] = ld4(z + row * D + i * 128 + lane * 4);
+        s += v[i].x + v[i].y + v[i].z + v[i].w;
+      }
+    const float mu = warp_sum(s) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_V; ++i)
+      if (i < nv) {
+        const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+        q += a * a + b * b + c * c + d * d;
+      }
+    const float rstd = rsqrtf(warp_sum(q) / D + ln_eps);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_V; ++i)
+      if (i < nv) {
+        const float4 g = ld4(gamma + i * 128 + lane * 4);
+        const float4 b = ld4(beta + i * 128 + lane * 4);
+        v[i] = make_float4((v[i].x - mu) * rstd * g.x + b.x, (v[i].y - mu) * rstd * g.y + b.y,
+                           (v[i].z - mu) * rstd * g.z + b.z, (v[i].w - mu) * rstd * g.w + b.w);
+        ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+        if (y_f32) st4(y_f32 + row * D + i * 128 + lane * 4, v[i]);
+      }
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mu;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+    if (yhat_bf16) {
+      const float inv = 1.0f / fmaxf(sqrtf(warp_sum(ss)), l2_eps);
+      if (lane == 0 && inv_norm_out) inv_norm_out[row] = inv;
+#pragma unroll
+      for (int i = 0; i < MAX_V; ++i)
+        if (i < nv)
+          st4(yhat_bf16 + row * D + i * 128 + lane * 4,
+              make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv));
+    }
+  }
+}
+
+// LayerNorm backward: dz = rstd * (g*dy - mean(g*dy) - zhat * mean(g*dy*zhat)); per-block partial dgamma/dbeta.
+// Outputs dz both as f32 (residual branch + bias grads) and bf16 (operand of the dW2 / dh GEMMs).
+template <int MAX_V>
+__global__ void __launch_bounds__(ROW_THREADS) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                                    const float* __restrict__ mean,
+                                                                    const float* __restrict__ rstd,
+                                                                    const float* __restrict__ gamma,
+                                                                    float* __restrict__ dz_f32,
+                                                                    __nv_bfloat16* __restrict__ dz_bf16,
+                                                                    float* __restrict__ partial /*[grid][2][D]*/, int rows,
+                                                                    int D) {
+  __shared__ float red[ROW_THREADS / 32][128];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nv = D >> 7;
+  float4 dg[MAX_V], db[MAX_V];
+#pragma unroll
+  for (int i = 0; i < MAX_V; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row = blockIdx.x * (ROW_THREADS / 32) + warp; row < rows;
+       row += static_cast<long long>(gridDim.x) * (ROW_THREADS / 32)) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 g[MAX_V], zh[MAX_V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_V; ++i)
+      if (i < nv) {
+        const float4 d = ld4(dy + row * D + i * 128 + lane * 4);
+        const float4 zz = ld4(z + row * D + i * 128 + lane * 4);
+        const float4 gm = ld4(gamma + i * 128 + lane * 4);
+        zh[i] = make_float4((zz.x - mu) * rs, (zz.y - mu) * rs, (zz.z - mu) * rs, (zz.w - mu) * rs);
+        dg[i].x += d.x * zh[i].x; dg[i].y += d.y * zh[i].y; dg[i].z += d.z * zh[i].z; dg[i].w += d.w * zh[i].w;
+        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+        g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        s2 += g[i].x * zh[i].x + g[i].y * zh[i].y + g[i].z * zh[i].z + g[i].w * zh[i].w;
+      }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int i = 0; i < MAX_V; ++i)
+      if (i < nv) {
+        const float4 o = make_float4(rs * (g[i].x - s1 - zh[i].x * s2), rs * (g[i].y - s1 - zh[i].y * s2),
+                                     rs * (g[i].z - s1 - zh[i].z * s2), rs * (g[i].w - s1 - zh[i].w * s2));
+        if (dz_f32) st4(dz_f32 + row * D + i * 128 + lane * 4, o);
+        if (dz_bf16) st4(dz_bf16 + row * D + i * 128 + lane * 4, o);
+      }
+  }
+  // block reduction of the per-warp dgamma/dbeta partials, one 128-column slab at a time
+  float* pg = partial + static_cast<long long>(blockIdx.x) * 2 * D;
+  for (int which = 0; which < 2; ++which) {
+    for (int i = 0; i < nv; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < MAX_V; ++k)
+        if (k == i) v = which == 0 ? dg[k] : db[k];
+      __syncthreads();
+      *reinterpret_cast<float4*>(&red[warp][lane * 4]) = v;
+      __syncthreads();
+      if (threadIdx.x < 128) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < ROW_THREADS / 32; ++w) acc += red[w][threadIdx.x];
+        pg[which * D + i * 128 + threadIdx.x] = acc;
+      }
+    }
+  }
+}
+
+// out[n] (+)= sum over `nparts` rows of partial[part][n]  (final stage of the two-stage column reductions)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, long long part_stride, int nparts,
+                                       float* __restrict__ out, int n, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int p = 0; p < nparts; ++p) acc += partial[p * part_stride + i];
+  out[i] = accumulate ? out[i] + acc : acc;
+}
+
+// column sums of a [rows, N] matrix (bias gradients): stage 1, each block owns a row slab and all N columns.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ a, long long lda, int rows, int N,
+                                                             int rows_per_block, float* __restrict__ partial) {
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = r0; r < r1; ++r) {
+      const float4 v = ld4(a + static_cast<long long>(r) * lda + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    st4(partial + static_cast<long long>(blockIdx.x) * N + c, acc);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    st4(out + i * 4, ld4(in + i * 4));
+}
+
+static inline int row_grid(long long rows) {
+  const long long want = (rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200clip_l2norm_fwd(const void* x, int x_is_bf16, long long ldx, void* y_bf16, float* y_f32,
+                                   float* inv_norm, long long rows, int D, float eps, void* stream) {
+  B200_REQUIRE(rows >= 0 && D > 0 && D % 128 == 0 && D <= MAX_D, "l2norm_fwd: D=%d must be a multiple of 128, <= %d", D, MAX_D);
+  B200_REQUIRE(aligned16(x) && (y_bf16 == nullptr || aligned16(y_bf16)) && (y_f32 == nullptr || aligned16(y_f32)),
+               "l2norm_fwd: pointers must be 16-byte aligned");
+  B200_REQUIRE(ldx % 4 == 0, "l2norm_fwd: ldx must be a multiple of 4");
+  if (rows == 0) return B200_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (x_is_bf16)
+    B200_DISPATCH_V(D, (l2norm_fwd_kernel<__nv_bfloat16, MAX_V><<<row_grid(rows), ROW_THREADS, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(y_bf16), y_f32, inv_norm, (int)rows, D, eps)));
+  else
+    B200_DISPATCH_V(D, (l2norm_fwd_kernel<float, MAX_V><<<row_grid(rows), ROW_THREADS, 0, s>>>(
+        static_cast<const float*>(x), ldx, static_cast<__nv_bfloat16*>(y_bf16), y_f32, inv_norm, (int)rows, D, eps)));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200clip_l2norm_bwd(const float* dy, const void* x, int x_is_bf16, long long ldx, const float* inv_norm,
+                                   float* dx, int accumulate, long long rows, int D, float eps, void* stream) {
+  B200_REQUIRE(rows >= 0 && D > 0 && D % 128 == 0 && D <= MAX_D, "l2norm_bwd: D=%d must be a multiple of 128, <= %d", D, MAX_D);
+  B200_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx), "l2norm_bwd: pointers must be 16-byte aligned");
+  if (rows == 0) return B200_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (x_is_bf16)
+    B200_DISPATCH_V(D, (l2norm_bwd_kernel<__nv_bfloat16, MAX_V><<<row_grid(rows), ROW_THREADS, 0, s>>>(
+        dy, static_cast<const __nv_bfloat16*>(x), ldx, inv_norm, dx, accumulate, (int)rows, D, eps)));
+  else
+    B200_DISPATCH_V(D, (l2norm_bwd_kernel<float, MAX_V><<<row_grid(rows), ROW_THREADS, 0, s>>>(
+        dy, static_cast<const float*>(x), ldx, inv_norm, dx, accumulate, (int)rows, D, eps)));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200clip_layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y_f32, void* yhat_bf16,
+                                      float* mean, float* rstd, float* inv_norm, long long rows, int D, float ln_eps,
+                                      float l2_eps, void* stream) {
+  B200_REQUIRE(rows >= 0 && D > 0 && D % 128 == 0 && D <= MAX_D, "layernorm_fwd: D=%d must be a multiple of 128, <= %d", D, MAX_D);
+  B200_REQUIRE(aligned16(z) && aligned16(gamma) && aligned16(beta), "layernorm_fwd: pointers must be 16-byte aligned");
+  if (rows == 0) return B200_OK;
+  B200_DISPATCH_V(D, (layernorm_fwd_kernel<MAX_V><<<row_grid(rows), ROW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      z, gamma, beta, y_f32, static_cast<__nv_bfloat16*>(yhat_bf16), mean, rstd, inv_norm, (int)rows, D, ln_eps, l2_eps)));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" size_t b200clip_layernorm_bwd_workspace_bytes(long long rows, int D) {
+  return static_cast<size_t>(row_grid(rows)) * 2 * D * sizeof(float);
+}
+
+extern "C" int b200clip_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd,
+                                      const float* gamma, float* dz_f32, void* dz_bf16, float* dgamma, float* dbeta,
+                                      int accumulate_params, long long rows, int D, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  B200_REQUIRE(rows > 0 && D > 0 && D % 128 == 0 && D <= MAX_D, "layernorm_bwd: D=%d must be a multiple of 128, <= %d", D, MAX_D);
+  const int grid = row_grid(rows);
+  if (workspace_bytes < static_cast<size_t>(grid) * 2 * D * sizeof(float))
+    return fail(B200_ERR_WORKSPACE, "layernorm_bwd: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  B200_DISPATCH_V(D, (layernorm_bwd_kernel<MAX_V><<<grid, ROW_THREADS, 0, s>>>(
+      dy, z, mean, rstd, gamma, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), partial, (int)rows, D)));
+  B200_LAUNCH_CHECK();
+  reduce_partials_kernel<<<(D + 127) / 128, 128, 0, s>>>(partial, 2LL * D, grid, dgamma, D, accumulate_params);
+  reduce_partials_kernel<<<(D + 127) / 128, 128, 0, s>>>(partial + D, 2LL * D, grid, dbeta, D, accumulate_params);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" size_t b200clip_colsum_workspace_bytes(long long rows, int N) {
+  const int rpb = 256;
+  return static_cast<size_t>((rows + rpb - 1) / rpb) * N * sizeof(float);
+}
+
+extern "C" int b200clip_colsum(const void* a, int a_is_bf16, long long lda, long long rows, int N, float* out,
+                               int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  B200_REQUIRE(rows > 0 && N > 0 && N % 4 == 0, "colsum: N=%d must be a multiple of 4", N);
+  const int rpb = 256;
+  const int nblk = static_cast<int>((rows + rpb - 1) / rpb);
+  if (workspace_bytes < static_cast<size_t>(nblk) * N * sizeof(float)) return fail(B200_ERR_WORKSPACE, "colsum: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  if (a_is_bf16)
+    colsum_partial_kernel<__nv_bfloat16><<<nblk, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(a), lda, (int)rows, N, rpb, partial);
+  else
+    colsum_partial_kernel<float><<<nblk, 256, 0, s>>>(static_cast<const float*>(a), lda, (int)rows, N, rpb, partial);
+  B200_LAUNCH_CHECK();
+  reduce_partials_kernel<<<(N + 127) / 128, 128, 0, s>>>(partial, N, nblk, out, N, accumulate);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200clip_cast_f32_bf16(const float* in, void* out, long long n, void* stream) {
+  B200_REQUIRE(n >= 0 && n % 4 == 0 && aligned16(in) && (reinterpret_cast<uintptr_t>(out) & 7u) == 0,
+               "cast: n must be a multiple of 4 and pointers aligned");
+  if (n == 0) return B200_OK;
+  const long long n4 = n / 4;
+  const int grid = static_cast<int>(std::min<long long>((n4 + 255) / 256, static_cast<long long>(num_sms()) * 16));
+  cast_f32_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, static_cast<__nv_bfloat16*>(out), n4);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}

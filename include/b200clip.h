@@ -1,0 +1,129 @@
+/*
+ * b200clip C ABI -- the drop-in boundary of the B200-native CLIP head.
+ *
+ * The reference (cjycarrie/CLIP-FOR-DL) has no FFI: its boundary is a set of Python symbols in train.py /
+ * disease_analysis.py.  The Python package `b200clip` re-exports those symbols
+ * (same names, arguments and error behaviour) and lowers each of them onto the entry points below through
+ * ctypes; every entry point cites the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - plain pointers + sizes; all pointers are DEVICE pointers unless a name ends in `_host`.
+ *  - the caller owns every buffer including workspaces (`*_workspace_bytes` tells the size); kernels never allocate.
+ *  - stream-ordered and re-entrant: `stream` is a cudaStream_t passed as void*; nothing synchronises the host.
+ *  - return 0 on success, negative on failure (-1 invalid argument, -2 CUDA error, -3 workspace too small,
+ *    -4 unsupported); b200clip_last_error_string() describes the last failure on this thread.  Nothing throws or
+ *    aborts across the boundary and there is no CPU fallback.
+ *  - bf16 tensors are row-major `__nv_bfloat16`, 16-byte aligned, leading dimension a multiple of 8 elements.
+ */
+#ifndef B200CLIP_H
+#define B200CLIP_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int b200clip_version(void);
+const char* b200clip_last_error_string(void);
+
+/* ---- generic tensor-core GEMM (tcgen05/TMEM, TMA) ------------------------------------------------------------
+ * D[M,N] = A*B, bf16 operands, fp32 accumulate.  a_mn_major=0: a[M][K], =1: a[K][M];  b_mn_major=0: b[N][K]
+ * (x W^T, nn.Linear 0426/train.py:78), =1: b[K][N].  epilogue: 0 store f32, 1 store bf16, 2 +bias,GELU -> (out0=p,
+ * out1=gelu(p)) bf16, 3 +bias +resid(bf16) -> f32, 4 atomicAdd f32 (split_k > 1), 5 out0 bf16 = acc*gelu'(resid)+aux,
+ * 6 relu(acc+bias) bf16. */
+int b200clip_gemm_bf16(const void* a, const void* b, int a_mn_major, int b_mn_major, int M, int N, int K,
+                       long long lda, long long ldb, int epilogue, float alpha, void* out0, long long ld0,
+                       void* out1, long long ld1, const float* bias, const void* resid, long long ld_res,
+                       const float* aux, long long ld_aux, int split_k, void* stream);
+
+/* ---- a-L2: F.normalize(x, dim=-1), eps 1e-12 -- 0426/train.py:191-192, :971; 0426/disease_analysis.py:332 ----- */
+int b200clip_l2norm_fwd(const void* x, int x_is_bf16, long long ldx, void* y_bf16, float* y_f32, float* inv_norm,
+                        long long rows, int D, float eps, void* stream);
+int b200clip_l2norm_bwd(const float* dy, const void* x, int x_is_bf16, long long ldx, const float* inv_norm, float* dx,
+                        int accumulate, long long rows, int D, float eps, void* stream);
+
+/* ---- LayerNorm tail of the projection block -- nn.LayerNorm(512), 0426/train.py:82,95 ------------------------ */
+int b200clip_layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y_f32, void* yhat_bf16,
+                           float* mean, float* rstd, float* inv_norm, long long rows, int D, float ln_eps, float l2_eps,
+                           void* stream);
+size_t b200clip_layernorm_bwd_workspace_bytes(long long rows, int D);
+int b200clip_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
+                           float* dz_f32, void* dz_bf16, float* dgamma, float* dbeta, int accumulate_params,
+                           long long rows, int D, void* workspace, size_t workspace_bytes, void* stream);
+size_t b200clip_colsum_workspace_bytes(long long rows, int N);
+int b200clip_colsum(const void* a, int a_is_bf16, long long lda, long long rows, int N, float* out, int accumulate,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int b200clip_cast_f32_bf16(const float* in, void* out_bf16, long long n, void* stream);
+int b200clip_sum_f32(const float* a, long long n, float* out, void* stream);
+
+/* ---- a-P1 / a-P2: ImageProjection.forward 0426/train.py:84-96, TextProjection.forward :109-116 -----------------
+ * Linear(E,D) -> GELU(erf) -> Linear(D,D) -> (dropout = identity) -> +residual -> LayerNorm [-> L2-normalised bf16].
+ * Saved for backward (caller tensors): p, h (bf16), z (f32), mean, rstd. */
+int b200clip_proj_fwd(const void* x_bf16, long long B, int E, int D, const void* w1_bf16, const float* b1,
+                      const void* w2_bf16, const float* b2, const float* gamma, const float* beta, float ln_eps,
+                      void* p_bf16, void* h_bf16, float* z_f32, float* y_f32, void* yhat_bf16, float* mean, float* rstd,
+                      float* inv_norm, void* stream);
+size_t b200clip_proj_bwd_workspace_bytes(long long B, int E, int D);
+int b200clip_proj_bwd(const float* dy, const void* x_bf16, long long B, int E, int D, const void* w1_bf16,
+                      const void* w2_bf16, const float* gamma, const void* p_bf16, const void* h_bf16, const float* z_f32,
+                      const float* mean, const float* rstd, float* dx_f32, float* dw1, float* db1, float* dw2, float* db2,
+                      float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a-N: contrastive_loss(image_features, text_features, temperature) -- 0426/train.py:154-176 ----------------
+ * Inputs are L2-normalised bf16 rows.  Data-parallel form: i_hat = this rank's rows [b_loc, D] (global rows
+ * row0 .. row0+b_loc), t_hat = all b_glob rows.  fwd_stats -> r (row sums, complete) and c_partial (this rank's
+ * column sums; SUM-combine across ranks).  loss -> sums[3] = {sum log r, sum_{c_lo<=j<c_hi} log c_j, sum S_ii},
+ * the half-inverse statistics the backward pass consumes and (if `loss` != NULL, single rank) the scalar loss.
+ * bwd -> d_i [b_loc, D] and d_t_partial [b_glob, D] (reduce-scatter across ranks), both f32, scaled by the optional
+ * device scalar *grad_scale. */
+size_t b200clip_infonce_workspace_bytes(long long b_loc, long long b_glob);
+int b200clip_infonce_fwd_stats(const void* i_hat, const void* t_hat, int D, long long b_loc, long long b_glob,
+                               float temperature, float* r, float* c_partial, void* workspace, size_t workspace_bytes,
+                               void* stream);
+int b200clip_infonce_loss(const void* i_hat, const void* t_hat, int D, long long b_loc, long long b_glob, long long row0,
+                          float temperature, const float* r, const float* c, long long c_lo, long long c_hi, float* rinvh,
+                          float* cinvh, double* sums, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D, long long b_loc, long long b_glob, long long row0,
+                         float temperature, const float* rinvh, const float* cinvh, const float* grad_scale, float* d_i,
+                         float* d_t_partial, void* stream);
+
+/* ---- a-B: multilabel_contrastive_loss(image_features, text_features, labels, temperature) -- 0426/train.py:178-230
+ * label_sum: device scalar = sum(labels) over the GLOBAL batch; total_elems = B_glob * C.  status gets 1 when the
+ * loss is NaN/Inf/>1000 (the reference's fallback condition, :224).  coef [B,C] = d loss / d (cos/tau) feeds
+ * b200clip_skinny_outer for the text-side gradient. */
+size_t b200clip_smallc_workspace_bytes(long long rows, int C, int D);
+int b200clip_mlbce_fwd_bwd(const float* image_features, long long ldx, const float* text_features, const float* labels,
+                           int label_cols, long long ld_labels, long long B, int C, int D, float temperature,
+                           const float* label_sum, double total_elems, const float* grad_scale, float* d_image,
+                           int d_image_accumulate, float* coef, float* x_inv_norm, double* sums, float* loss, int* status,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a-A: FC classification adapter nn.Linear(512,16) + nn.BCEWithLogitsLoss() -- NB02 c28:50-52, c29:23-25;
+ * prediction sigmoid(z) > 0.5 -- NB02 c30:42-43 */
+int b200clip_fc_bce_fwd_bwd(const float* x, long long ldx, const float* weight, const float* bias, const float* labels,
+                            long long ld_labels, long long B, int C, int D, double total_elems, float threshold,
+                            const float* grad_scale, float* d_x, int d_x_accumulate, float* coef, float* pred,
+                            float* logits, double* sums, float* loss, void* workspace, size_t workspace_bytes,
+                            void* stream);
+int b200clip_skinny_outer(const float* coef, int C, const float* x, long long ldx, const float* row_scale, long long rows,
+                          int D, float* out_w, float* out_b, int accumulate, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* ---- a-M: predict_multilabel(image_features, text_features, threshold) -- 0426/train.py:869-886 ---------------- */
+int b200clip_predict_multilabel(const float* image_features, long long ldx, const float* text_features, long long B,
+                                int C, int D, float temperature, float threshold, float* pred, void* stream);
+
+/* ---- a-Z: zero-shot scoring core of predict_zero_shot -- 0426/disease_analysis.py:329-356 (softmax top-k),
+ * multimodal_attention/disease_analysis.py:345-413 (sigmoid(cos/0.5) >= thr), NB02 c41:27-32, c44:24-36, and the
+ * 14 x (pos,neg) prompt shape.  thr_logit_host: HOST array of nlabels floats, a label passes when its score
+ * (cos/tau, or l+ - l- in pair mode) is > (or >= if thr_inclusive) the value, i.e. logit(threshold). */
+int b200clip_zeroshot_score(const void* x_bf16, long long ldx, long long n, const void* prompts_bf16, int np, int D,
+                            int pair_mode, int normalize_x, float temperature, const float* thr_logit_host,
+                            int thr_inclusive, float guard, int topk, int value_mode, uint8_t* argmax, void* mask,
+                            int mask_is_u32, uint8_t* topk_idx, float* topk_val, float* scores,
+                            unsigned long long* guard_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CLIP_H */

@@ -1,0 +1,109 @@
+"""Projection block (a-P1/a-P2) and the fused head step vs the oracle (fp32 CPU restatement of the reference) on the
+same bf16-rounded inputs/weights.  Tolerances: loss 1e-3 relative, gradients 2e-2 relative L2 (north_star)."""
+import pytest
+import torch
+
+from gpu_util import dev, gpu, rel_l2
+import ref_head as R
+import synth
+
+pytestmark = gpu
+
+
+def _load(mod, first, p):
+    with torch.no_grad():
+        getattr(mod, first).weight.copy_(p["w1"]); getattr(mod, first).bias.copy_(p["b1"])
+        mod.fc.weight.copy_(p["w2"]); mod.fc.bias.copy_(p["b2"])
+        mod.layer_norm.weight.copy_(p["gamma"]); mod.layer_norm.bias.copy_(p["beta"])
+
+
+def _round_params(p):
+    q = dict(p)
+    q["w1"], q["w2"] = synth.bf16_round(p["w1"]), synth.bf16_round(p["w2"])
+    return q
+
+
+@pytest.mark.parametrize("B,E,cls,first", [(24, 2048, "ImageProjection", "image_projection"),
+                                           (300, 768, "TextProjection", "text_projection"),
+                                           (1024, 768, "ImageProjection", "image_projection"),
+                                           (16, 768, "TextProjection", "text_projection")])
+def test_projection_forward_backward(B, E, cls, first):
+    import b200clip
+    D = 512
+    p = _round_params(synth.projection_params(100, E, D))
+    x = synth.bf16_round(synth.randn(7, B, E))
+    w = synth.randn(9, B, D)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    xr = x.clone().requires_grad_(True)
+    yref = R.projection_forward(xr, pr)
+    (yref * w).sum().backward()
+    mod = getattr(b200clip, cls)(E, D).to(dev()).eval()
+    _load(mod, first, p)
+    xg = x.to(dev()).requires_grad_(True)
+    y = mod(xg)
+    (y * w.to(dev())).sum().backward()
+    assert rel_l2(y, yref) < 1e-2
+    assert rel_l2(xg.grad, xr.grad) < 2e-2
+    assert rel_l2(getattr(mod, first).weight.grad, pr["w1"].grad) < 2e-2
+    assert rel_l2(getattr(mod, first).bias.grad, pr["b1"].grad) < 2e-2
+    assert rel_l2(mod.fc.weight.grad, pr["w2"].grad) < 2e-2
+    assert rel_l2(mod.fc.bias.grad, pr["b2"].grad) < 2e-2
+    assert rel_l2(mod.layer_norm.weight.grad, pr["gamma"].grad) < 2e-2
+    assert rel_l2(mod.layer_norm.bias.grad, pr["beta"].grad) < 2e-2
+
+
+def test_projection_state_dict_keys_and_4d_input():
+    import b200clip
+    m = b200clip.ImageProjection(2048, 512)
+    assert set(m.state_dict().keys()) == {"image_projection.weight", "image_projection.bias", "fc.weight", "fc.bias",
+                                          "layer_norm.weight", "layer_norm.bias"}
+    t = b200clip.TextProjection(768, 512)
+    assert set(t.state_dict().keys()) == {"text_projection.weight", "text_projection.bias", "fc.weight", "fc.bias",
+                                          "layer_norm.weight", "layer_norm.bias"}
+    m = m.to(dev()).eval()
+    x = torch.randn(8, 2048, 1, 1, device=dev())
+    assert m(x).shape == (8, 512)
+    m.train()
+    with pytest.raises(RuntimeError):
+        m(x)                                               # train-mode dropout is refused loudly, not skipped
+
+
+@pytest.mark.parametrize("B,E_img", [(256, 2048), (1024, 768)])
+def test_fused_head_step(B, E_img):
+    import b200clip
+    D, E_txt, C = 512, 768, 16
+    ip = _round_params(synth.projection_params(100, E_img, D))
+    tp = _round_params(synth.projection_params(200, E_txt, D))
+    fw, fb = synth.uniform(31, -0.04, 0.04, C, D), synth.uniform(32, -0.04, 0.04, C)
+    x_img, x_txt = synth.bf16_round(synth.randn(1, B, E_img)), synth.bf16_round(synth.randn(2, B, E_txt))
+    # correlate text with image inputs a little so the diagonal is informative
+    class_text = synth.unit_rows(3, C, D)
+    labels = synth.labels(4, B, C)
+    ipr = {k: v.clone().requires_grad_(True) for k, v in ip.items()}
+    tpr = {k: v.clone().requires_grad_(True) for k, v in tp.items()}
+    fwr, fbr = fw.clone().requires_grad_(True), fb.clone().requires_grad_(True)
+    xi_r, xt_r = x_img.clone().requires_grad_(True), x_txt.clone().requires_grad_(True)
+    ref = R.head_step(xi_r, xt_r, class_text, labels, ipr, tpr, fwr, fbr)
+    ref["loss"].backward()
+
+    head = b200clip.ClipHead(E_img, E_txt, D, C).to(dev())
+    _load(head.image_projector, "image_projection", ip)
+    _load(head.text_projector, "text_projection", tp)
+    with torch.no_grad():
+        head.classifier.weight.copy_(fw); head.classifier.bias.copy_(fb)
+    xi, xt = x_img.to(dev()).requires_grad_(True), x_txt.to(dev()).requires_grad_(True)
+    loss = head(xi, xt, class_text.to(dev()), labels.to(dev()))
+    loss.backward()
+    assert abs(loss.item() - ref["loss"].item()) <= 1e-3 * abs(ref["loss"].item()), (loss.item(), ref["loss"].item())
+    checks = {
+        "dx_img": (xi.grad, xi_r.grad), "dx_txt": (xt.grad, xt_r.grad),
+        "iw1": (head.image_projector.image_projection.weight.grad, ipr["w1"].grad),
+        "iw2": (head.image_projector.fc.weight.grad, ipr["w2"].grad),
+        "ig": (head.image_projector.layer_norm.weight.grad, ipr["gamma"].grad),
+        "tw1": (head.text_projector.text_projection.weight.grad, tpr["w1"].grad),
+        "tw2": (head.text_projector.fc.weight.grad, tpr["w2"].grad),
+        "tbeta": (head.text_projector.layer_norm.bias.grad, tpr["beta"].grad),
+        "fw": (head.classifier.weight.grad, fwr.grad), "fb": (head.classifier.bias.grad, fbr.grad),
+    }
+    for name, (a, b) in checks.items():
+        assert rel_l2(a, b) < 2e-2, name

@@ -1,0 +1,87 @@
+"""Small-C kernels (smallc.cu) vs the oracle: multilabel_contrastive_loss (a-B), FC adapter + BCE (a-A),
+predict_multilabel (a-M)."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import dev, gpu, rel_l2
+import ref_head as R
+import synth
+
+pytestmark = gpu
+
+
+@pytest.mark.parametrize("B,C,tau", [(40, 16, 1.0), (1000, 16, 0.07), (4096, 16, 1.0), (77, 5, 0.5)])
+def test_multilabel_contrastive_loss(B, C, tau):
+    import b200clip
+    x = synth.randn(21, B, 512)
+    t = synth.randn(22, C, 512)
+    y = synth.labels(23, B, C, density=0.1)
+    xr, tr = x.clone().requires_grad_(True), t.clone().requires_grad_(True)
+    lref = R.multilabel_contrastive_loss(xr, tr, y, tau)
+    lref.backward()
+    xg, tg = x.to(dev()).requires_grad_(True), t.to(dev()).requires_grad_(True)
+    loss = b200clip.multilabel_contrastive_loss(xg, tg, y.to(dev()), tau)
+    (2.0 * loss).backward()
+    assert abs(loss.item() - lref.item()) <= 1e-4 * abs(lref.item())
+    assert rel_l2(xg.grad, 2.0 * xr.grad) < 1e-3
+    assert rel_l2(tg.grad, 2.0 * tr.grad) < 1e-3
+    assert int(b200clip.multilabel_contrastive_loss.last_status.item()) == 0
+
+
+def test_multilabel_label_padding_and_empty_labels(golden):
+    import b200clip
+    d = dev()
+    x, t = synth.randn(21, 40, 64), synth.randn(22, 16, 64)
+    # kernels need D % 128 == 0: embed the D=64 golden case into D=128 by zero padding (cosines unchanged)
+    xp = torch.zeros(40, 128); xp[:, :64] = x
+    tp = torch.zeros(16, 128); tp[:, :64] = t
+    lp = b200clip.multilabel_contrastive_loss(xp.to(d), tp.to(d), synth.labels(24, 40, 12, density=0.2).to(d), 1.0)
+    np.testing.assert_allclose(lp.item(), golden["mlbce_loss_padded"], rtol=1e-5)
+    l0 = b200clip.multilabel_contrastive_loss(xp.to(d), tp.to(d), torch.zeros(40, 16, device=d), 1.0)
+    np.testing.assert_allclose(l0.item(), golden["mlbce_loss_nolabels"], rtol=1e-5)
+    l1 = b200clip.multilabel_contrastive_loss(xp.to(d), tp.to(d), synth.labels(23, 40, 16, density=0.2).to(d), 1.0)
+    np.testing.assert_allclose(l1.item(), golden["mlbce_loss_tau1.0"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("B,C", [(40, 16), (3000, 16), (129, 7)])
+def test_fc_adapter_bce(B, C):
+    import b200clip
+    d = dev()
+    x = synth.randn(33, B, 512)
+    w = synth.uniform(31, -0.05, 0.05, C, 512)
+    b = synth.uniform(32, -0.05, 0.05, C)
+    y = synth.labels(34, B, C, density=0.2)
+    xr, wr, br = (v.clone().requires_grad_(True) for v in (x, w, b))
+    lref = R.fc_adapter_bce(xr, wr, br, y)
+    lref.backward()
+    xg, wg, bg = (v.to(d).requires_grad_(True) for v in (x, w, b))
+    loss = b200clip.fc_adapter_bce(xg, wg, bg, y.to(d))
+    loss.backward()
+    assert abs(loss.item() - lref.item()) <= 1e-5 * abs(lref.item())
+    assert rel_l2(xg.grad, xr.grad) < 1e-4
+    assert rel_l2(wg.grad, wr.grad) < 1e-4
+    assert rel_l2(bg.grad, br.grad) < 1e-4
+    ad = b200clip.ClassificationAdapter(512, C).to(d)
+    with torch.no_grad():
+        ad.weight.copy_(w.to(d)); ad.bias.copy_(b.to(d))
+    assert rel_l2(ad(x.to(d)), R.fc_adapter_logits(x, w, b)) < 1e-5
+    pred = ad.predict(x.to(d))
+    ref_pred = R.fc_adapter_predict(x, w, b)
+    z = R.fc_adapter_logits(x, w, b)
+    safe = (z.abs() > 1e-4)                                 # decisions away from the fp32 tie band must agree
+    assert torch.equal(pred.cpu()[safe], ref_pred[safe])
+
+
+@pytest.mark.parametrize("B,thr", [(40, 0.5), (5000, 0.7)])
+def test_predict_multilabel(B, thr):
+    import b200clip
+    I = synth.randn(41, B, 512)
+    T = synth.unit_rows(42, 16, 512)
+    ref = R.predict_multilabel(I, T, thr)
+    out = b200clip.predict_multilabel(I.to(dev()), T.to(dev()), thr)
+    s = (I.double() @ T.double().T) / 0.07
+    safe = (torch.sigmoid(s) - thr).abs() > 1e-5
+    assert out.dtype == torch.float32 and out.shape == ref.shape
+    assert torch.equal(out.cpu()[safe], ref[safe])
+    assert safe.float().mean() > 0.999
