@@ -202,8 +202,15 @@ def infonce_forward(i_hat: torch.Tensor, t_hat: torch.Tensor, temperature: float
     ws = _ws(nb, dev)
     r = torch.empty((b_loc,), dtype=torch.float32, device=dev)
     c = torch.empty((b_glob,), dtype=torch.float32, device=dev)
+    ev = KERNEL_EVENTS["infonce_fwd"]
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.b200clip_infonce_fwd_stats(ptr(i_hat), ptr(t_hat), D, b_loc, b_glob, temperature, ptr(r), ptr(c), ptr(ws),
                                          ws.numel(), stream_ptr()), "infonce_fwd_stats")
+    if ev is not None:
+        e1.record()
+        ev.append((e0, e1))
     world = 1
     if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized() and b_loc != b_glob):
         world = torch.distributed.get_world_size(group)
@@ -223,6 +230,10 @@ def infonce_forward(i_hat: torch.Tensor, t_hat: torch.Tensor, temperature: float
     return loss, rinvh, cinvh
 
 
+# bench.py sets this to a list to collect (start, end) CUDA-event pairs around the dominant kernel (roofline leg)
+KERNEL_EVENTS = {"infonce_bwd": None, "infonce_fwd": None}
+
+
 def infonce_backward(i_hat, t_hat, temperature, rinvh, cinvh, grad_scale: Optional[torch.Tensor], row0: int = 0):
     """Returns d_i [b_loc, D] f32 and d_t_partial [b_glob, D] f32 (this rank's contribution)."""
     b_loc, D = i_hat.shape
@@ -233,8 +244,15 @@ def infonce_backward(i_hat, t_hat, temperature, rinvh, cinvh, grad_scale: Option
     gs = None
     if grad_scale is not None:
         gs = _f32c(grad_scale.reshape(()))
+    ev = KERNEL_EVENTS["infonce_bwd"]
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(load().b200clip_infonce_bwd(ptr(i_hat), ptr(t_hat), D, b_loc, b_glob, row0, temperature, ptr(rinvh), ptr(cinvh),
                                       ptr(gs), ptr(d_i), ptr(d_t), stream_ptr()), "infonce_bwd")
+    if ev is not None:
+        e1.record()
+        ev.append((e0, e1))
     return d_i, d_t
 
 

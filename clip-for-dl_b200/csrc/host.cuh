@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
 
@@ -44,7 +45,16 @@ inline int fail(int code, const char* fmt, ...) {
   do {                                                                     \
     if (!(cond)) return ::b200::fail(::b200::B200_ERR_INVALID, __VA_ARGS__); \
   } while (0)
-#define B200_LAUNCH_CHECK() B200_CHECK_CUDA(cudaGetLastError())
+// every kernel launch is followed by exactly one B200_LAUNCH_CHECK(): it also feeds b200clip_launch_count()
+inline std::atomic<unsigned long long>& launch_counter() {
+  static std::atomic<unsigned long long> n{0};
+  return n;
+}
+#define B200_LAUNCH_CHECK()                              \
+  do {                                                   \
+    ::b200::launch_counter().fetch_add(1);               \
+    B200_CHECK_CUDA(cudaGetLastError());                 \
+  } while (0)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -70,6 +80,14 @@ inline PFN_encodeTiled get_encode_tiled() {
 // (box_cols * 2 bytes must be <= 128). Out-of-bounds elements read as zero.
 inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                              uint32_t box_cols, uint32_t box_rows) {
+  // The driver entry point needs a current context on THIS thread; PyTorch's autograd engine calls us from worker
+  // threads where only its own runtime instance has bound one.  A no-op runtime call binds the primary context.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaError_t e = cudaFree(nullptr);
+    if (e != cudaSuccess) return fail(B200_ERR_CUDA, "cudaFree(0) (context bind) failed: %s", cudaGetErrorString(e));
+    ctx_bound = true;
+  }
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
   if (!aligned16(base)) return fail(B200_ERR_INVALID, "TMA base pointer must be 16-byte aligned");

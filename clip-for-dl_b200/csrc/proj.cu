@@ -97,4 +97,5 @@ extern "C" int b200clip_proj_bwd(const float* dy, const void* x_bf16, long long 
 }
 
 extern "C" int b200clip_version(void) { return 100; }
+extern "C" unsigned long long b200clip_launch_count(void) { return b200::launch_counter().load(); }
 extern "C" const char* b200clip_last_error_string(void) { return b200::last_error().c_str(); }

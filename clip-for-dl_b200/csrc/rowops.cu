@@ -335,6 +335,7 @@ extern "C" int b200clip_layernorm_bwd(const float* dy, const float* z, const flo
       dy, z, mean, rstd, gamma, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), partial, (int)rows, D)));
   B200_LAUNCH_CHECK();
   reduce_partials_kernel<<<(D + 127) / 128, 128, 0, s>>>(partial, 2LL * D, grid, dgamma, D, accumulate_params);
+  B200_LAUNCH_CHECK();
   reduce_partials_kernel<<<(D + 127) / 128, 128, 0, s>>>(partial + D, 2LL * D, grid, dbeta, D, accumulate_params);
   B200_LAUNCH_CHECK();
   return B200_OK;

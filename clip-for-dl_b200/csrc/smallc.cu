@@ -415,7 +415,10 @@ extern "C" int b200clip_skinny_outer(const float* coef, int C, const float* x, l
   B200_LAUNCH_CHECK();
   const int nw = C * D;
   reduce_partials2_kernel<<<(nw + 255) / 256, 256, 0, s>>>(partial, stride, nblk, out_w, nw, accumulate);
-  if (out_b) reduce_partials2_kernel<<<1, 32, 0, s>>>(partial + nw, stride, nblk, out_b, C, accumulate);
   B200_LAUNCH_CHECK();
+  if (out_b) {
+    reduce_partials2_kernel<<<1, 32, 0, s>>>(partial + nw, stride, nblk, out_b, C, accumulate);
+    B200_LAUNCH_CHECK();
+  }
   return B200_OK;
 }

@@ -25,6 +25,8 @@ extern "C" {
 
 int b200clip_version(void);
 const char* b200clip_last_error_string(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long b200clip_launch_count(void);
 
 /* ---- generic tensor-core GEMM (tcgen05/TMEM, TMA) ------------------------------------------------------------
  * D[M,N] = A*B, bf16 operands, fp32 accumulate.  a_mn_major=0: a[M][K], =1: a[K][M];  b_mn_major=0: b[N][K]
