@@ -242,7 +242,6 @@ struct NceBwdParams {
   int diag_off[2];          // diagonal: y column == x row + diag_off   (dir0: +row0, dir1: -row0)
   const float* row_stat[2]; // 0.5 / r or c for X rows
   const float* col_stat[2]; // 0.5 / c or r for Y rows
-  const __nv_bfloat16* ymat[2];   // Y matrix (bf16 [ncols, 512]): the -delta_ij/B term is applied in fp32 at the end
   float* out[2];            // dX [nrows, 512] f32
   float k1, k2;
   float out_scale;          // 1 / (B_glob * tau)
@@ -434,7 +433,9 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constan
         for (int t = 0; t < 4; ++t) {
           const int col = col0 + i + t;
           const float e = fast_exp2(fmaf(__uint_as_float(v[i + t]), p.k1, -p.k2));
-          g[t] = (col < ncols) ? e * (rstat + cs[t]) : 0.f;
+          float gv = e * (rstat + cs[t]);
+          if (col == diag_col) gv -= 1.0f;               // G_ii = p_ii - 1 rounded as a whole: error relative to G_ii itself
+          g[t] = (col < ncols) ? gv : 0.f;
         }
         packed[i / 2] = pack_bf16x2(g[0], g[1]);
         packed[i / 2 + 1] = pack_bf16x2(g[2], g[3]);
@@ -453,9 +454,6 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constan
     float scale = p.out_scale;
     if (p.grad_scale) scale *= *p.grad_scale;
     float* orow = p.out[dir] + static_cast<long long>(row) * NCE_D + h * 256 + w * 128;
-    // G = P - I/B: the bf16 tile held only P (softmax mass); the identity part is subtracted here in fp32
-    const bool has_diag = row_ok && diag_col >= 0 && diag_col < ncols;
-    const __nv_bfloat16* yrow = p.ymat[dir] + static_cast<long long>(has_diag ? diag_col : 0) * NCE_D + h * 256 + w * 128;
 #pragma unroll 1
     for (int c = 0; c < 128; c += 32) {
       uint32_t v[32];
@@ -463,20 +461,10 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constan
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (has_diag) {
-            const uint4 yy = *reinterpret_cast<const uint4*>(yrow + c + i);
-            y[0] = bf16_lo(yy.x); y[1] = bf16_hi(yy.x); y[2] = bf16_lo(yy.y); y[3] = bf16_hi(yy.y);
-            y[4] = bf16_lo(yy.z); y[5] = bf16_hi(yy.z); y[6] = bf16_lo(yy.w); y[7] = bf16_hi(yy.w);
-          }
+        for (int i = 0; i < 32; i += 4)
           *reinterpret_cast<float4*>(orow + c + i) =
-              make_float4((__uint_as_float(v[i]) - y[0]) * scale, (__uint_as_float(v[i + 1]) - y[1]) * scale,
-                          (__uint_as_float(v[i + 2]) - y[2]) * scale, (__uint_as_float(v[i + 3]) - y[3]) * scale);
-          *reinterpret_cast<float4*>(orow + c + i + 4) =
-              make_float4((__uint_as_float(v[i + 4]) - y[4]) * scale, (__uint_as_float(v[i + 5]) - y[5]) * scale,
-                          (__uint_as_float(v[i + 6]) - y[6]) * scale, (__uint_as_float(v[i + 7]) - y[7]) * scale);
-        }
+              make_float4(__uint_as_float(v[i]) * scale, __uint_as_float(v[i + 1]) * scale,
+                          __uint_as_float(v[i + 2]) * scale, __uint_as_float(v[i + 3]) * scale);
       }
     }
   }
@@ -684,8 +672,8 @@ extern "C" int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D,
   NceBwdParams p{};
   p.nrows[0] = (int)b_loc;  p.ncols[0] = (int)b_glob; p.diag_off[0] = (int)row0;
   p.nrows[1] = (int)b_glob; p.ncols[1] = (int)b_loc;  p.diag_off[1] = -(int)row0;
-  p.row_stat[0] = rinvh; p.col_stat[0] = cinvh; p.out[0] = d_i;         p.ymat[0] = static_cast<const __nv_bfloat16*>(t_hat);
-  p.row_stat[1] = cinvh; p.col_stat[1] = rinvh; p.out[1] = d_t_partial; p.ymat[1] = static_cast<const __nv_bfloat16*>(i_hat);
+  p.row_stat[0] = rinvh; p.col_stat[0] = cinvh; p.out[0] = d_i;
+  p.row_stat[1] = cinvh; p.col_stat[1] = rinvh; p.out[1] = d_t_partial;
   p.k1 = LOG2E / temperature; p.k2 = LOG2E / temperature;
   p.out_scale = 1.0f / (static_cast<float>(b_glob) * temperature);
   p.grad_scale = grad_scale;
