@@ -78,19 +78,37 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-#ifndef B200_WATCHDOG_CYCLES
-#define B200_WATCHDOG_CYCLES (4000000000ll)   // ~2-3 s at 1.3-1.9 GHz
-#endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > B200_WATCHDOG_CYCLES) {
-      printf("b200clip: mbarrier watchdog fired (block %d,%d,%d thread %d bar@%u parity %u)\n", blockIdx.x,
-             blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
+// Watchdog: a protocol bug must trap instead of hanging the GPU box.  try_wait suspends for a HW-defined time per
+// attempt (~100-200 clk), so 1<<24 failed attempts is seconds.  The report lives out of line to keep waits lean.
+static __device__ __noinline__ void mbar_watchdog_fire(uint32_t bar_addr, uint32_t parity) {
+  printf("b200clip: mbarrier watchdog fired (block %d,%d,%d thread %d bar@%u parity %u)\n", blockIdx.x, blockIdx.y,
+         blockIdx.z, threadIdx.x, bar_addr, parity);
+  __trap();
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
+  if (mbar_try_wait_a(bar_addr, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait_a(bar_addr, parity)) {
+    if (++spins > (1u << 24)) mbar_watchdog_fire(bar_addr, parity);
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_a(smem_u32(bar), parity); }
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
 
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / tcgen05.mma smem reads)
@@ -110,6 +128,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_addr), "r"(c0), "r"(c1)
       : "memory");
 }
 // with an L2 cache-policy hint
@@ -159,6 +183,10 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
                : "memory");
 }
 
+__device__ __forceinline__ void tc_commit_a(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+
 // smem matrix descriptor (64-bit). Fields in 16-byte units: start [0,14), LBO [16,30), SBO [32,46);
 // version=1 at [46,48); layout type at [61,64): 0 none, 2 = 128B swizzle, 4 = 64B, 6 = 32B.
 constexpr uint32_t LAYOUT_SW128 = 2;
@@ -180,6 +208,23 @@ __device__ __forceinline__ uint64_t desc_kmajor_sw128(uint32_t smem_addr) {
 // (SBO); successive 64-element MN groups are `mn_group_stride_bytes` apart (LBO).
 __device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t smem_addr, uint32_t mn_group_stride_bytes) {
   return make_smem_desc(smem_addr, mn_group_stride_bytes, 1024, LAYOUT_SW128);
+}
+
+// Lean form for issue loops: a descriptor is {lo, hi} with hi constant for every 128B-swizzled tile
+// (SBO = 1024 B, version 1, layout SW128) and lo = (addr >> 4) | (LBO >> 4) << 16, so advancing along K is ONE 32-bit add.
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (LAYOUT_SW128 << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ void mma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(static_cast<uint32_t>(accumulate)), "r"(DESC_HI_SW128)
+      : "memory");
 }
 
 // instruction descriptor, .kind::f16 : bf16 x bf16 -> fp32

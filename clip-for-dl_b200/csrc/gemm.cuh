@@ -95,52 +95,60 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * STAGE_BYTES;
-        uint8_t* sb = sa + A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-        const int k0 = (kc0 + i) * GEMM_BK;
+    // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
+    {
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), smem0 = smem_u32(smem);
+      int s = 0;
+      uint32_t ph = 0;
+      int k0 = kc0 * GEMM_BK;
+      for (int i = 0; i < nk; ++i, k0 += GEMM_BK) {
+        mbar_wait_a(empty0 + 8 * s, ph ^ 1);
+        const uint32_t sa = smem0 + s * STAGE_BYTES, sb = sa + A_BYTES, fb = full0 + 8 * s;
+        if (elect_one()) {
+        mbar_arrive_expect_tx_a(fb, STAGE_BYTES);
         if constexpr (!A_MN) {
-          tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0);                      // box {64 k, 128 m}
+          tma_load_2d_a(sa, &tmap_a, fb, k0, m0);                               // box {64 k, 128 m}
         } else {
 #pragma unroll
-          for (int g = 0; g < GEMM_BM / 64; ++g)                                // box {64 m, 64 k}
-            tma_load_2d(sa + g * 8192, &tmap_a, &full_bar[s], m0 + g * 64, k0);
+          for (int g = 0; g < GEMM_BM / 64; ++g) tma_load_2d_a(sa + g * 8192, &tmap_a, fb, m0 + g * 64, k0);   // {64 m, 64 k}
         }
         if constexpr (!B_MN) {
-          tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n0);                      // box {64 k, BN n}
+          tma_load_2d_a(sb, &tmap_b, fb, k0, n0);                               // box {64 k, BN n}
         } else {
 #pragma unroll
-          for (int g = 0; g < BN / 64; ++g)                                     // box {64 n, 64 k}
-            tma_load_2d(sb + g * 8192, &tmap_b, &full_bar[s], n0 + g * 64, k0);
+          for (int g = 0; g < BN / 64; ++g) tma_load_2d_a(sb + g * 8192, &tmap_b, fb, n0 + g * 64, k0);        // {64 n, 64 k}
         }
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: warp-uniform loop (descriptor words live in uniform registers), one
+    // elected lane issues; one 32-bit add per operand per MMA =====================
+    {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
+      constexpr uint32_t A_STEP = (A_MN ? 2048 : 32) >> 4, B_STEP = (B_MN ? 2048 : 32) >> 4;
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      const uint32_t a_lo0 = desc_lo(smem_u32(smem), A_MN ? 8192 : 16);
+      const uint32_t b_lo0 = desc_lo(smem_u32(smem) + A_BYTES, B_MN ? 8192 : 16);
+      int s = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < nk; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait_a(full0 + 8 * s, ph);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
+        const uint32_t a_lo = a_lo0 + s * (STAGE_BYTES >> 4), b_lo = b_lo0 + s * (STAGE_BYTES >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < GEMM_BK / 16; ++j) {
-          const uint64_t da = A_MN ? desc_mnmajor_sw128(sa + j * 2048, 8192) : desc_kmajor_sw128(sa + j * 32);
-          const uint64_t db = B_MN ? desc_mnmajor_sw128(sb + j * 2048, 8192) : desc_kmajor_sw128(sb + j * 32);
-          mma_ss(tmem_base, da, db, idesc, (i | j) ? 1u : 0u);
+          for (int j = 0; j < GEMM_BK / 16; ++j)
+            mma_ss_lo(tmem_base, a_lo + j * A_STEP, b_lo + j * B_STEP, idesc, (i | j) != 0);
+          tc_commit_a(empty0 + 8 * s);                // frees the smem stage once these MMAs have read it
         }
-        tc_commit(&empty_bar[s]);                     // frees the smem stage once these MMAs have read it
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      tc_commit(accum_bar);                           // accumulator complete
+      if (elect_one()) tc_commit(accum_bar);          // accumulator complete
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> global =====================

@@ -22,7 +22,7 @@ namespace b200 {
 
 constexpr int NCE_D = 512;                 // shared embedding size (0426/config.py:30)
 constexpr int NCE_KC = NCE_D / 64;         // 8 K-chunks of 64 bf16 (one 128-B swizzle row each)
-constexpr int NCE_THREADS = 384;           // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue WG0, 8-11 WG1
+
 constexpr int X_CHUNK_BYTES = 128 * 128;   // [128 rows x 64 bf16]
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -57,28 +57,32 @@ struct NceFwdParams {
   int nrows_pad;
 };
 
-template <int BN, int STAGES>
+// Issue loops below are WARP-UNIFORM (all 32 lanes run the loop, one elected lane issues TMA / tcgen05 instructions):
+// descriptor words then live in uniform registers and an MMA costs one 32-bit add per operand.  The first version
+// ran them under `if (lane == 0)`; ncu showed ~230 SASS instructions per 4 MMAs and the tensor pipe 14-33 % busy.
+template <int BN, int STAGES, int NWG>
 constexpr int nce_fwd_smem_bytes() {
-  return NCE_KC * X_CHUNK_BYTES + STAGES * BN * 128 + 2 * 4 * BN * 4 + 512 + 1024;
+  return NCE_KC * X_CHUNK_BYTES + STAGES * BN * 128 + NWG * 4 * BN * 4 + 512 + 1024;
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(NCE_THREADS, 1)
+template <int BN, int STAGES, int NWG>
+__global__ void __launch_bounds__(128 + NWG * 128, 1)
 nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
                const NceFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX = smem;
   uint8_t* sY = sX + NCE_KC * X_CHUNK_BYTES;
-  float* scratch = reinterpret_cast<float*>(sY + STAGES * BN * 128);        // [2 WG][4 warps][BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 2 * 4 * BN);
+  float* scratch = reinterpret_cast<float*>(sY + STAGES * BN * 128);        // [NWG][4 warps][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + NWG * 4 * BN);
   uint64_t* x_full = bars;
   uint64_t* x_empty = bars + 1;
   uint64_t* y_full = bars + 2;
   uint64_t* y_empty = y_full + STAGES;
-  uint64_t* s_full = y_empty + STAGES;
-  uint64_t* s_empty = s_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
+  uint64_t* s_full = y_empty + STAGES;          // NWG
+  uint64_t* s_empty = s_full + NWG;             // NWG
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + NWG);
+  constexpr int Y_BYTES = BN * 128;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -97,14 +101,14 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       mbar_init(&y_full[s], 1);
       mbar_init(&y_empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NWG; ++b) {
       mbar_init(&s_full[b], 1);
       mbar_init(&s_empty[b], 128);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_alloc(tmem_slot, NWG * BN);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -113,97 +117,130 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int y_it = 0, xcount = 0, cur_rb = -1;
-      for (int t = t0; t < t1; ++t) {
-        const int rb = t / CT, ct = t - rb * CT;
-        if (rb != cur_rb) {
-          mbar_wait(x_empty, (xcount & 1) ^ 1);
-          mbar_arrive_expect_tx(x_full, NCE_KC * X_CHUNK_BYTES);
+    // ===================== TMA producer =====================
+    const uint32_t xf = smem_u32(x_full), xe = smem_u32(x_empty), yf0 = smem_u32(y_full), ye0 = smem_u32(y_empty);
+    const uint32_t sx = smem_u32(sX), sy = smem_u32(sY);
+    int s = 0, cur_rb = -1;
+    uint32_t ph = 0, xph = 0;
+    int rb = t0 / CT, ct = t0 - rb * CT;
+    for (int t = t0; t < t1; ++t) {
+      if (rb != cur_rb) {
+        mbar_wait_a(xe, xph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx_a(xf, NCE_KC * X_CHUNK_BYTES);
 #pragma unroll
-          for (int kc = 0; kc < NCE_KC; ++kc) tma_load_2d(sX + kc * X_CHUNK_BYTES, &tmap_x, x_full, kc * 64, rb * 128);
-          ++xcount;
-          cur_rb = rb;
+          for (int kc = 0; kc < NCE_KC; ++kc) tma_load_2d_a(sx + kc * X_CHUNK_BYTES, &tmap_x, xf, kc * 64, rb * 128);
         }
-        for (int kc = 0; kc < NCE_KC; ++kc, ++y_it) {
-          const int s = y_it % STAGES;
-          mbar_wait(&y_empty[s], ((y_it / STAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(&y_full[s], BN * 128);
-          tma_load_2d(sY + s * BN * 128, &tmap_y, &y_full[s], kc * 64, ct * BN);
-        }
+        __syncwarp();
+        xph ^= 1;
+        cur_rb = rb;
       }
+#pragma unroll 1
+      for (int kc = 0; kc < NCE_KC; ++kc) {
+        mbar_wait_a(ye0 + 8 * s, ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx_a(yf0 + 8 * s, Y_BYTES);
+          tma_load_2d_a(sy + s * Y_BYTES, &tmap_y, yf0 + 8 * s, kc * 64, ct * BN);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      if (++ct == CT) { ct = 0; ++rb; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
-      int y_it = 0, xcount = 0, cur_rb = -1, n = 0;
-      for (int t = t0; t < t1; ++t, ++n) {
-        const int rb = t / CT;
-        if (rb != cur_rb) {
-          mbar_wait(x_full, xcount & 1);
-          ++xcount;
-          cur_rb = rb;
-        }
-        const int buf = n & 1;
-        mbar_wait(&s_empty[buf], ((n >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kc = 0; kc < NCE_KC; ++kc, ++y_it) {
-          const int s = y_it % STAGES;
-          mbar_wait(&y_full[s], (y_it / STAGES) & 1);
-          tc_fence_after();
-          const uint32_t xa = smem_u32(sX + kc * X_CHUNK_BYTES);
-          const uint32_t yb = smem_u32(sY + s * BN * 128);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            mma_ss(d_tmem, desc_kmajor_sw128(xa + j * 32), desc_kmajor_sw128(yb + j * 32), idesc, (kc | j) ? 1u : 0u);
-          tc_commit(&y_empty[s]);
-        }
-        tc_commit(&s_full[buf]);
-        if (t + 1 == t1 || (t + 1) / CT != rb) tc_commit(x_empty);
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
+    const uint32_t xf = smem_u32(x_full), xe = smem_u32(x_empty), yf0 = smem_u32(y_full), ye0 = smem_u32(y_empty);
+    const uint32_t sf0 = smem_u32(s_full), se0 = smem_u32(s_empty);
+    const uint32_t x_lo = desc_lo(smem_u32(sX), 16), y_lo = desc_lo(smem_u32(sY), 16);
+    int s = 0, cur_rb = -1, buf = 0;
+    uint32_t ph = 0, xph = 0, sph = 0;               // sph: phase of the s_empty ring (flips when buf wraps)
+    int rb = t0 / CT, ct = t0 - rb * CT;
+    for (int t = t0; t < t1; ++t) {
+      if (rb != cur_rb) {
+        mbar_wait_a(xf, xph);
+        xph ^= 1;
+        cur_rb = rb;
       }
+      mbar_wait_a(se0 + 8 * buf, sph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+#pragma unroll
+      for (int kc = 0; kc < NCE_KC; ++kc) {
+        mbar_wait_a(yf0 + 8 * s, ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a = x_lo + kc * (X_CHUNK_BYTES >> 4), b = y_lo + s * (Y_BYTES >> 4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mma_ss_lo(d_tmem, a + 2 * j, b + 2 * j, idesc, (kc | j) != 0);
+          tc_commit_a(ye0 + 8 * s);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      const bool last_of_rb = (ct + 1 == CT) || (t + 1 == t1);
+      if (elect_one()) {
+        tc_commit_a(sf0 + 8 * buf);
+        if (last_of_rb) tc_commit_a(xe);
+      }
+      __syncwarp();
+      if (++buf == NWG) { buf = 0; sph ^= 1; }
+      if (++ct == CT) { ct = 0; ++rb; }
     }
   } else if (warp >= 4) {
+    // ===================== epilogue warpgroups: tile n of this CTA -> warpgroup n % NWG =====================
     const int w = (warp - 4) >> 2;                 // epilogue warpgroup
     const int q = warp & 3;                        // TMEM lane quadrant
     const int tid_wg = threadIdx.x - 128 - w * 128;
     float* my_scratch = scratch + w * 4 * BN;
+    const uint32_t sf = smem_u32(s_full) + 8 * w, se = smem_u32(s_empty) + 8 * w;
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + w * BN;
     float rsum = 0.f;
     int cur_rb = -1;
-    int n = w;
+    uint32_t sph = 0;
     auto flush_rsum = [&](int rb) {
       const int row = rb * 128 + q * 32 + lane;
       const int first_cta = (rb * CT) / p.tiles_per_cta;
-      const int slot = 2 * (static_cast<int>(blockIdx.x) - first_cta) + w;
+      const int slot = NWG * (static_cast<int>(blockIdx.x) - first_cta) + w;
       if (row < p.nrows) p.r_part[static_cast<long long>(slot) * p.nrows_pad + row] = rsum;
       rsum = 0.f;
     };
-    for (int t = t0 + w; t < t1; t += 2, n += 2) {
+    for (int t = t0 + w; t < t1; t += NWG) {
       const int rb = t / CT, ct = t - rb * CT;
       if (rb != cur_rb) {
         if (cur_rb >= 0) flush_rsum(cur_rb);
         cur_rb = rb;
       }
       const int row = rb * 128 + q * 32 + lane;
-      const bool row_ok = row < p.nrows;
-      mbar_wait(&s_full[w], (n >> 1) & 1);
+      const bool interior = (rb * 128 + 128 <= p.nrows) && (ct * BN + BN <= p.ncols);   // warp-uniform
+      mbar_wait_a(sf, sph);
+      sph ^= 1;
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t v[32];
-        tmem_ld_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + w * BN + c, v);
+        tmem_ld_x32(t_addr + c, v);
         tmem_ld_wait();
         if (c + 32 == BN) {                         // last TMEM read of this tile: hand the buffer back
           tc_fence_before();
-          mbar_arrive(&s_empty[w]);
+          mbar_arrive_a(se);
         }
-        const int col0 = ct * BN + c;
         float e[32];
+        if (interior) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = fast_exp2(fmaf(__uint_as_float(v[i]), p.k1, -p.k2));
-          e[i] = (row_ok && (col0 + i) < p.ncols) ? x : 0.f;
-          rsum += e[i];
+          for (int i = 0; i < 32; ++i) {
+            e[i] = fast_exp2(fmaf(__uint_as_float(v[i]), p.k1, -p.k2));
+            rsum += e[i];
+          }
+        } else {
+          const bool row_ok = row < p.nrows;
+          const int col0 = ct * BN + c;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = fast_exp2(fmaf(__uint_as_float(v[i]), p.k1, -p.k2));
+            e[i] = (row_ok && (col0 + i) < p.ncols) ? x : 0.f;
+            rsum += e[i];
+          }
         }
         my_scratch[q * BN + c + lane] = warp_colsum32(e, lane);
       }
@@ -221,19 +258,21 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
+  if (warp == 2) tmem_dealloc(tmem_base, NWG * BN);
 }
 
 // ================================================================================================
 // Pass 2: gradients
 // ================================================================================================
 constexpr int BWD_BN = 32;                  // columns per S tile
-constexpr int BWD_RA = 6;                   // ring A slots (Y K-chunks outside this CTA's D-half), 4 KB each
-constexpr int BWD_RB = 12;                  // ring B slots (Y K-chunks inside the D-half; 3 tiles x 4 chunks)
-constexpr int BWD_SLOT_BYTES = BWD_BN * 128;
+constexpr int BWD_TA = 2;                   // ring A depth in tiles (the 4 Y K-chunks outside this CTA's D-half)
+constexpr int BWD_TB = 3;                   // ring B depth in tiles (the 4 Y K-chunks inside the D-half; live until dX MMA)
+constexpr int BWD_SLOT_BYTES = BWD_BN * 128;            // one [32 x 64] bf16 chunk
+constexpr int BWD_GROUP_BYTES = 4 * BWD_SLOT_BYTES;     // 4 chunks = half a Y tile
 constexpr int BWD_G_BYTES = 128 * 128;      // [128 rows x 64 bf16]: even tiles use K cols 0-31, odd tiles 32-63
+constexpr int BWD_THREADS = 384;            // warp 0 TMA, 1 S-MMA issuer, 2 TMEM alloc + dX-MMA issuer, 3 idle, 4-11 epilogue
 constexpr int nce_bwd_smem_bytes() {
-  return NCE_KC * X_CHUNK_BYTES + (BWD_RA + BWD_RB) * BWD_SLOT_BYTES + BWD_G_BYTES + 512 + 1024;
+  return NCE_KC * X_CHUNK_BYTES + (BWD_TA + BWD_TB) * BWD_GROUP_BYTES + BWD_G_BYTES + 512 + 1024;
 }
 
 struct NceBwdParams {
@@ -248,14 +287,15 @@ struct NceBwdParams {
   const float* grad_scale;  // optional device scalar multiplied into out_scale (upstream dLoss)
 };
 
-__global__ void __launch_bounds__(NCE_THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 nce_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constant__ CUtensorMap tmap_y0,
                const __grid_constant__ CUtensorMap tmap_x1, const __grid_constant__ CUtensorMap tmap_y1,
                const NceBwdParams p) {
   const int dir = blockIdx.z;
   const int h = blockIdx.y;                         // D-half owned by this CTA
   const int rb = blockIdx.x;
-  const int nrows = p.nrows[dir], ncols = p.ncols[dir];
+  const int nrows = dir ? p.nrows[1] : p.nrows[0];
+  const int ncols = dir ? p.ncols[1] : p.ncols[0];
   if (rb * 128 >= nrows) return;                    // uniform per CTA, before any barrier / allocation
   const CUtensorMap* tmap_x = dir == 0 ? &tmap_x0 : &tmap_x1;
   const CUtensorMap* tmap_y = dir == 0 ? &tmap_y0 : &tmap_y1;
@@ -264,15 +304,15 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX = smem;
   uint8_t* sA = sX + NCE_KC * X_CHUNK_BYTES;
-  uint8_t* sB = sA + BWD_RA * BWD_SLOT_BYTES;
-  uint8_t* sG = sB + BWD_RB * BWD_SLOT_BYTES;
+  uint8_t* sB = sA + BWD_TA * BWD_GROUP_BYTES;
+  uint8_t* sG = sB + BWD_TB * BWD_GROUP_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sG + BWD_G_BYTES);
   uint64_t* x_full = bars;                          // 1
-  uint64_t* a_full = bars + 1;                      // RA
-  uint64_t* a_empty = a_full + BWD_RA;              // RA
-  uint64_t* b_full = a_empty + BWD_RA;              // RB
-  uint64_t* b_empty = b_full + BWD_RB;              // RB/4 (per tile group)
-  uint64_t* s_full = b_empty + BWD_RB / 4;          // 2
+  uint64_t* a_full = bars + 1;                      // TA
+  uint64_t* a_empty = a_full + BWD_TA;              // TA
+  uint64_t* b_full = a_empty + BWD_TA;              // TB
+  uint64_t* b_empty = b_full + BWD_TB;              // TB
+  uint64_t* s_full = b_empty + BWD_TB;              // 2
   uint64_t* s_empty = s_full + 2;                   // 2
   uint64_t* g_full = s_empty + 2;                   // 2
   uint64_t* g_empty = g_full + 2;                   // 2
@@ -289,9 +329,8 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constan
   }
   if (warp == 1 && lane == 0) {
     mbar_init(x_full, 1);
-    for (int s = 0; s < BWD_RA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < BWD_RB; ++s) mbar_init(&b_full[s], 1);
-    for (int s = 0; s < BWD_RB / 4; ++s) mbar_init(&b_empty[s], 1);
+    for (int s = 0; s < BWD_TA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < BWD_TB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
       mbar_init(&s_empty[b], 128);
@@ -313,147 +352,181 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constan
   const uint32_t tmem_s = tmem_base + 256;          // 2 x 32 columns
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(x_full, NCE_KC * X_CHUNK_BYTES);
+    // ===================== TMA producer: one 16 KB group (4 K-chunks) per barrier =====================
+    const uint32_t xf = smem_u32(x_full);
+    const uint32_t af0 = smem_u32(a_full), ae0 = smem_u32(a_empty), bf0 = smem_u32(b_full), be0 = smem_u32(b_empty);
+    const uint32_t sa = smem_u32(sA), sb = smem_u32(sB), sx = smem_u32(sX);
+    if (elect_one()) {
+      mbar_arrive_expect_tx_a(xf, NCE_KC * X_CHUNK_BYTES);
 #pragma unroll
-      for (int kc = 0; kc < NCE_KC; ++kc) tma_load_2d(sX + kc * X_CHUNK_BYTES, tmap_x, x_full, kc * 64, rb * 128);
-      int a_it = 0;
-      for (int n = 0; n < nt; ++n) {
-        const int grp = n % (BWD_RB / 4);
-        for (int kc = 0; kc < NCE_KC; ++kc) {
-          if ((kc >> 2) == h) {
-            const int slot = grp * 4 + (kc & 3);
-            if ((kc & 3) == 0) mbar_wait(&b_empty[grp], ((n / (BWD_RB / 4)) & 1) ^ 1);
-            mbar_arrive_expect_tx(&b_full[slot], BWD_SLOT_BYTES);
-            tma_load_2d(sB + slot * BWD_SLOT_BYTES, tmap_y, &b_full[slot], kc * 64, n * BWD_BN);
-          } else {
-            const int slot = a_it % BWD_RA;
-            mbar_wait(&a_empty[slot], ((a_it / BWD_RA) & 1) ^ 1);
-            mbar_arrive_expect_tx(&a_full[slot], BWD_SLOT_BYTES);
-            tma_load_2d(sA + slot * BWD_SLOT_BYTES, tmap_y, &a_full[slot], kc * 64, n * BWD_BN);
-            ++a_it;
-          }
-        }
+      for (int kc = 0; kc < NCE_KC; ++kc) tma_load_2d_a(sx + kc * X_CHUNK_BYTES, tmap_x, xf, kc * 64, rb * 128);
+    }
+    __syncwarp();
+    int ia = 0, ib = 0;
+    uint32_t pa = 0, pb = 0;
+    const int k_in = h * 256, k_out = (1 - h) * 256;          // element offsets of the two K halves
+    for (int n = 0; n < nt; ++n) {
+      mbar_wait_a(be0 + 8 * ib, pb ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx_a(bf0 + 8 * ib, BWD_GROUP_BYTES);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          tma_load_2d_a(sb + ib * BWD_GROUP_BYTES + c * BWD_SLOT_BYTES, tmap_y, bf0 + 8 * ib, k_in + c * 64, n * BWD_BN);
       }
+      __syncwarp();
+      mbar_wait_a(ae0 + 8 * ia, pa ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx_a(af0 + 8 * ia, BWD_GROUP_BYTES);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          tma_load_2d_a(sa + ia * BWD_GROUP_BYTES + c * BWD_SLOT_BYTES, tmap_y, af0 + 8 * ia, k_out + c * 64, n * BWD_BN);
+      }
+      __syncwarp();
+      if (++ia == BWD_TA) { ia = 0; pa ^= 1; }
+      if (++ib == BWD_TB) { ib = 0; pb ^= 1; }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, BWD_BN, false, false);
-      constexpr uint32_t idesc_g = make_idesc_bf16(128, 256, false, true);      // B = Y tile read MN-major
-      int a_it = 0;
-      auto issue_s = [&](int n) {
-        const int buf = n & 1;
-        const int grp = n % (BWD_RB / 4);
-        mbar_wait(&s_empty[buf], ((n >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_s + buf * BWD_BN;
-        for (int kc = 0; kc < NCE_KC; ++kc) {
-          uint32_t yb;
-          const bool in_half = (kc >> 2) == h;
-          int slot;
-          if (in_half) {
-            slot = grp * 4 + (kc & 3);
-            mbar_wait(&b_full[slot], (n / (BWD_RB / 4)) & 1);
-            yb = smem_u32(sB + slot * BWD_SLOT_BYTES);
-          } else {
-            slot = a_it % BWD_RA;
-            mbar_wait(&a_full[slot], (a_it / BWD_RA) & 1);
-            yb = smem_u32(sA + slot * BWD_SLOT_BYTES);
-          }
-          tc_fence_after();
-          const uint32_t xa = smem_u32(sX + kc * X_CHUNK_BYTES);
+    // ===================== S-MMA issuer: S[buf] = X (128 x 512) . Y_tile^T (32 x 512) =====================
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, BWD_BN, false, false);
+    const uint32_t af0 = smem_u32(a_full), ae0 = smem_u32(a_empty), bf0 = smem_u32(b_full);
+    const uint32_t sf0 = smem_u32(s_full), se0 = smem_u32(s_empty);
+    const uint32_t x_in = desc_lo(smem_u32(sX) + h * 4 * X_CHUNK_BYTES, 16);
+    const uint32_t x_out = desc_lo(smem_u32(sX) + (1 - h) * 4 * X_CHUNK_BYTES, 16);
+    const uint32_t a_lo0 = desc_lo(smem_u32(sA), 16), b_lo0 = desc_lo(smem_u32(sB), 16);
+    mbar_wait_a(smem_u32(x_full), 0);
+    int ia = 0, ib = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int n = 0; n < nt; ++n) {
+      const int buf = n & 1;
+      mbar_wait_a(se0 + 8 * buf, ((n >> 1) & 1) ^ 1);
+      mbar_wait_a(bf0 + 8 * ib, pb);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_s + buf * BWD_BN;
+      if (elect_one()) {
+        const uint32_t yb = b_lo0 + ib * (BWD_GROUP_BYTES >> 4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            mma_ss(d_tmem, desc_kmajor_sw128(xa + j * 32), desc_kmajor_sw128(yb + j * 32), idesc_s, (kc | j) ? 1u : 0u);
-          if (!in_half) {
-            tc_commit(&a_empty[slot]);
-            ++a_it;
-          }
-        }
-        tc_commit(&s_full[buf]);
-      };
-      auto issue_g = [&](int n) {
-        const int par = n & 1;
-        const int grp = n % (BWD_RB / 4);
-        mbar_wait(&g_full[par], (n >> 1) & 1);
-        tc_fence_after();
-        const uint32_t ga = smem_u32(sG) + par * 64;
-        const uint32_t yb = smem_u32(sB + grp * 4 * BWD_SLOT_BYTES);
+            mma_ss_lo(d_tmem, x_in + c * (X_CHUNK_BYTES >> 4) + 2 * j, yb + c * (BWD_SLOT_BYTES >> 4) + 2 * j, idesc_s, (c | j) != 0);
+      }
+      __syncwarp();
+      mbar_wait_a(af0 + 8 * ia, pa);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t ya = a_lo0 + ia * (BWD_GROUP_BYTES >> 4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            mma_ss_lo(d_tmem, x_out + c * (X_CHUNK_BYTES >> 4) + 2 * j, ya + c * (BWD_SLOT_BYTES >> 4) + 2 * j, idesc_s, true);
+        tc_commit_a(ae0 + 8 * ia);                  // ring A group is free once these MMAs have read it
+        tc_commit_a(sf0 + 8 * buf);                 // S tile complete -> epilogue
+      }
+      __syncwarp();
+      if (++ia == BWD_TA) { ia = 0; pa ^= 1; }
+      if (++ib == BWD_TB) { ib = 0; pb ^= 1; }
+    }
+  } else if (warp == 2) {
+    // ===================== dX-MMA issuer: acc += G_tile (128 x 32, bf16 in smem) . Y_tile[:, half] (MN-major) ==========
+    constexpr uint32_t idesc_g = make_idesc_bf16(128, 256, false, true);
+    const uint32_t gf0 = smem_u32(g_full), ge0 = smem_u32(g_empty), be0 = smem_u32(b_empty);
+    const uint32_t g_lo = desc_lo(smem_u32(sG), 16);
+    const uint32_t y_lo0 = desc_lo(smem_u32(sB), BWD_SLOT_BYTES);       // LBO = stride between 64-wide D groups
+    int ib = 0;
+    for (int n = 0; n < nt; ++n) {
+      const int par = n & 1;
+      mbar_wait_a(gf0 + 8 * par, (n >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t yb = y_lo0 + ib * (BWD_GROUP_BYTES >> 4);
 #pragma unroll
         for (int jj = 0; jj < BWD_BN / 16; ++jj)
-          mma_ss(tmem_acc, desc_kmajor_sw128(ga + jj * 32), desc_mnmajor_sw128(yb + jj * 2048, BWD_SLOT_BYTES), idesc_g,
-                 (n | jj) ? 1u : 0u);
-        tc_commit(&b_empty[grp]);
-        tc_commit(&g_empty[par]);
-      };
-      mbar_wait(x_full, 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int n = 0; n < nt; ++n) {
-        if (n + 1 < nt) issue_s(n + 1);
-        issue_g(n);
+          mma_ss_lo(tmem_acc, g_lo + par * 4 + jj * 2, yb + jj * (2048 >> 4), idesc_g, (n | jj) != 0);
+        tc_commit_a(be0 + 8 * ib);                  // ring B group no longer needed
+        tc_commit_a(ge0 + 8 * par);                 // G half-buffer free
       }
-      tc_commit(acc_full);
+      __syncwarp();
+      if (++ib == BWD_TB) ib = 0;
     }
+    if (elect_one()) tc_commit(acc_full);
+    __syncwarp();
   } else if (warp >= 4) {
-    // ===================== epilogue warpgroups =====================
+    // ===================== epilogue warpgroups: tile n -> warpgroup n & 1 =====================
     const int w = (warp - 4) >> 2;
     const int q = warp & 3;
     const int row_l = q * 32 + lane;
     const int row = rb * 128 + row_l;
     const bool row_ok = row < nrows;
-    const float rstat = row_ok ? p.row_stat[dir][row] : 0.f;
-    const float* cstat = p.col_stat[dir];
-    const int diag_col = row + p.diag_off[dir];
+    const float rstat = row_ok ? (dir ? p.row_stat[1] : p.row_stat[0])[row] : 0.f;
+    const float* cstat = dir ? p.col_stat[1] : p.col_stat[0];
+    const int diag_col = row + (dir ? p.diag_off[1] : p.diag_off[0]);
+    const int warp_diag_lo = rb * 128 + q * 32 + (dir ? p.diag_off[1] : p.diag_off[0]);   // diag cols of this warp's rows
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t sf = smem_u32(s_full) + 8 * w, se = smem_u32(s_empty) + 8 * w;
+    const uint32_t gf = smem_u32(g_full) + 8 * w, ge = smem_u32(g_empty) + 8 * w;
+    uint8_t* g_row = sG + row_l * 128;
+    uint32_t ph = 0;
     for (int n = w; n < nt; n += 2) {
-      mbar_wait(&s_full[w], (n >> 1) & 1);
+      const int col0 = n * BWD_BN;
+      const bool full_tile = col0 + BWD_BN <= ncols;                                      // uniform
+      const bool diag_tile = (col0 < warp_diag_lo + 32) && (col0 + BWD_BN > warp_diag_lo);  // warp-uniform
+      // column statistics first: their L2 latency hides behind the wait for the S tile
+      float cs[32];
+      if (full_tile) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(cstat + col0 + i));
+          cs[i] = c4.x; cs[i + 1] = c4.y; cs[i + 2] = c4.z; cs[i + 3] = c4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cs[i] = (col0 + i < ncols) ? cstat[col0 + i] : 0.f;
+      }
+      mbar_wait_a(sf, ph);
       tc_fence_after();
       uint32_t v[32];
       tmem_ld_x32(tmem_s + lane_base + w * BWD_BN, v);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&s_empty[w]);
-      const int col0 = n * BWD_BN;
+      mbar_arrive_a(se);
       uint32_t packed[16];
+      if (full_tile && !diag_tile) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float cs[4];
-        if (col0 + i + 3 < ncols) {
-          const float4 c4 = *reinterpret_cast<const float4*>(cstat + col0 + i);
-          cs[0] = c4.x; cs[1] = c4.y; cs[2] = c4.z; cs[3] = c4.w;
-        } else {
-#pragma unroll
-          for (int t = 0; t < 4; ++t) cs[t] = (col0 + i + t < ncols) ? cstat[col0 + i + t] : 0.f;
+        for (int i = 0; i < 32; i += 2) {
+          const float g0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.k1, -p.k2)) * (rstat + cs[i]);
+          const float g1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.k1, -p.k2)) * (rstat + cs[i + 1]);
+          packed[i / 2] = pack_bf16x2(g0, g1);
         }
-        float g[4];
+      } else {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int col = col0 + i + t;
-          const float e = fast_exp2(fmaf(__uint_as_float(v[i + t]), p.k1, -p.k2));
-          float gv = e * (rstat + cs[t]);
-          if (col == diag_col) gv -= 1.0f;               // G_ii = p_ii - 1 rounded as a whole: error relative to G_ii itself
-          g[t] = (col < ncols) ? gv : 0.f;
+        for (int i = 0; i < 32; i += 2) {
+          float g[2];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int col = col0 + i + t;
+            float gv = fast_exp2(fmaf(__uint_as_float(v[i + t]), p.k1, -p.k2)) * (rstat + cs[i + t]);
+            if (col == diag_col) gv -= 1.0f;           // G_ii = p_ii - 1 rounded as a whole: error relative to G_ii itself
+            g[t] = (col < ncols) ? gv : 0.f;
+          }
+          packed[i / 2] = pack_bf16x2(g[0], g[1]);
         }
-        packed[i / 2] = pack_bf16x2(g[0], g[1]);
-        packed[i / 2 + 1] = pack_bf16x2(g[2], g[3]);
       }
-      mbar_wait(&g_empty[w], ((n >> 1) & 1) ^ 1);
+      mbar_wait_a(ge, ph ^ 1);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(sG + sw128_offset(row_l, w * 4 + c)) =
+        *reinterpret_cast<uint4*>(g_row + (((w * 4 + c) ^ (row_l & 7)) << 4)) =
             make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
       fence_proxy_async_smem();
-      mbar_arrive(&g_full[w]);
+      mbar_arrive_a(gf);
+      ph ^= 1;
     }
     // final: dX[:, h*256 + w*128 .. +128) = acc * scale
     mbar_wait(acc_full, 0);
     tc_fence_after();
     float scale = p.out_scale;
     if (p.grad_scale) scale *= *p.grad_scale;
-    float* orow = p.out[dir] + static_cast<long long>(row) * NCE_D + h * 256 + w * 128;
+    float* orow = (dir ? p.out[1] : p.out[0]) + static_cast<long long>(row) * NCE_D + h * 256 + w * 128;
 #pragma unroll 1
     for (int c = 0; c < 128; c += 32) {
       uint32_t v[32];
@@ -564,6 +637,7 @@ __global__ void __launch_bounds__(256) nce_loss_kernel(const __nv_bfloat16* __re
 
 constexpr int FWD_BN = 128;
 constexpr int FWD_STAGES = 5;
+constexpr int FWD_NWG = 4;                 // epilogue warpgroups = TMEM S buffers (4 x 128 columns)
 
 struct NceFwdPlan {
   int row_blocks, col_tiles, total_tiles, tiles_per_cta, grid, r_slots, nrows_pad;
@@ -578,7 +652,7 @@ static NceFwdPlan plan_fwd(long long b_loc, long long b_glob) {
   pl.tiles_per_cta = (pl.total_tiles + sms - 1) / sms;
   if (pl.tiles_per_cta < 1) pl.tiles_per_cta = 1;
   pl.grid = (pl.total_tiles + pl.tiles_per_cta - 1) / pl.tiles_per_cta;
-  pl.r_slots = 2 * ((pl.col_tiles + pl.tiles_per_cta - 1) / pl.tiles_per_cta + 1);
+  pl.r_slots = FWD_NWG * ((pl.col_tiles + pl.tiles_per_cta - 1) / pl.tiles_per_cta + 1);
   pl.nrows_pad = pl.row_blocks * 128;
   pl.r_part_bytes = static_cast<size_t>(pl.r_slots) * pl.nrows_pad * sizeof(float);
   pl.c_part_bytes = static_cast<size_t>(pl.row_blocks) * b_glob * sizeof(float);
@@ -619,14 +693,14 @@ extern "C" int b200clip_infonce_fwd_stats(const void* i_hat, const void* t_hat, 
   p.nrows = (int)b_loc; p.ncols = (int)b_glob; p.num_col_tiles = pl.col_tiles; p.total_tiles = pl.total_tiles;
   p.tiles_per_cta = pl.tiles_per_cta; p.r_slots = pl.r_slots; p.k1 = LOG2E / temperature; p.k2 = LOG2E / temperature;
   p.r_part = r_part; p.c_part = c_part; p.nrows_pad = pl.nrows_pad;
-  auto kern = nce_fwd_kernel<FWD_BN, FWD_STAGES>;
-  constexpr int smem = nce_fwd_smem_bytes<FWD_BN, FWD_STAGES>();
+  auto kern = nce_fwd_kernel<FWD_BN, FWD_STAGES, FWD_NWG>;
+  constexpr int smem = nce_fwd_smem_bytes<FWD_BN, FWD_STAGES, FWD_NWG>();
   static bool configured = false;
   if (!configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<pl.grid, NCE_THREADS, smem, s>>>(tx, ty, p);
+  kern<<<pl.grid, 128 + FWD_NWG * 128, smem, s>>>(tx, ty, p);
   B200_LAUNCH_CHECK();
   const int n = (int)std::max(b_loc, b_glob);
   nce_reduce_stats_kernel<<<(n + 255) / 256, 256, 0, s>>>(r_part, pl.r_slots, pl.nrows_pad, (int)b_loc, c_part, pl.row_blocks,
@@ -684,7 +758,7 @@ extern "C" int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D,
     configured = true;
   }
   dim3 grid(static_cast<unsigned>((b_glob + 127) / 128), 2, 2);
-  nce_bwd_kernel<<<grid, NCE_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tx0, ty0, tx1, ty1, p);
+  nce_bwd_kernel<<<grid, BWD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tx0, ty0, tx1, ty1, p);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
