@@ -62,21 +62,22 @@ class ClipHeadFn(torch.autograd.Function):
             work.wait()
         l_nce, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, group=group if W > 1 else None)
         C = class_text.shape[0]
-        l_bce, status, bsums, *_ = ops.mlbce(y_img, class_text, labels_f, tau_bce, label_sum=lsum,
-                                             total_elems=float(b_glob) * C, finalize=(W == 1))
-        l_fc, fsums, *_ = ops.fc_bce(y_img, fw, fb, labels_f, total_elems=float(b_glob) * C, finalize=(W == 1))
+        Cf = fw.shape[0]
+        l_bce, l_fc, status, both, _ = ops.bce_heads(y_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
+                                                     total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
+                                                     finalize=(W == 1))
         if W > 1:
-            both = torch.stack([bsums[0], bsums[1], fsums[0]])
             dist.all_reduce(both, group=group)
             P = lsum.double()
             N = float(b_glob) * C - P
             l_bce = (0.5 * (-both[0] / (P + 1e-8) - both[1] / (N + 1e-8))).float()
-            l_fc = (both[2] / (float(b_glob) * C)).float()
+            l_fc = (both[2] / (float(b_glob) * Cf)).float()
         loss = l_nce + l_bce + l_fc
         ctx.save_for_backward(xi, xt, iw1b, iw2b, tw1b, tw2b, f(ig), f(tg), f(class_text), labels_f, lsum, y_img, y_txt, ihat,
                               that_all, inv_img, inv_txt, rinvh, cinvh, f(fw), f(fb) if fb is not None else None,
                               *saved_i, *saved_t)
         ctx.meta = (tau_nce, tau_bce, group, W, row0, b_loc, b_glob, x_img.requires_grad, x_txt.requires_grad)
+        ctx.in_dtypes = (x_img.dtype, x_txt.dtype)
         ctx.parts = (l_nce.detach(), l_bce.detach(), l_fc.detach())
         return loss
 
@@ -96,16 +97,15 @@ class ClipHeadFn(torch.autograd.Function):
             d_that_loc, work = d_that, None
         # image side: through the L2 normalisation, then add the two BCE heads' gradients (they act on y_img itself)
         dy_img = ops.l2norm_bwd(d_ihat, y_img, inv_img)
-        ops.mlbce(y_img, class_text, labels_f, tau_bce, grad_scale=g, label_sum=lsum, total_elems=float(b_glob) * C,
-                  finalize=False, dx_accum=dy_img)
-        _, _, _, coef, _, _ = ops.fc_bce(y_img, fw, fb, labels_f, grad_scale=g, total_elems=float(b_glob) * C, want_coef=True,
-                                         finalize=False, dx_accum=dy_img)
+        *_, coef = ops.bce_heads(y_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
+                                 total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * fw.shape[0], grad_scale=g,
+                                 dx_accum=dy_img, want_coef=True, finalize=False)
         dfw, dfb = ops.skinny_outer(coef, y_img, want_bias=True)
-        gi = ops.proj_bwd(dy_img, xi, iw1b, iw2b, ig, saved_i, need_dxi)
+        gi = ops.proj_bwd(dy_img, xi, iw1b, iw2b, ig, saved_i, need_dxi, ctx.in_dtypes[0])
         if work is not None:
             work.wait()
         dy_txt = ops.l2norm_bwd(d_that_loc, y_txt, inv_txt)
-        gt = ops.proj_bwd(dy_txt, xt, tw1b, tw2b, tg, saved_t, need_dxt)
+        gt = ops.proj_bwd(dy_txt, xt, tw1b, tw2b, tg, saved_t, need_dxt, ctx.in_dtypes[1])
         grads = [gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], gt[1], gt[2], gt[3], gt[4], gt[5], gt[6], dfw, dfb]
         if W > 1:
             # DDP-style: average is NOT taken -- the losses are already normalised by the GLOBAL batch, so SUM is exact

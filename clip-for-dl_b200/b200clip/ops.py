@@ -147,20 +147,21 @@ def proj_fwd(x_bf16, w1_bf16, b1, w2_bf16, b2, gamma, beta, want_yhat: bool):
     return y, yhat, inv, (p, h, z, mean, rstd)
 
 
-def proj_bwd(dy, x_bf16, w1_bf16, w2_bf16, gamma, saved, need_dx: bool):
+def proj_bwd(dy, x_bf16, w1_bf16, w2_bf16, gamma, saved, need_dx: bool, dx_dtype=torch.float32):
     p, h, z, mean, rstd = saved
     B, E = x_bf16.shape
     D = w1_bf16.shape[0]
     dev = x_bf16.device
     dy = _f32c(dy)
-    dx = torch.empty((B, E), dtype=torch.float32, device=dev) if need_dx else None
+    dx_bf = need_dx and dx_dtype == torch.bfloat16
+    dx = torch.empty((B, E), dtype=torch.bfloat16 if dx_bf else torch.float32, device=dev) if need_dx else None
     dw1 = torch.empty((D, E), dtype=torch.float32, device=dev)
     dw2 = torch.empty((D, D), dtype=torch.float32, device=dev)
     db1, db2, dg, dbeta = (torch.empty((D,), dtype=torch.float32, device=dev) for _ in range(4))
     nb = load().b200clip_proj_bwd_workspace_bytes(B, E, D)
     ws = _ws(nb, dev)
     check(load().b200clip_proj_bwd(ptr(dy), ptr(x_bf16), B, E, D, ptr(w1_bf16), ptr(w2_bf16), ptr(gamma), ptr(p), ptr(h), ptr(z),
-                                   ptr(mean), ptr(rstd), ptr(dx), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dg), ptr(dbeta),
+                                   ptr(mean), ptr(rstd), ptr(None if dx_bf else dx), ptr(dx if dx_bf else None), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dg), ptr(dbeta),
                                    ptr(ws), ws.numel(), stream_ptr()), "proj_bwd")
     return dx, dw1, db1, dw2, db2, dg, dbeta
 
@@ -183,8 +184,9 @@ class ProjectionFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         xb, w1b, w2b, gamma, p, h, z, mean, rstd = ctx.saved_tensors
-        dx, dw1, db1, dw2, db2, dg, dbeta = proj_bwd(dy, xb, w1b, w2b, gamma, (p, h, z, mean, rstd), ctx.need_dx)
-        if dx is not None and ctx.x_dtype != torch.float32:
+        dx, dw1, db1, dw2, db2, dg, dbeta = proj_bwd(dy, xb, w1b, w2b, gamma, (p, h, z, mean, rstd), ctx.need_dx,
+                                                     torch.bfloat16 if ctx.x_dtype == torch.bfloat16 else torch.float32)
+        if dx is not None and dx.dtype != ctx.x_dtype:
             dx = dx.to(ctx.x_dtype)
         return dx, dw1, db1, dw2, db2, dg, dbeta
 
@@ -426,6 +428,30 @@ class LinearSmallFn(torch.autograd.Function):
             raise RuntimeError("b200clip: input gradient of the stand-alone adapter Linear is not implemented; "
                                "use fc_adapter_bce (fused) or freeze the encoder as NB02 c28:54-62 does")
         return dx, dw, (db if ctx.has_bias else None)
+
+
+def bce_heads(image_features, class_text, fc_weight, fc_bias, labels, temperature, *, label_sum, total_elems_text,
+              total_elems_fc, grad_scale=None, dx_accum=None, want_coef=False, finalize=True):
+    """Both BCE heads (a-B on the class texts + a-A FC adapter) in one pass over the image features."""
+    lib = load()
+    x, t, w = _f32c(image_features), _f32c(class_text), _f32c(fc_weight)
+    b = _f32c(fc_bias) if fc_bias is not None else None
+    y = _f32c(labels)
+    B, D = x.shape
+    c1, c2 = t.shape[0], w.shape[0]
+    dev = x.device
+    coef = torch.empty((B, c2), dtype=torch.float32, device=dev) if want_coef else None
+    sums = torch.empty((3,), dtype=torch.float64, device=dev)
+    l_text = torch.empty((), dtype=torch.float32, device=dev) if finalize else None
+    l_fc = torch.empty((), dtype=torch.float32, device=dev) if finalize else None
+    status = torch.zeros((), dtype=torch.int32, device=dev) if finalize else None
+    ws = _ws(lib.b200clip_smallc_workspace_bytes(B, c1 + c2, D), dev)
+    gs = _f32c(grad_scale.reshape(())) if grad_scale is not None else None
+    check(lib.b200clip_bce_heads_fwd_bwd(ptr(x), x.stride(0), ptr(t), c1, ptr(w), ptr(b), c2, ptr(y), y.shape[1], y.stride(0), B, D,
+                                         float(temperature), ptr(label_sum), float(total_elems_text), float(total_elems_fc),
+                                         ptr(gs), ptr(dx_accum), int(dx_accum is not None), ptr(coef), ptr(sums), ptr(l_text),
+                                         ptr(l_fc), ptr(status), ptr(ws), ws.numel(), stream_ptr()), "bce_heads_fwd_bwd")
+    return l_text, l_fc, status, sums, coef
 
 
 # --------------------------------------------------------------------------------------------------------------

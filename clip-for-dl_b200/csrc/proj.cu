@@ -53,8 +53,8 @@ extern "C" size_t b200clip_proj_bwd_workspace_bytes(long long B, int E, int D) {
 
 extern "C" int b200clip_proj_bwd(const float* dy, const void* x_bf16, long long B, int E, int D, const void* w1_bf16,
                                  const void* w2_bf16, const float* gamma, const void* p_bf16, const void* h_bf16,
-                                 const float* z_f32, const float* mean, const float* rstd, float* dx_f32, float* dw1,
-                                 float* db1, float* dw2, float* db2, float* dgamma, float* dbeta, void* workspace,
+                                 const float* z_f32, const float* mean, const float* rstd, float* dx_f32, void* dx_bf16,
+                                 float* dw1, float* db1, float* dw2, float* db2, float* dgamma, float* dbeta, void* workspace,
                                  size_t workspace_bytes, void* stream) {
   B200_REQUIRE(B > 0 && E % 8 == 0 && D % 128 == 0 && D <= 1024, "proj_bwd: bad shape B=%lld E=%d D=%d", B, E, D);
   if (workspace_bytes < b200clip_proj_bwd_workspace_bytes(B, E, D)) return fail(B200_ERR_WORKSPACE, "proj_bwd: workspace too small");
@@ -69,9 +69,8 @@ extern "C" int b200clip_proj_bwd(const float* dy, const void* x_bf16, long long 
   const size_t cs_ws = b200clip_colsum_workspace_bytes(B, D);
   void* cs_work = carve(cs_ws);
 
-  int rc = b200clip_layernorm_bwd(dy, z_f32, mean, rstd, gamma, dz, dz_bf, dgamma, dbeta, 0, B, D, ln_work, ln_ws, stream);
+  int rc = b200clip_layernorm_bwd(dy, z_f32, mean, rstd, gamma, dz, dz_bf, dgamma, dbeta, db2, 0, B, D, ln_work, ln_ws, stream);
   if (rc) return rc;
-  if ((rc = b200clip_colsum(dz, 0, D, B, D, db2, 0, cs_work, cs_ws, stream))) return rc;
   // dW2[o][j] = sum_b dz[b][o] h[b][j]
   B200_CHECK_CUDA(cudaMemsetAsync(dw2, 0, static_cast<size_t>(D) * D * 4, s));
   if ((rc = gemm_bf16(dz_bf, h_bf16, 1, 1, D, D, (int)B, D, D, EPI_ATOMIC_F32, 1.0f, dw2, D, nullptr, 0, nullptr, nullptr, 0,
@@ -87,10 +86,10 @@ extern "C" int b200clip_proj_bwd(const float* dy, const void* x_bf16, long long 
   if ((rc = gemm_bf16(dp_bf, x_bf16, 1, 1, D, E, (int)B, D, E, EPI_ATOMIC_F32, 1.0f, dw1, E, nullptr, 0, nullptr, nullptr, 0,
                       nullptr, 0, split_for(D, E, (int)B), s)))
     return rc;
-  if (dx_f32) {
+  if (dx_f32 || dx_bf16) {                         // input gradient in the caller's dtype (bf16 inputs get bf16 grads directly)
     B200_REQUIRE(E % 32 == 0, "proj_bwd: dx needs E %% 32 == 0");
-    if ((rc = gemm_bf16(dp_bf, w1_bf16, 0, 1, (int)B, E, D, D, E, EPI_STORE_F32, 1.0f, dx_f32, E, nullptr, 0, nullptr, nullptr,
-                        0, nullptr, 0, 1, s)))
+    if ((rc = gemm_bf16(dp_bf, w1_bf16, 0, 1, (int)B, E, D, D, E, dx_f32 ? EPI_STORE_F32 : EPI_STORE_BF16, 1.0f,
+                        dx_f32 ? static_cast<void*>(dx_f32) : dx_bf16, E, nullptr, 0, nullptr, nullptr, 0, nullptr, 0, 1, s)))
       return rc;
   }
   return B200_OK;

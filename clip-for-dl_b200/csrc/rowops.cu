@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_fwd_kernel(const float*
   }
 }
 
-// LayerNorm backward: dz = rstd * (g*dy - mean(g*dy) - zhat * mean(g*dy*zhat)); per-block partial dgamma/dbeta.
+// LayerNorm backward: dz = rstd * (g*dy - mean(g*dy) - zhat * mean(g*dy*zhat)); per-block partial dgamma/dbeta and
+// column sums of dz (the bias gradient of the Linear feeding the residual sum), reduced by reduce_partials_kernel.
 // Outputs dz both as f32 (residual branch + bias grads) and bf16 (operand of the dW2 / dh GEMMs).
 template <int MAX_V>
 __global__ void __launch_bounds__(ROW_THREADS) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
@@ -170,15 +171,15 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_bwd_kernel(const float*
                                                                     const float* __restrict__ gamma,
                                                                     float* __restrict__ dz_f32,
                                                                     __nv_bfloat16* __restrict__ dz_bf16,
-                                                                    float* __restrict__ partial /*[grid][2][D]*/, int rows,
+                                                                    float* __restrict__ partial /*[grid][3][D]*/, int rows,
                                                                     int D) {
   __shared__ float red[ROW_THREADS / 32][128];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nv = D >> 7;
-  float4 dg[MAX_V], db[MAX_V];
+  float4 dg[MAX_V], db[MAX_V], dzs[MAX_V];
 #pragma unroll
-  for (int i = 0; i < MAX_V; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < MAX_V; ++i) dg[i] = db[i] = dzs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long row = blockIdx.x * (ROW_THREADS / 32) + warp; row < rows;
        row += static_cast<long long>(gridDim.x) * (ROW_THREADS / 32)) {
     const float mu = mean[row], rs = rstd[row];
@@ -204,18 +205,19 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_bwd_kernel(const float*
       if (i < nv) {
         const float4 o = make_float4(rs * (g[i].x - s1 - zh[i].x * s2), rs * (g[i].y - s1 - zh[i].y * s2),
                                      rs * (g[i].z - s1 - zh[i].z * s2), rs * (g[i].w - s1 - zh[i].w * s2));
+        dzs[i].x += o.x; dzs[i].y += o.y; dzs[i].z += o.z; dzs[i].w += o.w;
         if (dz_f32) st4(dz_f32 + row * D + i * 128 + lane * 4, o);
         if (dz_bf16) st4(dz_bf16 + row * D + i * 128 + lane * 4, o);
       }
   }
   // block reduction of the per-warp dgamma/dbeta partials, one 128-column slab at a time
-  float* pg = partial + static_cast<long long>(blockIdx.x) * 2 * D;
-  for (int which = 0; which < 2; ++which) {
+  float* pg = partial + static_cast<long long>(blockIdx.x) * 3 * D;
+  for (int which = 0; which < 3; ++which) {
     for (int i = 0; i < nv; ++i) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < MAX_V; ++k)
-        if (k == i) v = which == 0 ? dg[k] : db[k];
+        if (k == i) v = which == 0 ? dg[k] : (which == 1 ? db[k] : dzs[k]);
       __syncthreads();
       *reinterpret_cast<float4*>(&red[warp][lane * 4]) = v;
       __syncthreads();
@@ -229,29 +231,65 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_bwd_kernel(const float*
   }
 }
 
-// out[n] (+)= sum over `nparts` rows of partial[part][n]  (final stage of the two-stage column reductions)
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, long long part_stride, int nparts,
-                                       float* __restrict__ out, int n, int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// out_k[i] (+)= sum over `nparts` rows of partial[part][k*seg + i]   (final stage of the two-stage column reductions)
+// Block = 32 columns x 8 row-slices: coalesced 128-B reads, the 8 slices are folded through shared memory.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, long long part_stride,
+                                                              int nparts, int n, int seg, float* __restrict__ out0,
+                                                              float* __restrict__ out1, float* __restrict__ out2,
+                                                              int accumulate) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
   float acc = 0.f;
-  for (int p = 0; p < nparts; ++p) acc += partial[p * part_stride + i];
-  out[i] = accumulate ? out[i] + acc : acc;
+  if (col < n)
+    for (int p = sl; p < nparts; p += 8) acc += partial[p * part_stride + col];
+  red[sl][cx] = acc;
+  __syncthreads();
+  if (sl == 0 && col < n) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += red[k][cx];
+    const int which = col / seg, i = col - which * seg;
+    float* o = which == 0 ? out0 : (which == 1 ? out1 : out2);
+    if (o) o[i] = accumulate ? o[i] + v : v;
+  }
 }
 
-// column sums of a [rows, N] matrix (bias gradients): stage 1, each block owns a row slab and all N columns.
-template <typename T>
-__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ a, long long lda, int rows, int N,
-                                                             int rows_per_block, float* __restrict__ partial) {
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = min(rows, r0 + rows_per_block);
-  for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = r0; r < r1; ++r) {
-      const float4 v = ld4(a + static_cast<long long>(r) * lda + c);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+// column sums of a [rows, N] matrix (bias gradients), stage 1: warp per row, lanes across columns (128-bit loads),
+// per-lane register accumulators, block fold through shared memory -> partial[block][N]
+template <typename T, int MAX_V>
+__global__ void __launch_bounds__(ROW_THREADS) colsum_rows_kernel(const T* __restrict__ a, long long lda, int rows, int N,
+                                                                  float* __restrict__ partial) {
+  __shared__ float red[ROW_THREADS / 32][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = N >> 7;
+  float4 acc[MAX_V];
+#pragma unroll
+  for (int i = 0; i < MAX_V; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row = blockIdx.x * (ROW_THREADS / 32) + warp; row < rows;
+       row += static_cast<long long>(gridDim.x) * (ROW_THREADS / 32)) {
+#pragma unroll
+    for (int i = 0; i < MAX_V; ++i)
+      if (i < nv) {
+        const float4 v = ld4(a + row * lda + i * 128 + lane * 4);
+        acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
+      }
+  }
+  float* pg = partial + static_cast<long long>(blockIdx.x) * N;
+  for (int i = 0; i < nv; ++i) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < MAX_V; ++k)
+      if (k == i) v = acc[k];
+    __syncthreads();
+    *reinterpret_cast<float4*>(&red[warp][lane * 4]) = v;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < ROW_THREADS / 32; ++w) t += red[w][threadIdx.x];
+      pg[i * 128 + threadIdx.x] = t;
     }
-    st4(partial + static_cast<long long>(blockIdx.x) * N + c, acc);
   }
 }
 
@@ -261,6 +299,11 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16
     st4(out + i * 4, ld4(in + i * 4));
 }
 
+static inline int part_grid(long long rows) {      // kernels that emit per-block partials: keep the partial count small
+  const long long want = (rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
+  const long long cap = static_cast<long long>(num_sms()) * 2;
+  return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+}
 static inline int row_grid(long long rows) {
   const long long want = (rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
   const long long cap = static_cast<long long>(num_sms()) * 8;
@@ -318,48 +361,49 @@ extern "C" int b200clip_layernorm_fwd(const float* z, const float* gamma, const 
 }
 
 extern "C" size_t b200clip_layernorm_bwd_workspace_bytes(long long rows, int D) {
-  return static_cast<size_t>(row_grid(rows)) * 2 * D * sizeof(float);
+  return static_cast<size_t>(part_grid(rows)) * 3 * D * sizeof(float);
 }
 
 extern "C" int b200clip_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd,
                                       const float* gamma, float* dz_f32, void* dz_bf16, float* dgamma, float* dbeta,
-                                      int accumulate_params, long long rows, int D, void* workspace,
+                                      float* dz_colsum, int accumulate_params, long long rows, int D, void* workspace,
                                       size_t workspace_bytes, void* stream) {
   B200_REQUIRE(rows > 0 && D > 0 && D % 128 == 0 && D <= MAX_D, "layernorm_bwd: D=%d must be a multiple of 128, <= %d", D, MAX_D);
-  const int grid = row_grid(rows);
-  if (workspace_bytes < static_cast<size_t>(grid) * 2 * D * sizeof(float))
+  const int grid = part_grid(rows);
+  if (workspace_bytes < static_cast<size_t>(grid) * 3 * D * sizeof(float))
     return fail(B200_ERR_WORKSPACE, "layernorm_bwd: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
   B200_DISPATCH_V(D, (layernorm_bwd_kernel<MAX_V><<<grid, ROW_THREADS, 0, s>>>(
       dy, z, mean, rstd, gamma, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), partial, (int)rows, D)));
   B200_LAUNCH_CHECK();
-  reduce_partials_kernel<<<(D + 127) / 128, 128, 0, s>>>(partial, 2LL * D, grid, dgamma, D, accumulate_params);
-  B200_LAUNCH_CHECK();
-  reduce_partials_kernel<<<(D + 127) / 128, 128, 0, s>>>(partial + D, 2LL * D, grid, dbeta, D, accumulate_params);
+  reduce_partials_kernel<<<(3 * D + 31) / 32, 256, 0, s>>>(partial, 3LL * D, grid, 3 * D, D, dgamma, dbeta, dz_colsum,
+                                                         accumulate_params);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
 
 extern "C" size_t b200clip_colsum_workspace_bytes(long long rows, int N) {
-  const int rpb = 256;
-  return static_cast<size_t>((rows + rpb - 1) / rpb) * N * sizeof(float);
+  return static_cast<size_t>(part_grid(rows)) * N * sizeof(float) + 256;
 }
 
 extern "C" int b200clip_colsum(const void* a, int a_is_bf16, long long lda, long long rows, int N, float* out,
                                int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
-  B200_REQUIRE(rows > 0 && N > 0 && N % 4 == 0, "colsum: N=%d must be a multiple of 4", N);
-  const int rpb = 256;
-  const int nblk = static_cast<int>((rows + rpb - 1) / rpb);
-  if (workspace_bytes < static_cast<size_t>(nblk) * N * sizeof(float)) return fail(B200_ERR_WORKSPACE, "colsum: workspace too small");
+  B200_REQUIRE(rows > 0 && N > 0 && N % 128 == 0 && N <= 2048, "colsum: N=%d must be a multiple of 128, <= 2048", N);
+  B200_REQUIRE(aligned16(a) && lda % 8 == 0, "colsum: operand must be 16-byte aligned with lda %% 8 == 0");
+  const int grid = part_grid(rows);
+  if (workspace_bytes < static_cast<size_t>(grid) * N * sizeof(float)) return fail(B200_ERR_WORKSPACE, "colsum: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
-  if (a_is_bf16)
-    colsum_partial_kernel<__nv_bfloat16><<<nblk, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(a), lda, (int)rows, N, rpb, partial);
-  else
-    colsum_partial_kernel<float><<<nblk, 256, 0, s>>>(static_cast<const float*>(a), lda, (int)rows, N, rpb, partial);
+#define B200_COLSUM_LAUNCH(T, V) colsum_rows_kernel<T, V><<<grid, ROW_THREADS, 0, s>>>(static_cast<const T*>(a), lda, (int)rows, N, partial)
+  if (a_is_bf16) {
+    if (N <= 512) B200_COLSUM_LAUNCH(__nv_bfloat16, 4); else if (N <= 1024) B200_COLSUM_LAUNCH(__nv_bfloat16, 8); else B200_COLSUM_LAUNCH(__nv_bfloat16, 16);
+  } else {
+    if (N <= 512) B200_COLSUM_LAUNCH(float, 4); else if (N <= 1024) B200_COLSUM_LAUNCH(float, 8); else B200_COLSUM_LAUNCH(float, 16);
+  }
+#undef B200_COLSUM_LAUNCH
   B200_LAUNCH_CHECK();
-  reduce_partials_kernel<<<(N + 127) / 128, 128, 0, s>>>(partial, N, nblk, out, N, accumulate);
+  reduce_partials_kernel<<<(N + 31) / 32, 256, 0, s>>>(partial, N, grid, N, N, out, nullptr, nullptr, accumulate);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

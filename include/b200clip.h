@@ -50,8 +50,9 @@ int b200clip_layernorm_fwd(const float* z, const float* gamma, const float* beta
                            void* stream);
 size_t b200clip_layernorm_bwd_workspace_bytes(long long rows, int D);
 int b200clip_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
-                           float* dz_f32, void* dz_bf16, float* dgamma, float* dbeta, int accumulate_params,
-                           long long rows, int D, void* workspace, size_t workspace_bytes, void* stream);
+                           float* dz_f32, void* dz_bf16, float* dgamma, float* dbeta, float* dz_colsum,
+                           int accumulate_params, long long rows, int D, void* workspace, size_t workspace_bytes,
+                           void* stream);
 size_t b200clip_colsum_workspace_bytes(long long rows, int N);
 int b200clip_colsum(const void* a, int a_is_bf16, long long lda, long long rows, int N, float* out, int accumulate,
                     void* workspace, size_t workspace_bytes, void* stream);
@@ -68,8 +69,8 @@ int b200clip_proj_fwd(const void* x_bf16, long long B, int E, int D, const void*
 size_t b200clip_proj_bwd_workspace_bytes(long long B, int E, int D);
 int b200clip_proj_bwd(const float* dy, const void* x_bf16, long long B, int E, int D, const void* w1_bf16,
                       const void* w2_bf16, const float* gamma, const void* p_bf16, const void* h_bf16, const float* z_f32,
-                      const float* mean, const float* rstd, float* dx_f32, float* dw1, float* db1, float* dw2, float* db2,
-                      float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
+                      const float* mean, const float* rstd, float* dx_f32, void* dx_bf16, float* dw1, float* db1, float* dw2,
+                      float* db2, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a-N: contrastive_loss(image_features, text_features, temperature) -- 0426/train.py:154-176 ----------------
  * Inputs are L2-normalised bf16 rows.  Data-parallel form: i_hat = this rank's rows [b_loc, D] (global rows
@@ -110,6 +111,15 @@ int b200clip_fc_bce_fwd_bwd(const float* x, long long ldx, const float* weight, 
 int b200clip_skinny_outer(const float* coef, int C, const float* x, long long ldx, const float* row_scale, long long rows,
                           int D, float* out_w, float* out_b, int accumulate, void* workspace, size_t workspace_bytes,
                           void* stream);
+
+/* a-B + a-A fused for the head step: one pass over the image features serves both BCE heads (classes [0,c1) = class
+ * texts, [c1,c1+c2) = FC adapter rows).  sums[3] = {text pos numerator, text neg numerator, FC BCE sum}. */
+int b200clip_bce_heads_fwd_bwd(const float* image_features, long long ldx, const float* text_features, int c1,
+                               const float* fc_weight, const float* fc_bias, int c2, const float* labels, int label_cols,
+                               long long ld_labels, long long B, int D, float temperature, const float* label_sum,
+                               double total_elems_text, double total_elems_fc, const float* grad_scale, float* d_image,
+                               int d_image_accumulate, float* fc_coef, double* sums, float* loss_text, float* loss_fc,
+                               int* status, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a-M: predict_multilabel(image_features, text_features, threshold) -- 0426/train.py:869-886 ---------------- */
 int b200clip_predict_multilabel(const float* image_features, long long ldx, const float* text_features, long long B,

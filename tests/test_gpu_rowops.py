@@ -60,19 +60,20 @@ def test_layernorm_fwd_bwd(rows, D):
     assert rel_l2(inv, 1.0 / yref.norm(dim=-1)) < 1e-6
     dz = torch.empty_like(z)
     dzb = torch.empty(rows, D, dtype=torch.bfloat16, device=d)
-    dg, db = torch.empty(D, device=d), torch.empty(D, device=d)
+    dg, db, dzs = torch.empty(D, device=d), torch.empty(D, device=d), torch.empty(D, device=d)
     nb = lib.b200clip_layernorm_bwd_workspace_bytes(rows, D)
     ws = torch.empty(nb, dtype=torch.uint8, device=d)
     _lib.check(lib.b200clip_layernorm_bwd(_lib.ptr(dy), _lib.ptr(z), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma),
-                                          _lib.ptr(dz), _lib.ptr(dzb), _lib.ptr(dg), _lib.ptr(db), 0, rows, D, _lib.ptr(ws), nb,
+                                          _lib.ptr(dz), _lib.ptr(dzb), _lib.ptr(dg), _lib.ptr(db), _lib.ptr(dzs), 0, rows, D, _lib.ptr(ws), nb,
                                           _lib.stream_ptr()), "lnb")
     assert rel_l2(dz, zr.grad) < 1e-5
     assert rel_l2(dzb.float(), zr.grad) < 4e-3
     assert rel_l2(dg, gr.grad) < 1e-5
     assert rel_l2(db, br.grad) < 1e-5
+    assert rel_l2(dzs, zr.grad.sum(0)) < 1e-4
 
 
-@pytest.mark.parametrize("rows,N,bf16", [(1000, 512, False), (257, 768, True), (5, 16, False)])
+@pytest.mark.parametrize("rows,N,bf16", [(1000, 512, False), (257, 768, True), (5, 128, False), (40000, 512, True), (300, 2048, False)])
 def test_colsum(rows, N, bf16):
     from b200clip import _lib
     lib = _lib.load()
