@@ -1,0 +1,82 @@
+"""Data-parallel choreography of the CLIP head: the collectives and the algebra that combines
+per-rank partial results.  Device-agnostic on purpose: the same functions run over NCCL on B200s (head.py, ops.py) and
+over gloo on CPU tensors in tests/test_dp_gloo.py, where the test supplies the per-rank arithmetic.
+
+  rank r owns rows [r*B/W, (r+1)*B/W) of images and texts
+  fwd: gather_rows(T_hat)  ->  local row block of logits vs all columns  ->  sum_across(column sum-exp partials)
+       -> sum_across(3 loss scalars)
+  bwd: dI_hat complete locally; dT_hat partial [B, D] -> scatter_sum_rows ; allreduce_flat(parameter gradients)
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world(group=None) -> int:
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def rank(group=None) -> int:
+    return dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
+
+
+def gather_rows(local: torch.Tensor, group=None, async_op: bool = False):
+    """all_gather along dim 0 (contiguous rank order).  Returns (full, work-or-None)."""
+    W = world(group)
+    if W == 1:
+        return local, None
+    full = torch.empty((local.shape[0] * W, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    work = dist.all_gather_into_tensor(full, local.contiguous(), group=group, async_op=async_op)
+    return full, (work if async_op else None)
+
+
+def sum_across(t: torch.Tensor, group=None) -> torch.Tensor:
+    if world(group) > 1:
+        dist.all_reduce(t, group=group)
+    return t
+
+
+def scatter_sum_rows(full: torch.Tensor, group=None, async_op: bool = False):
+    """reduce_scatter(SUM) along dim 0: every rank contributes a [B, ...] partial and keeps its own row block."""
+    W = world(group)
+    if W == 1:
+        return full, None
+    n = full.shape[0] // W
+    if dist.get_backend(group) == "gloo":                 # gloo has no reduce_scatter: all_reduce + slice (tests only)
+        dist.all_reduce(full, group=group)
+        r = rank(group)
+        return full[r * n:(r + 1) * n].contiguous(), None
+    out = torch.empty((n, *full.shape[1:]), dtype=full.dtype, device=full.device)
+    work = dist.reduce_scatter_tensor(out, full.contiguous(), group=group, async_op=async_op)
+    return out, (work if async_op else None)
+
+
+def allreduce_flat(tensors: Sequence[torch.Tensor], group=None) -> List[torch.Tensor]:
+    """One bucket for all head parameter gradients (~2 M floats): SUM is exact because every loss term is already
+    normalised by the GLOBAL batch."""
+    if world(group) == 1:
+        return list(tensors)
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, group=group)
+    out, o = [], 0
+    for t in tensors:
+        out.append(flat[o:o + t.numel()].view_as(t))
+        o += t.numel()
+    return out
+
+
+def infonce_loss_from_sums(sums: torch.Tensor, temperature: float, b_glob: int) -> torch.Tensor:
+    """sums = [sum_i log r_i, sum_j log c_j, sum_i S_ii] (already summed over ranks); fixed shift m = 1/tau."""
+    return (1.0 / temperature + (sums[0] + sums[1]) / (2.0 * b_glob) - sums[2] / b_glob).to(torch.float32)
+
+
+def bce_losses_from_sums(sums: torch.Tensor, label_sum: torch.Tensor, total_text: float, total_fc: float):
+    """sums = [text pos numerator, text neg numerator, FC BCE sum] summed over ranks (0426/train.py:218-221)."""
+    P = label_sum.double()
+    N = total_text - P
+    l_text = (0.5 * (-sums[0] / (P + 1e-8) - sums[1] / (N + 1e-8))).float()
+    l_fc = (sums[2] / total_fc).float()
+    return l_text, l_fc

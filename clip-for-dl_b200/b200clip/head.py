@@ -21,18 +21,13 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from . import ops
+from . import dp, ops
 from .modules import MODEL_CONFIG, ClassificationAdapter, ImageProjection, TextProjection
 
 PARAM_ORDER = ("iw1", "ib1", "iw2", "ib2", "ig", "ibeta", "tw1", "tb1", "tw2", "tb2", "tg", "tbeta", "fw", "fb")
 
 
-def _world(group) -> int:
-    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-
-
-def _rank(group) -> int:
-    return dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
+_world, _rank = dp.world, dp.rank
 
 
 class ClipHeadFn(torch.autograd.Function):
@@ -49,16 +44,12 @@ class ClipHeadFn(torch.autograd.Function):
         f = ops._f32c
         # text first so its all-gather can overlap the image projection
         y_txt, that_loc, inv_txt, saved_t = ops.proj_fwd(xt, tw1b, f(tb1), tw2b, f(tb2), f(tg), f(tbeta), want_yhat=True)
-        if W > 1:
-            that_all = torch.empty((b_glob, that_loc.shape[1]), dtype=torch.bfloat16, device=that_loc.device)
-            work = dist.all_gather_into_tensor(that_all, that_loc, group=group, async_op=True)
-        else:
-            that_all, work = that_loc, None
+        that_all, work = dp.gather_rows(that_loc, group, async_op=True)
         y_img, ihat, inv_img, saved_i = ops.proj_fwd(xi, iw1b, f(ib1), iw2b, f(ib2), f(ig), f(ibeta), want_yhat=True)
         labels_f = f(labels)
         lsum = ops._label_sum(labels_f)
         if W > 1:
-            dist.all_reduce(lsum, group=group)
+            dp.sum_across(lsum, group)
             work.wait()
         l_nce, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, group=group if W > 1 else None)
         C = class_text.shape[0]
@@ -67,11 +58,8 @@ class ClipHeadFn(torch.autograd.Function):
                                                      total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
                                                      finalize=(W == 1))
         if W > 1:
-            dist.all_reduce(both, group=group)
-            P = lsum.double()
-            N = float(b_glob) * C - P
-            l_bce = (0.5 * (-both[0] / (P + 1e-8) - both[1] / (N + 1e-8))).float()
-            l_fc = (both[2] / (float(b_glob) * Cf)).float()
+            dp.sum_across(both, group)
+            l_bce, l_fc = dp.bce_losses_from_sums(both, lsum, float(b_glob) * C, float(b_glob) * Cf)
         loss = l_nce + l_bce + l_fc
         ctx.save_for_backward(xi, xt, iw1b, iw2b, tw1b, tw2b, f(ig), f(tg), f(class_text), labels_f, lsum, y_img, y_txt, ihat,
                               that_all, inv_img, inv_txt, rinvh, cinvh, f(fw), f(fb) if fb is not None else None,
@@ -90,11 +78,7 @@ class ClipHeadFn(torch.autograd.Function):
         C = class_text.shape[0]
         g = ops._f32c(g)
         d_ihat, d_that = ops.infonce_backward(ihat, that_all, tau_nce, rinvh, cinvh, g, row0=row0)
-        if W > 1:
-            d_that_loc = torch.empty((b_loc, d_that.shape[1]), dtype=torch.float32, device=d_that.device)
-            work = dist.reduce_scatter_tensor(d_that_loc, d_that, group=group, async_op=True)
-        else:
-            d_that_loc, work = d_that, None
+        d_that_loc, work = dp.scatter_sum_rows(d_that, group, async_op=True)
         # image side: through the L2 normalisation, then add the two BCE heads' gradients (they act on y_img itself)
         dy_img = ops.l2norm_bwd(d_ihat, y_img, inv_img)
         *_, coef = ops.bce_heads(y_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
@@ -107,15 +91,7 @@ class ClipHeadFn(torch.autograd.Function):
         dy_txt = ops.l2norm_bwd(d_that_loc, y_txt, inv_txt)
         gt = ops.proj_bwd(dy_txt, xt, tw1b, tw2b, tg, saved_t, need_dxt, ctx.in_dtypes[1])
         grads = [gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], gt[1], gt[2], gt[3], gt[4], gt[5], gt[6], dfw, dfb]
-        if W > 1:
-            # DDP-style: average is NOT taken -- the losses are already normalised by the GLOBAL batch, so SUM is exact
-            flat = torch.cat([t.reshape(-1) for t in grads])
-            dist.all_reduce(flat, group=group)
-            out, o = [], 0
-            for t in grads:
-                out.append(flat[o:o + t.numel()].view_as(t))
-                o += t.numel()
-            grads = out
+        grads = dp.allreduce_flat(grads, group)     # SUM, not mean: every loss term is normalised by the GLOBAL batch
         return (gi[0], gt[0], None, None, None, None, None, *grads)
 
 

@@ -10,7 +10,7 @@ from typing import Optional, Sequence, Tuple
 
 import torch
 
-from . import _lib
+from . import _lib, dp
 from ._lib import check, load, ptr, require_cuda, stream_ptr
 
 LN_EPS = 1e-5          # nn.LayerNorm default (0426/train.py:82)
@@ -213,11 +213,9 @@ def infonce_forward(i_hat: torch.Tensor, t_hat: torch.Tensor, temperature: float
     if ev is not None:
         e1.record()
         ev.append((e0, e1))
-    world = 1
-    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized() and b_loc != b_glob):
-        world = torch.distributed.get_world_size(group)
+    world = dp.world(group) if (group is not None or b_loc != b_glob) else 1
     if world > 1:
-        torch.distributed.all_reduce(c, group=group)          # partial column sums -> global
+        dp.sum_across(c, group)                               # partial column sums -> global
     rinvh = torch.empty_like(r)
     cinvh = torch.empty_like(c)
     sums = torch.empty((3,), dtype=torch.float64, device=dev)
@@ -227,8 +225,7 @@ def infonce_forward(i_hat: torch.Tensor, t_hat: torch.Tensor, temperature: float
                                     ptr(rinvh), ptr(cinvh), ptr(sums), ptr(loss) if world == 1 else None, ptr(ws), ws.numel(),
                                     stream_ptr()), "infonce_loss")
     if world > 1:
-        torch.distributed.all_reduce(sums, group=group)
-        loss = (1.0 / temperature + (sums[0] + sums[1]) / (2.0 * b_glob) - sums[2] / b_glob).to(torch.float32)
+        loss = dp.infonce_loss_from_sums(dp.sum_across(sums, group), temperature, b_glob)
     return loss, rinvh, cinvh
 
 
