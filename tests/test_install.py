@@ -1,0 +1,51 @@
+"""Drop-in installation: install() rebinds the names the reference looks up as module globals; module
+state_dict keys/shapes equal the reference's so its checkpoints load.  When /root/reference is present (build container)
+the real reference module is patched and its own state_dict is loaded into the replacement."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+import b200clip
+
+
+def test_install_patches_module_globals():
+    fake = types.ModuleType("train")
+    for n in ("ImageProjection", "TextProjection", "contrastive_loss", "multilabel_contrastive_loss", "predict_multilabel"):
+        setattr(fake, n, object())
+    fake.unrelated = 1
+    b200clip.install(fake)
+    assert fake.ImageProjection is b200clip.ImageProjection and fake.TextProjection is b200clip.TextProjection
+    assert fake.contrastive_loss is b200clip.contrastive_loss
+    assert fake.multilabel_contrastive_loss is b200clip.multilabel_contrastive_loss
+    assert fake.predict_multilabel is b200clip.predict_multilabel
+    assert fake.unrelated == 1 and not hasattr(fake, "predict_zero_shot")
+
+
+def test_signatures_match_reference_defaults():
+    import inspect
+    sig = inspect.signature(b200clip.contrastive_loss)
+    assert list(sig.parameters) == ["image_features", "text_features", "temperature"] and sig.parameters["temperature"].default == 1.0
+    sig = inspect.signature(b200clip.multilabel_contrastive_loss)
+    assert list(sig.parameters)[:4] == ["image_features", "text_features", "labels", "temperature"]
+    sig = inspect.signature(b200clip.predict_multilabel)
+    assert list(sig.parameters) == ["image_features", "text_features", "threshold"] and sig.parameters["threshold"].default == 0.5
+    sig = inspect.signature(b200clip.predict_zero_shot)
+    assert list(sig.parameters)[:6] == ["images", "models", "disease_list", "top_k", "prompts", "use_enhanced_prompts"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/0426"), reason="reference only exists in the build container")
+def test_reference_checkpoint_keys_load(tmp_path):
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    from make_golden import import_reference
+    ref = import_reference("0426")
+    ref_img, ref_txt = ref.ImageProjection(2048, 512), ref.TextProjection(768, 512)
+    b200clip.install(ref)
+    assert ref.ImageProjection is b200clip.ImageProjection
+    mine_img, mine_txt = ref.ImageProjection(2048, 512), ref.TextProjection(768, 512)      # built through the patched globals
+    assert {k: tuple(v.shape) for k, v in mine_img.state_dict().items()} == {k: tuple(v.shape) for k, v in ref_img.state_dict().items()}
+    mine_img.load_state_dict(ref_img.state_dict())                                          # strict load of a reference checkpoint
+    mine_txt.load_state_dict(ref_txt.state_dict())
+    assert torch.equal(mine_img.fc.weight, ref_img.fc.weight)
