@@ -153,6 +153,14 @@ __device__ __forceinline__ void mbar_wait_cluster_a(uint32_t bar_addr, uint32_t 
     if (++spins > (1u << 24)) mbar_watchdog_fire(bar_addr, parity);
   }
 }
+// asynchronous 16-byte store into (possibly remote) cluster shared memory; completion is signalled as 16 tx-bytes on the
+// mbarrier at `cluster_bar` (which must live in the same CTA as the destination).  Performed by the async proxy: a
+// consumer that observed the barrier phase can feed the data to TMA / tcgen05.mma without a proxy fence.
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint4 v, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_bar)
+               : "memory");
+}
 // tcgen05.commit that arrives on the barrier at the same offset in every CTA of `cta_mask`
 __device__ __forceinline__ void tc_commit_multicast_a(uint32_t bar_addr, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
