@@ -272,14 +272,9 @@ constexpr int BWD_TB = 3;                   // ring B depth in tiles (the 4 Y K-
 constexpr int BWD_SLOT_BYTES = BWD_BN * 128;            // one [32 x 64] bf16 chunk
 constexpr int BWD_GROUP_BYTES = 4 * BWD_SLOT_BYTES;     // 4 chunks = half a Y tile
 constexpr int BWD_G_BYTES = 128 * 128;      // [128 rows x 64 bf16]: even tiles use K cols 0-31, odd tiles 32-63
-constexpr int BWD3_TA = 3;                  // version 3 rings (X in-half lives in TMEM): 3 A groups, 6 B groups
-constexpr int BWD3_TB = 6;
 constexpr int BWD4_TA = 3;                  // version 4: 3 A groups, 5 B groups, two G buffers
 constexpr int BWD4_TB = 5;
 constexpr int BWD_THREADS = 384;            // warp 0 TMA, 1 S-MMA issuer, 2 TMEM alloc + dX-MMA issuer, 3 idle, 4-11 epilogue
-constexpr int nce_bwd3_smem_bytes() {
-  return 4 * X_CHUNK_BYTES + (BWD3_TA + BWD3_TB) * BWD_GROUP_BYTES + BWD_G_BYTES + 512 + 1024;
-}
 constexpr int nce_bwd4_smem_bytes() {
   return 4 * X_CHUNK_BYTES + (BWD4_TA + BWD4_TB) * BWD_GROUP_BYTES + 2 * BWD_G_BYTES + 512 + 1024;
 }
@@ -561,635 +556,30 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pass 2, cluster version: the two D-half CTAs of a row block form a CTA pair (cluster 1x2x1).
-// Column tile n is OWNED by CTA (n & 1): only the owner recomputes S and forms G for it, and writes the bf16 G tile
-// into BOTH CTAs' shared memory (local st.shared + st.shared::cluster), so each logit is exponentiated once per
-// direction instead of once per D-half.  Every CTA still runs the dX MMA for every tile on its own D-half.
-//   executed tensor work per direction: S once (2 B^2 D) + dX (2 B^2 D)   (was 2x S + dX)
-// Y traffic per CTA: the in-half K-chunks of every tile (ring B) + the out-of-half chunks of its own tiles (ring A).
-// Cross-CTA protocol for G half-buffer p (= owner's rank): g_full[p] in each CTA counts the 128 producer threads
-// (remote ones arrive with release.cluster); g_empty[p] counts 2 = one multicast tcgen05.commit from each CTA's dX issuer.
-// ------------------------------------------------------------------------------------------------
-__global__ void __cluster_dims__(1, 2, 1) __launch_bounds__(BWD_THREADS, 1)
-nce_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constant__ CUtensorMap tmap_y0,
-                const __grid_constant__ CUtensorMap tmap_x1, const __grid_constant__ CUtensorMap tmap_y1,
-                const NceBwdParams p) {
-  const int dir = blockIdx.z;
-  const int h = blockIdx.y;                         // D-half owned by this CTA == rank in the pair
-  const int rb = blockIdx.x;
-  const int nrows = dir ? p.nrows[1] : p.nrows[0];
-  const int ncols = dir ? p.ncols[1] : p.ncols[0];
-  if (rb * 128 >= nrows) return;                    // uniform over the whole cluster (same rb), before any barrier
-  const CUtensorMap* tmap_x = dir == 0 ? &tmap_x0 : &tmap_x1;
-  const CUtensorMap* tmap_y = dir == 0 ? &tmap_y0 : &tmap_y1;
-  const uint32_t peer = static_cast<uint32_t>(h ^ 1);
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sX = smem;
-  uint8_t* sA = sX + NCE_KC * X_CHUNK_BYTES;
-  uint8_t* sB = sA + BWD_TA * BWD_GROUP_BYTES;
-  uint8_t* sG = sB + BWD_TB * BWD_GROUP_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + BWD_G_BYTES);
-  uint64_t* x_full = bars;                          // 1
-  uint64_t* a_full = bars + 1;                      // TA
-  uint64_t* a_empty = a_full + BWD_TA;              // TA
-  uint64_t* b_full = a_empty + BWD_TA;              // TB
-  uint64_t* b_empty = b_full + BWD_TB;              // TB
-  uint64_t* s_full = b_empty + BWD_TB;              // 2
-  uint64_t* s_empty = s_full + 2;                   // 2
-  uint64_t* g_full = s_empty + 2;                   // 2 (indexed by owner rank)
-  uint64_t* g_empty = g_full + 2;                   // 4: [owner rank][own-tile parity] (see the note at the wait)
-  uint64_t* acc_full = g_empty + 4;                 // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int nt = (ncols + BWD_BN - 1) / BWD_BN;     // all tiles
-  const int nown = (nt - h + 1) / 2;                // tiles owned by this CTA: n = 2m + h
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(tmap_x);
-    tma_prefetch_desc(tmap_y);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(x_full, 1);
-    for (int s = 0; s < BWD_TA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < BWD_TB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], 128);
-      mbar_init(&g_full[b], 128);
-    }
-    for (int b = 0; b < 4; ++b) mbar_init(&g_empty[b], 2);   // one multicast commit from each CTA of the pair
-    mbar_init(acc_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  cluster_sync_all();                               // barrier inits visible to the peer before any remote arrive
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_acc = tmem_base;
-  const uint32_t tmem_s = tmem_base + 256;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    const uint32_t xf = smem_u32(x_full);
-    const uint32_t af0 = smem_u32(a_full), ae0 = smem_u32(a_empty), bf0 = smem_u32(b_full), be0 = smem_u32(b_empty);
-    const uint32_t sa = smem_u32(sA), sb = smem_u32(sB), sx = smem_u32(sX);
-    if (elect_one()) {
-      mbar_arrive_expect_tx_a(xf, NCE_KC * X_CHUNK_BYTES);
-#pragma unroll
-      for (int kc = 0; kc < NCE_KC; ++kc) tma_load_2d_a(sx + kc * X_CHUNK_BYTES, tmap_x, xf, kc * 64, rb * 128);
-    }
-    __syncwarp();
-    int ia = 0, ib = 0;
-    uint32_t pa = 0, pb = 0;
-    const int k_in = h * 256, k_out = (1 - h) * 256;
-    for (int n = 0; n < nt; ++n) {
-      mbar_wait_a(be0 + 8 * ib, pb ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx_a(bf0 + 8 * ib, BWD_GROUP_BYTES);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          tma_load_2d_a(sb + ib * BWD_GROUP_BYTES + c * BWD_SLOT_BYTES, tmap_y, bf0 + 8 * ib, k_in + c * 64, n * BWD_BN);
-      }
-      __syncwarp();
-      if (++ib == BWD_TB) { ib = 0; pb ^= 1; }
-      if ((n & 1) == h) {
-        mbar_wait_a(ae0 + 8 * ia, pa ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx_a(af0 + 8 * ia, BWD_GROUP_BYTES);
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            tma_load_2d_a(sa + ia * BWD_GROUP_BYTES + c * BWD_SLOT_BYTES, tmap_y, af0 + 8 * ia, k_out + c * 64, n * BWD_BN);
-        }
-        __syncwarp();
-        if (++ia == BWD_TA) { ia = 0; pa ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== S-MMA issuer (own tiles only) =====================
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, BWD_BN, false, false);
-    const uint32_t af0 = smem_u32(a_full), ae0 = smem_u32(a_empty), bf0 = smem_u32(b_full);
-    const uint32_t sf0 = smem_u32(s_full), se0 = smem_u32(s_empty);
-    const uint32_t x_in = desc_lo(smem_u32(sX) + h * 4 * X_CHUNK_BYTES, 16);
-    const uint32_t x_out = desc_lo(smem_u32(sX) + (1 - h) * 4 * X_CHUNK_BYTES, 16);
-    const uint32_t a_lo0 = desc_lo(smem_u32(sA), 16), b_lo0 = desc_lo(smem_u32(sB), 16);
-    mbar_wait_a(smem_u32(x_full), 0);
-    int ia = 0;
-    uint32_t pa = 0;
-    // ring B position of tile n: slot n % TB, phase (n / TB) & 1 -- tracked incrementally over ALL tiles
-    int ib = 0;
-    uint32_t pb = 0;
-    if (h == 1) { ib = 1 % BWD_TB; }                 // first own tile is n = 1
-    for (int m = 0; m < nown; ++m) {
-      const int buf = m & 1;
-      mbar_wait_a(se0 + 8 * buf, ((m >> 1) & 1) ^ 1);
-      mbar_wait_a(bf0 + 8 * ib, pb);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_s + buf * BWD_BN;
-      if (elect_one()) {
-        const uint32_t yb = b_lo0 + ib * (BWD_GROUP_BYTES >> 4);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            mma_ss_lo(d_tmem, x_in + c * (X_CHUNK_BYTES >> 4) + 2 * j, yb + c * (BWD_SLOT_BYTES >> 4) + 2 * j, idesc_s, (c | j) != 0);
-      }
-      __syncwarp();
-      mbar_wait_a(af0 + 8 * ia, pa);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t ya = a_lo0 + ia * (BWD_GROUP_BYTES >> 4);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            mma_ss_lo(d_tmem, x_out + c * (X_CHUNK_BYTES >> 4) + 2 * j, ya + c * (BWD_SLOT_BYTES >> 4) + 2 * j, idesc_s, true);
-        tc_commit_a(ae0 + 8 * ia);
-        tc_commit_a(sf0 + 8 * buf);
-      }
-      __syncwarp();
-      if (++ia == BWD_TA) { ia = 0; pa ^= 1; }
-      // advance the ring-B cursor by two tiles
-#pragma unroll
-      for (int t = 0; t < 2; ++t)
-        if (++ib == BWD_TB) { ib = 0; pb ^= 1; }
-    }
-  } else if (warp == 2) {
-    // ===================== dX-MMA issuer (every tile, this CTA's D-half) =====================
-    constexpr uint32_t idesc_g = make_idesc_bf16(128, 256, false, true);
-    const uint32_t gf0 = smem_u32(g_full), ge0 = smem_u32(g_empty), be0 = smem_u32(b_empty), bf0 = smem_u32(b_full);
-    const uint32_t g_lo = desc_lo(smem_u32(sG), 16);
-    const uint32_t y_lo0 = desc_lo(smem_u32(sB), BWD_SLOT_BYTES);
-    int ib = 0;
-    uint32_t pb = 0;
-    for (int n = 0; n < nt; ++n) {
-      const int par = n & 1;
-      mbar_wait_a(bf0 + 8 * ib, pb);                // tiles owned by the peer were never waited on by the S issuer
-      mbar_wait_cluster_a(gf0 + 8 * par, (n >> 1) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t yb = y_lo0 + ib * (BWD_GROUP_BYTES >> 4);
-#pragma unroll
-        for (int jj = 0; jj < BWD_BN / 16; ++jj)
-          mma_ss_lo(tmem_acc, g_lo + par * 4 + jj * 2, yb + jj * (2048 >> 4), idesc_g, (n | jj) != 0);
-        tc_commit_a(be0 + 8 * ib);
-        // both CTAs' g_empty[par][own-tile parity]: the owner may refill G half `par` once BOTH CTAs have read it
-        tc_commit_multicast_a(ge0 + 8 * (par * 2 + ((n >> 1) & 1)), 0x3);
-      }
-      __syncwarp();
-      if (++ib == BWD_TB) { ib = 0; pb ^= 1; }
-    }
-    if (elect_one()) tc_commit(acc_full);
-    __syncwarp();
-  } else if (warp >= 4) {
-    // ===================== epilogue warpgroups: own tile m -> warpgroup m & 1 =====================
-    const int w = (warp - 4) >> 2;
-    const int q = warp & 3;
-    const int row_l = q * 32 + lane;
-    const int row = rb * 128 + row_l;
-    const bool row_ok = row < nrows;
-    const float rstat = row_ok ? (dir ? p.row_stat[1] : p.row_stat[0])[row] : 0.f;
-    const float* cstat = dir ? p.col_stat[1] : p.col_stat[0];
-    const int diag_col = row + (dir ? p.diag_off[1] : p.diag_off[0]);
-    const int warp_diag_lo = rb * 128 + q * 32 + (dir ? p.diag_off[1] : p.diag_off[0]);
-    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t sf = smem_u32(s_full) + 8 * w, se = smem_u32(s_empty) + 8 * w;
-    const uint32_t gf = smem_u32(g_full) + 8 * h, ge = smem_u32(g_empty) + 8 * (2 * h);
-    const uint32_t gf_peer = mapa_u32(gf, peer);
-    const uint32_t g_row = smem_u32(sG) + row_l * 128;
-    const uint32_t g_row_peer = mapa_u32(g_row, peer);
-    uint32_t ph = 0;
-    for (int m = w; m < nown; m += 2) {
-      const int n = 2 * m + h;
-      const int col0 = n * BWD_BN;
-      const bool full_tile = col0 + BWD_BN <= ncols;
-      const bool diag_tile = (col0 < warp_diag_lo + 32) && (col0 + BWD_BN > warp_diag_lo);
-      float cs[32];
-      if (full_tile) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 c4 = __ldg(reinterpret_cast<const float4*>(cstat + col0 + i));
-          cs[i] = c4.x; cs[i + 1] = c4.y; cs[i + 2] = c4.z; cs[i + 3] = c4.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) cs[i] = (col0 + i < ncols) ? cstat[col0 + i] : 0.f;
-      }
-      mbar_wait_a(sf, ph);
-      tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_x32(tmem_s + lane_base + w * BWD_BN, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive_a(se);
-      uint32_t packed[16];
-      if (full_tile && !diag_tile) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float g0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.k1, -p.k2)) * (rstat + cs[i]);
-          const float g1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.k1, -p.k2)) * (rstat + cs[i + 1]);
-          packed[i / 2] = pack_bf16x2(g0, g1);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float g[2];
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int col = col0 + i + t;
-            float gv = fast_exp2(fmaf(__uint_as_float(v[i + t]), p.k1, -p.k2)) * (rstat + cs[i + t]);
-            if (col == diag_col) gv -= 1.0f;
-            g[t] = (col < ncols) ? gv : 0.f;
-          }
-          packed[i / 2] = pack_bf16x2(g[0], g[1]);
-        }
-      }
-      // G half-buffer h is reused by every own tile: wait until BOTH CTAs' dX MMAs of own tile m-1 have read it.
-      // Consumption of own tile m' is signalled on g_empty[h][m' & 1]; this warpgroup (m & 1 == w) therefore always
-      // waits on the OTHER parity's barrier and sees its completions one by one (a single shared barrier would let a
-      // warpgroup that runs ahead observe a stale phase -- parity aliasing).
-      if (m > 0) mbar_wait_cluster_a(ge + 8 * ((m - 1) & 1), ((m - 1) >> 1) & 1);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t off = static_cast<uint32_t>(((h * 4 + c) ^ (row_l & 7)) << 4);
-        const uint4 val = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(g_row + off), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
-        st_cluster_v4(g_row_peer + off, val);
-      }
-      fence_proxy_async_all();                      // generic-proxy writes (local + peer smem) -> async proxy (tcgen05.mma)
-      mbar_arrive_a(gf);
-      mbar_arrive_cluster_a(gf_peer);
-      ph ^= 1;
-    }
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    float scale = p.out_scale;
-    if (p.grad_scale) scale *= *p.grad_scale;
-    float* orow = (dir ? p.out[1] : p.out[0]) + static_cast<long long>(row) * NCE_D + h * 256 + w * 128;
-#pragma unroll 1
-    for (int c = 0; c < 128; c += 32) {
-      uint32_t v[32];
-      tmem_ld_x32(tmem_acc + lane_base + w * 128 + c, v);
-      tmem_ld_wait();
-      if (row_ok) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(orow + c + i) =
-              make_float4(__uint_as_float(v[i]) * scale, __uint_as_float(v[i + 1]) * scale,
-                          __uint_as_float(v[i + 2]) * scale, __uint_as_float(v[i + 3]) * scale);
-      }
-    }
-  }
-
-  tc_fence_before();
-  cluster_sync_all();                               // the peer may still be writing into / arriving on this CTA's smem
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Pass 2, cluster version 3 (= version 2 + the in-half K range of X resident in TMEM as the A operand of the S MMA,
-// which frees 64 KB of shared memory for a 6-tile ring B / 3-group ring A: the pipeline is latency-bound on ring depth).
-// Pass 2, cluster version: the two D-half CTAs of a row block form a CTA pair (cluster 1x2x1).
-// Column tile n is OWNED by CTA (n & 1): only the owner recomputes S and forms G for it, and writes the bf16 G tile
-// into BOTH CTAs' shared memory (local st.shared + st.shared::cluster), so each logit is exponentiated once per
-// direction instead of once per D-half.  Every CTA still runs the dX MMA for every tile on its own D-half.
-//   executed tensor work per direction: S once (2 B^2 D) + dX (2 B^2 D)   (was 2x S + dX)
-// Y traffic per CTA: the in-half K-chunks of every tile (ring B) + the out-of-half chunks of its own tiles (ring A).
-// Cross-CTA protocol for G half-buffer p (= owner's rank): g_full[p] in each CTA counts the 128 producer threads
-// (remote ones arrive with release.cluster); g_empty[p] counts 2 = one multicast tcgen05.commit from each CTA's dX issuer.
-// ------------------------------------------------------------------------------------------------
-__global__ void __cluster_dims__(1, 2, 1) __launch_bounds__(BWD_THREADS, 1)
-nce_bwd3_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constant__ CUtensorMap tmap_y0,
-                const __grid_constant__ CUtensorMap tmap_x1, const __grid_constant__ CUtensorMap tmap_y1,
-                const NceBwdParams p) {
-  const int dir = blockIdx.z;
-  const int h = blockIdx.y;                         // D-half owned by this CTA == rank in the pair
-  const int rb = blockIdx.x;
-  const int nrows = dir ? p.nrows[1] : p.nrows[0];
-  const int ncols = dir ? p.ncols[1] : p.ncols[0];
-  if (rb * 128 >= nrows) return;                    // uniform over the whole cluster (same rb), before any barrier
-  const CUtensorMap* tmap_x = dir == 0 ? &tmap_x0 : &tmap_x1;
-  const CUtensorMap* tmap_y = dir == 0 ? &tmap_y0 : &tmap_y1;
-  const uint32_t peer = static_cast<uint32_t>(h ^ 1);
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sX = smem;
-  uint8_t* sA = sX + 4 * X_CHUNK_BYTES;             // sX holds only the OUT-of-half K range of X (4 chunks)
-  uint8_t* sB = sA + BWD3_TA * BWD_GROUP_BYTES;
-  uint8_t* sG = sB + BWD3_TB * BWD_GROUP_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + BWD_G_BYTES);
-  uint64_t* x_full = bars;                          // 1
-  uint64_t* a_full = bars + 1;                      // TA
-  uint64_t* a_empty = a_full + BWD3_TA;              // TA
-  uint64_t* b_full = a_empty + BWD3_TA;              // TB
-  uint64_t* b_empty = b_full + BWD3_TB;              // TB
-  uint64_t* s_full = b_empty + BWD3_TB;              // 2
-  uint64_t* s_empty = s_full + 2;                   // 2
-  uint64_t* g_full = s_empty + 2;                   // 2 (indexed by owner rank)
-  uint64_t* g_empty = g_full + 2;                   // 4: [owner rank][own-tile parity] (see the note at the wait)
-  uint64_t* acc_full = g_empty + 4;                 // 1
-  uint64_t* xt_full = acc_full + 1;                 // 1: X in-half range stored to TMEM by warpgroup 0
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xt_full + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int nt = (ncols + BWD_BN - 1) / BWD_BN;     // all tiles
-  const int nown = (nt - h + 1) / 2;                // tiles owned by this CTA: n = 2m + h
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(tmap_x);
-    tma_prefetch_desc(tmap_y);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(x_full, 1);
-    for (int s = 0; s < BWD3_TA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < BWD3_TB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], 128);
-      mbar_init(&g_full[b], 128);
-    }
-    for (int b = 0; b < 4; ++b) mbar_init(&g_empty[b], 2);   // one multicast commit from each CTA of the pair
-    mbar_init(acc_full, 1);
-    mbar_init(xt_full, 128);
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  cluster_sync_all();                               // barrier inits visible to the peer before any remote arrive
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_acc = tmem_base;
-  const uint32_t tmem_s = tmem_base + 256;          // 2 x 32 columns
-  const uint32_t tmem_x = tmem_base + 320;          // 128 columns: X[:, h*256 .. +256) as packed bf16 pairs
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    const uint32_t xf = smem_u32(x_full);
-    const uint32_t af0 = smem_u32(a_full), ae0 = smem_u32(a_empty), bf0 = smem_u32(b_full), be0 = smem_u32(b_empty);
-    const uint32_t sa = smem_u32(sA), sb = smem_u32(sB), sx = smem_u32(sX);
-    if (elect_one()) {
-      mbar_arrive_expect_tx_a(xf, 4 * X_CHUNK_BYTES);
-#pragma unroll
-      for (int kc = 0; kc < 4; ++kc) tma_load_2d_a(sx + kc * X_CHUNK_BYTES, tmap_x, xf, (1 - h) * 256 + kc * 64, rb * 128);
-    }
-    __syncwarp();
-    int ia = 0, ib = 0;
-    uint32_t pa = 0, pb = 0;
-    const int k_in = h * 256, k_out = (1 - h) * 256;
-    for (int n = 0; n < nt; ++n) {
-      mbar_wait_a(be0 + 8 * ib, pb ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx_a(bf0 + 8 * ib, BWD_GROUP_BYTES);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          tma_load_2d_a(sb + ib * BWD_GROUP_BYTES + c * BWD_SLOT_BYTES, tmap_y, bf0 + 8 * ib, k_in + c * 64, n * BWD_BN);
-      }
-      __syncwarp();
-      if (++ib == BWD3_TB) { ib = 0; pb ^= 1; }
-      if ((n & 1) == h) {
-        mbar_wait_a(ae0 + 8 * ia, pa ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx_a(af0 + 8 * ia, BWD_GROUP_BYTES);
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            tma_load_2d_a(sa + ia * BWD_GROUP_BYTES + c * BWD_SLOT_BYTES, tmap_y, af0 + 8 * ia, k_out + c * 64, n * BWD_BN);
-        }
-        __syncwarp();
-        if (++ia == BWD3_TA) { ia = 0; pa ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== S-MMA issuer (own tiles only) =====================
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, BWD_BN, false, false);
-    const uint32_t af0 = smem_u32(a_full), ae0 = smem_u32(a_empty), bf0 = smem_u32(b_full);
-    const uint32_t sf0 = smem_u32(s_full), se0 = smem_u32(s_empty);
-    const uint32_t x_out = desc_lo(smem_u32(sX), 16);
-    const uint32_t a_lo0 = desc_lo(smem_u32(sA), 16), b_lo0 = desc_lo(smem_u32(sB), 16);
-    mbar_wait_a(smem_u32(x_full), 0);
-    mbar_wait_a(smem_u32(xt_full), 0);
-    tc_fence_after();
-    int ia = 0;
-    uint32_t pa = 0;
-    // ring B position of tile n: slot n % TB, phase (n / TB) & 1 -- tracked incrementally over ALL tiles
-    int ib = 0;
-    uint32_t pb = 0;
-    if (h == 1) { ib = 1 % BWD3_TB; }                 // first own tile is n = 1
-    for (int m = 0; m < nown; ++m) {
-      const int buf = m & 1;
-      mbar_wait_a(se0 + 8 * buf, ((m >> 1) & 1) ^ 1);
-      mbar_wait_a(bf0 + 8 * ib, pb);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_s + buf * BWD_BN;
-      if (elect_one()) {
-        const uint32_t yb = b_lo0 + ib * (BWD_GROUP_BYTES >> 4);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            mma_ts_lo(d_tmem, tmem_x + c * 32 + j * 8, yb + c * (BWD_SLOT_BYTES >> 4) + 2 * j, idesc_s, (c | j) != 0);
-      }
-      __syncwarp();
-      mbar_wait_a(af0 + 8 * ia, pa);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t ya = a_lo0 + ia * (BWD_GROUP_BYTES >> 4);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            mma_ss_lo(d_tmem, x_out + c * (X_CHUNK_BYTES >> 4) + 2 * j, ya + c * (BWD_SLOT_BYTES >> 4) + 2 * j, idesc_s, true);
-        tc_commit_a(ae0 + 8 * ia);
-        tc_commit_a(sf0 + 8 * buf);
-      }
-      __syncwarp();
-      if (++ia == BWD3_TA) { ia = 0; pa ^= 1; }
-      // advance the ring-B cursor by two tiles
-#pragma unroll
-      for (int t = 0; t < 2; ++t)
-        if (++ib == BWD3_TB) { ib = 0; pb ^= 1; }
-    }
-  } else if (warp == 2) {
-    // ===================== dX-MMA issuer (every tile, this CTA's D-half) =====================
-    constexpr uint32_t idesc_g = make_idesc_bf16(128, 256, false, true);
-    const uint32_t gf0 = smem_u32(g_full), ge0 = smem_u32(g_empty), be0 = smem_u32(b_empty), bf0 = smem_u32(b_full);
-    const uint32_t g_lo = desc_lo(smem_u32(sG), 16);
-    const uint32_t y_lo0 = desc_lo(smem_u32(sB), BWD_SLOT_BYTES);
-    int ib = 0;
-    uint32_t pb = 0;
-    for (int n = 0; n < nt; ++n) {
-      const int par = n & 1;
-      mbar_wait_a(bf0 + 8 * ib, pb);                // tiles owned by the peer were never waited on by the S issuer
-      mbar_wait_cluster_a(gf0 + 8 * par, (n >> 1) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t yb = y_lo0 + ib * (BWD_GROUP_BYTES >> 4);
-#pragma unroll
-        for (int jj = 0; jj < BWD_BN / 16; ++jj)
-          mma_ss_lo(tmem_acc, g_lo + par * 4 + jj * 2, yb + jj * (2048 >> 4), idesc_g, (n | jj) != 0);
-        tc_commit_a(be0 + 8 * ib);
-        // both CTAs' g_empty[par][own-tile parity]: the owner may refill G half `par` once BOTH CTAs have read it
-        tc_commit_multicast_a(ge0 + 8 * (par * 2 + ((n >> 1) & 1)), 0x3);
-      }
-      __syncwarp();
-      if (++ib == BWD3_TB) { ib = 0; pb ^= 1; }
-    }
-    if (elect_one()) tc_commit(acc_full);
-    __syncwarp();
-  } else if (warp >= 4) {
-    // ===================== epilogue warpgroups: own tile m -> warpgroup m & 1 =====================
-    const int w = (warp - 4) >> 2;
-    const int q = warp & 3;
-    const int row_l = q * 32 + lane;
-    const int row = rb * 128 + row_l;
-    const bool row_ok = row < nrows;
-    const float rstat = row_ok ? (dir ? p.row_stat[1] : p.row_stat[0])[row] : 0.f;
-    const float* cstat = dir ? p.col_stat[1] : p.col_stat[0];
-    const int diag_col = row + (dir ? p.diag_off[1] : p.diag_off[0]);
-    const int warp_diag_lo = rb * 128 + q * 32 + (dir ? p.diag_off[1] : p.diag_off[0]);
-    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t sf = smem_u32(s_full) + 8 * w, se = smem_u32(s_empty) + 8 * w;
-    const uint32_t gf = smem_u32(g_full) + 8 * h, ge = smem_u32(g_empty) + 8 * (2 * h);
-    const uint32_t gf_peer = mapa_u32(gf, peer);
-    const uint32_t g_row = smem_u32(sG) + row_l * 128;
-    const uint32_t g_row_peer = mapa_u32(g_row, peer);
-    if (w == 0) {
-      // X[row, h*256 .. +256) -> TMEM columns tmem_x .. +128 of this thread's lane (bf16 pairs, K ascending)
-      const uint4* xsrc = reinterpret_cast<const uint4*>((dir ? p.xmat[1] : p.xmat[0]) + static_cast<long long>(row_ok ? row : 0) * NCE_D + h * 256);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t xr[32];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 t = row_ok ? __ldg(xsrc + c * 8 + i) : make_uint4(0u, 0u, 0u, 0u);
-          xr[4 * i] = t.x; xr[4 * i + 1] = t.y; xr[4 * i + 2] = t.z; xr[4 * i + 3] = t.w;
-        }
-        tmem_st_x32(tmem_x + lane_base + c * 32, xr);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive_a(smem_u32(xt_full));
-    }
-    uint32_t ph = 0;
-    for (int m = w; m < nown; m += 2) {
-      const int n = 2 * m + h;
-      const int col0 = n * BWD_BN;
-      const bool full_tile = col0 + BWD_BN <= ncols;
-      const bool diag_tile = (col0 < warp_diag_lo + 32) && (col0 + BWD_BN > warp_diag_lo);
-      float cs[32];
-      if (full_tile) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 c4 = __ldg(reinterpret_cast<const float4*>(cstat + col0 + i));
-          cs[i] = c4.x; cs[i + 1] = c4.y; cs[i + 2] = c4.z; cs[i + 3] = c4.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) cs[i] = (col0 + i < ncols) ? cstat[col0 + i] : 0.f;
-      }
-      mbar_wait_a(sf, ph);
-      tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_x32(tmem_s + lane_base + w * BWD_BN, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive_a(se);
-      uint32_t packed[16];
-      if (full_tile && !diag_tile) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float g0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.k1, -p.k2)) * (rstat + cs[i]);
-          const float g1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.k1, -p.k2)) * (rstat + cs[i + 1]);
-          packed[i / 2] = pack_bf16x2(g0, g1);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float g[2];
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int col = col0 + i + t;
-            float gv = fast_exp2(fmaf(__uint_as_float(v[i + t]), p.k1, -p.k2)) * (rstat + cs[i + t]);
-            if (col == diag_col) gv -= 1.0f;
-            g[t] = (col < ncols) ? gv : 0.f;
-          }
-          packed[i / 2] = pack_bf16x2(g[0], g[1]);
-        }
-      }
-      // G half-buffer h is reused by every own tile: wait until BOTH CTAs' dX MMAs of own tile m-1 have read it.
-      // Consumption of own tile m' is signalled on g_empty[h][m' & 1]; this warpgroup (m & 1 == w) therefore always
-      // waits on the OTHER parity's barrier and sees its completions one by one (a single shared barrier would let a
-      // warpgroup that runs ahead observe a stale phase -- parity aliasing).
-      if (m > 0) mbar_wait_cluster_a(ge + 8 * ((m - 1) & 1), ((m - 1) >> 1) & 1);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t off = static_cast<uint32_t>(((h * 4 + c) ^ (row_l & 7)) << 4);
-        const uint4 val = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(g_row + off), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
-        st_cluster_v4(g_row_peer + off, val);
-      }
-      fence_proxy_async_cluster_smem();             // generic-proxy writes (local + peer smem) -> async proxy (tcgen05.mma)
-      mbar_arrive_a(gf);
-      mbar_arrive_cluster_a(gf_peer);
-      ph ^= 1;
-    }
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    float scale = p.out_scale;
-    if (p.grad_scale) scale *= *p.grad_scale;
-    float* orow = (dir ? p.out[1] : p.out[0]) + static_cast<long long>(row) * NCE_D + h * 256 + w * 128;
-#pragma unroll 1
-    for (int c = 0; c < 128; c += 32) {
-      uint32_t v[32];
-      tmem_ld_x32(tmem_acc + lane_base + w * 128 + c, v);
-      tmem_ld_wait();
-      if (row_ok) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(orow + c + i) =
-              make_float4(__uint_as_float(v[i]) * scale, __uint_as_float(v[i + 1]) * scale,
-                          __uint_as_float(v[i + 2]) * scale, __uint_as_float(v[i + 3]) * scale);
-      }
-    }
-  }
-
-  tc_fence_before();
-  cluster_sync_all();                               // the peer may still be writing into / arriving on this CTA's smem
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Pass 2, cluster version 4 (= version 3 + double-buffered G per owner, each epilogue warpgroup owning one slot, and the
-// G tile delivered to BOTH CTAs with st.async (async-proxy stores that complete tx-bytes on the consumer's mbarrier):
-// no generic->async proxy fences and no release.cluster arrivals on the critical S -> G -> dX chain).
-// Pass 2, cluster version 3 (= version 2 + the in-half K range of X resident in TMEM as the A operand of the S MMA,
-// which frees 64 KB of shared memory for a 6-tile ring B / 3-group ring A: the pipeline is latency-bound on ring depth).
-// Pass 2, cluster version: the two D-half CTAs of a row block form a CTA pair (cluster 1x2x1).
-// Column tile n is OWNED by CTA (n & 1): only the owner recomputes S and forms G for it, and writes the bf16 G tile
-// into BOTH CTAs' shared memory (local st.shared + st.shared::cluster), so each logit is exponentiated once per
-// direction instead of once per D-half.  Every CTA still runs the dX MMA for every tile on its own D-half.
-//   executed tensor work per direction: S once (2 B^2 D) + dX (2 B^2 D)   (was 2x S + dX)
-// Y traffic per CTA: the in-half K-chunks of every tile (ring B) + the out-of-half chunks of its own tiles (ring A).
-// Cross-CTA protocol for G half-buffer p (= owner's rank): g_full[p] in each CTA counts the 128 producer threads
-// (remote ones arrive with release.cluster); g_empty[p] counts 2 = one multicast tcgen05.commit from each CTA's dX issuer.
+// Pass 2, CTA-pair kernel (default).  The two D-half CTAs of a row block form a cluster (1x2x1).
+//  * Column tile n (32 columns) is OWNED by CTA (n & 1): only the owner recomputes S and forms G for it, so each logit is
+//    exponentiated once per direction instead of once per D-half (executed tensor work per direction: S once + dX).
+//  * The owner's epilogue warpgroup w = (own tile index & 1) owns G slot (owner, w) in BOTH CTAs and delivers the bf16
+//    tile with st.async: async-proxy stores that complete tx-bytes on the consumer CTA's g_full mbarrier, so no
+//    generic->async proxy fence and no release.cluster arrive sit on the S -> G -> dX critical chain.
+//  * g_full[slot]: 1 arming arrival (the local dX issuer) + 128 x 64 B of tx; g_empty[slot]: one multicast tcgen05.commit
+//    from each CTA's dX issuer (the slot may be refilled once BOTH CTAs have read it).  One barrier per slot and one
+//    waiter per barrier: every waiter sees consecutive phases (a barrier shared by two producers aliases parities).
+//  * The in-half K range of X lives in TMEM as the A operand of the S MMA (tcgen05.mma TS form): frees 64 KB of shared
+//    memory for a 5-tile ring B / 3-group ring A -- the S -> G -> dX -> free-slot pipeline is bound by ring depth.
+//  * Y traffic per CTA: in-half K-chunks of every tile (ring B, also the MN-major B operand of the dX MMA) + out-of-half
+//    chunks of its own tiles (ring A).
+// TMEM: acc [0,256) | S 2 x 32 [256,320) | X in-half K range [320,448).
+// Experiments that lost (kept in git history): 64-column tiles with a bulk DSMEM copy of G (4.85 ms vs 4.42 ms at
+// B=32768: rings too shallow), pairing own tiles / splitting the dX accumulator to interleave independent accumulators.
 // ------------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(1, 2, 1) __launch_bounds__(BWD_THREADS, 1)
 nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constant__ CUtensorMap tmap_y0,
                 const __grid_constant__ CUtensorMap tmap_x1, const __grid_constant__ CUtensorMap tmap_y1,
                 const NceBwdParams p) {
   const int dir = blockIdx.z;
-  const int h = blockIdx.y;                         // D-half owned by this CTA == rank in the pair
+  int h;                                            // D-half owned by this CTA == rank in the pair; read once (volatile asm:
+  asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(h));   // the compiler otherwise re-reads the special register in the tile loop)
   const int rb = blockIdx.x;
   const int nrows = dir ? p.nrows[1] : p.nrows[0];
   const int ncols = dir ? p.ncols[1] : p.ncols[0];
@@ -1694,23 +1084,16 @@ extern "C" int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D,
   p.grad_scale = grad_scale;
   constexpr int smem = nce_bwd_smem_bytes();
   static bool configured = false;
-  static int variant = 4;            // 4: v3 + double-buffered G via st.async; 3: CTA pair + X half in TMEM; 2: CTA pair; 1: independent CTAs
+  static int variant = 4;            // 4: CTA-pair kernel (default); 1: independent D-half CTAs (B200CLIP_BWD_VARIANT=1)
   if (!configured) {
-    if (const char* e = getenv("B200CLIP_BWD_VARIANT")) variant = atoi(e);
-    if (variant < 1 || variant > 4) variant = 4;
+    if (const char* e = getenv("B200CLIP_BWD_VARIANT")) variant = atoi(e) == 1 ? 1 : 4;
     B200_CHECK_CUDA(cudaFuncSetAttribute(nce_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nce_bwd4_smem_bytes()));
-    B200_CHECK_CUDA(cudaFuncSetAttribute(nce_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nce_bwd3_smem_bytes()));
     B200_CHECK_CUDA(cudaFuncSetAttribute(nce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    B200_CHECK_CUDA(cudaFuncSetAttribute(nce_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   dim3 grid(static_cast<unsigned>((b_glob + 127) / 128), 2, 2);
   if (variant == 4)
     nce_bwd4_kernel<<<grid, BWD_THREADS, nce_bwd4_smem_bytes(), static_cast<cudaStream_t>(stream)>>>(tx0, ty0, tx1, ty1, p);
-  else if (variant == 3)
-    nce_bwd3_kernel<<<grid, BWD_THREADS, nce_bwd3_smem_bytes(), static_cast<cudaStream_t>(stream)>>>(tx0, ty0, tx1, ty1, p);
-  else if (variant == 2)
-    nce_bwd2_kernel<<<grid, BWD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tx0, ty0, tx1, ty1, p);
   else
     nce_bwd_kernel<<<grid, BWD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tx0, ty0, tx1, ty1, p);
   B200_LAUNCH_CHECK();
