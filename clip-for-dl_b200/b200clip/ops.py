@@ -490,7 +490,8 @@ def zeroshot_score(x_bf16: torch.Tensor, prompts_bf16: torch.Tensor, *, pair_mod
     L = np_ // 2 if pair_mode else np_
     dev = x_bf16.device
     if guard is None:
-        guard = 1e-4 / temperature
+        # fp32 (HMMA) accumulation error of a cosine is ~1e-6; re-evaluate in fp64 inside 2e-5 (on the cosine scale)
+        guard = 2e-5 / temperature
     thr_arr = None
     if want_mask:
         if thresholds is None:

@@ -18,7 +18,7 @@
 namespace b200 {
 
 constexpr int ZS_D = 512;
-constexpr int ZS_THREADS = 256;
+
 constexpr int ZS_MAXP = 32;
 
 struct ZsParams {
@@ -103,54 +103,113 @@ __device__ void emit_row_fp64(const ZsParams& p, long long row, const double* sc
   }
 }
 
-__global__ void __launch_bounds__(ZS_THREADS, 2) zeroshot_kernel(const ZsParams p) {
+constexpr int ZS_CONSUMERS = 12;                        // consumer warps (3 per SM sub-partition); the last warp is the bulk-copy producer
+constexpr int ZS_THREADS2 = (ZS_CONSUMERS + 1) * 32;
+constexpr int ZS_PITCH = ZS_D * 2;                      // dense rows: ONE 16 KB bulk copy per block (small copies cost ~75 clk each)
+constexpr int ZS_STAGE_BYTES = 16 * ZS_PITCH;           // one 16-row block
+constexpr int ZS_STAGES = 12;
+// a consumer may hold a claim at most ZS_CONSUMERS-1 blocks ahead of the oldest unconsumed block; with fewer stages than
+// consumers a claim could be two fills ahead of its stage's barrier and the parity wait would alias
+static_assert(ZS_STAGES >= ZS_CONSUMERS, "ring must have at least as many stages as consumer warps");
+constexpr int ZS_SMEM_BYTES = 16 * 4 * 32 * 16 + ZS_STAGES * ZS_STAGE_BYTES + 2 * ZS_STAGES * 8 + 128;
+
+__device__ __forceinline__ void bulk_load_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// Rows are staged by a producer warp with asynchronous bulk copies (one 16 KB copy per 16-row block) into
+// a 10-stage ring, so ~160 KB of loads are in flight per SM independent of the consumers' registers and occupancy;
+// the 8 consumer warps take 16-row blocks round-robin and read their MMA fragments from the padded rows.
+__global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams p) {
+  extern __shared__ __align__(128) uint8_t zs_smem[];
   // prompt fragments in consumption order: frag[(s*4 + t)*32 + lane] = P[8t + lane/4][32s + 8(lane%4) .. +7]
-  __shared__ uint4 s_frag[16 * 4 * 32];
+  uint4* s_frag = reinterpret_cast<uint4*>(zs_smem);
+  uint8_t* ring = zs_smem + 16 * 4 * 32 * 16;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + ZS_STAGES * ZS_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + ZS_STAGES;
+  int* next_claim = reinterpret_cast<int*>(empty_bar + ZS_STAGES);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane & 3, r = lane >> 2;
-  for (int i = threadIdx.x; i < 16 * 4 * 32; i += ZS_THREADS) {
+  for (int i = threadIdx.x; i < 16 * 4 * 32; i += ZS_THREADS2) {
     const int l = i & 31, t = (i >> 5) & 3, s = i >> 7;
     const int n = 8 * t + (l >> 2), k0 = 32 * s + 8 * (l & 3);
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (n < p.np) v = *reinterpret_cast<const uint4*>(p.prompts + static_cast<long long>(n) * ZS_D + k0);
     s_frag[i] = v;
   }
+  if (threadIdx.x == 0) {
+    *next_claim = 0;
+    for (int s = 0; s < ZS_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    fence_mbar_init();
+  }
   __syncthreads();
 
   const long long nblocks16 = (p.n + 15) / 16;
   const int L = p.nlabels;
-  for (long long blk = static_cast<long long>(blockIdx.x) * (ZS_THREADS / 32) + warp; blk < nblocks16;
-       blk += static_cast<long long>(gridDim.x) * (ZS_THREADS / 32)) {
+  const uint32_t ring_a = smem_u32(ring), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+
+  if (warp == ZS_CONSUMERS) {
+    // ===================== producer =====================
+    int st = 0;
+    uint32_t ph = 0;
+    for (long long blk = blockIdx.x; blk < nblocks16; blk += gridDim.x) {
+      mbar_wait_a(empty_a + 8 * st, ph ^ 1);
+      const long long row0 = blk * 16;
+      const int valid = static_cast<int>(min(16ll, p.n - row0));
+      if (lane == 0) mbar_arrive_expect_tx_a(full_a + 8 * st, static_cast<uint32_t>(valid) * ZS_D * 2);
+      __syncwarp();
+      if (p.ldx == ZS_D) {
+        if (lane == 0)
+          bulk_load_g2s(ring_a + st * ZS_STAGE_BYTES, p.x + row0 * p.ldx, static_cast<uint32_t>(valid) * ZS_D * 2, full_a + 8 * st);
+      } else if (lane < valid) {
+        bulk_load_g2s(ring_a + st * ZS_STAGE_BYTES + lane * ZS_PITCH, p.x + (row0 + lane) * p.ldx, ZS_D * 2, full_a + 8 * st);
+      }
+      if (++st == ZS_STAGES) { st = 0; ph ^= 1; }
+    }
+    return;
+  }
+
+  // ===================== consumers: blocks are claimed dynamically (a warp busy with the rare fp64 re-evaluation must not
+  // stall the ring for the other seven); block i of this CTA lives in stage i % ZS_STAGES =====================
+  for (;;) {
+    long long it = 0;
+    if (lane == 0) it = atomicAdd(next_claim, 1);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    const long long blk = static_cast<long long>(blockIdx.x) + it * gridDim.x;
+    if (blk >= nblocks16) break;
+    const int st = static_cast<int>(it % ZS_STAGES);
+    const uint32_t ph = static_cast<uint32_t>((it / ZS_STAGES) & 1);
     const long long row_a = blk * 16 + r, row_b = row_a + 8;
     const bool ok_a = row_a < p.n, ok_b = row_b < p.n;
-    const uint4* pa = reinterpret_cast<const uint4*>(p.x + (ok_a ? row_a : 0) * p.ldx) + q;
-    const uint4* pb = reinterpret_cast<const uint4*>(p.x + (ok_b ? row_b : 0) * p.ldx) + q;
+    mbar_wait_a(full_a + 8 * st, ph);
+    const uint4* pa = reinterpret_cast<const uint4*>(ring + st * ZS_STAGE_BYTES + r * ZS_PITCH) + q;
+    const uint4* pb = reinterpret_cast<const uint4*>(ring + st * ZS_STAGE_BYTES + (r + 8) * ZS_PITCH) + q;
     float acc[4][4];
 #pragma unroll
     for (int t = 0; t < 4; ++t)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
     float ss_a = 0.f, ss_b = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < 16; ++s) {
+      const uint4 xa = ok_a ? pa[s * 4] : make_uint4(0u, 0u, 0u, 0u);
+      const uint4 xb = ok_b ? pb[s * 4] : make_uint4(0u, 0u, 0u, 0u);
+      ss_a += sumsq8(xa);
+      ss_b += sumsq8(xb);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint4 xa[8], xb[8];
-#pragma unroll
-      for (int s = 0; s < 8; ++s) {                       // 16 independent 128-bit loads in flight per lane
-        xa[s] = ok_a ? __ldg(pa + (half * 8 + s) * 4) : make_uint4(0u, 0u, 0u, 0u);
-        xb[s] = ok_b ? __ldg(pb + (half * 8 + s) * 4) : make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        ss_a += sumsq8(xa[s]);
-        ss_b += sumsq8(xb[s]);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const uint4 f = s_frag[((half * 8 + s) * 4 + t) * 32 + lane];
-          mma_bf16_16816(acc[t], xa[s].x, xb[s].x, xa[s].y, xb[s].y, f.x, f.y);
-          mma_bf16_16816(acc[t], xa[s].z, xb[s].z, xa[s].w, xb[s].w, f.z, f.w);
-        }
+      for (int t = 0; t < 4; ++t) {
+        const uint4 f = s_frag[(s * 4 + t) * 32 + lane];
+        mma_bf16_16816(acc[t], xa.x, xb.x, xa.y, xb.y, f.x, f.y);
+        mma_bf16_16816(acc[t], xa.z, xb.z, xa.w, xb.w, f.z, f.w);
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_a(empty_a + 8 * st);       // stage consumed (smem reads above are complete: values are in registers)
     // row norms: the 4 lanes of a quad hold disjoint K slices of rows r and r+8
     ss_a += __shfl_xor_sync(0xffffffffu, ss_a, 1); ss_a += __shfl_xor_sync(0xffffffffu, ss_a, 2);
     ss_b += __shfl_xor_sync(0xffffffffu, ss_b, 1); ss_b += __shfl_xor_sync(0xffffffffu, ss_b, 2);
@@ -319,8 +378,9 @@ __global__ void __launch_bounds__(ZS_THREADS, 2) zeroshot_kernel(const ZsParams 
       const double kk = (p.normalize_x ? 1.0 / fmax(sqrt(ss), 1e-12) : 1.0) * static_cast<double>(p.inv_tau);
       double l[ZS_MAXP];
       for (int c = 0; c < p.np; ++c) {
-        const uint4* pp = reinterpret_cast<const uint4*>(p.prompts + static_cast<long long>(c) * ZS_D) + lane * 2;
-        const uint4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+        // P[c][16*lane .. +16) from the fragment table: s = lane/2, 8-element groups 2*(lane&1) and 2*(lane&1)+1
+        const int fbase = ((lane >> 1) * 4 + (c >> 3)) * 32 + (c & 7) * 4 + (lane & 1) * 2;
+        const uint4 p0 = s_frag[fbase], p1 = s_frag[fbase + 1];
         const uint32_t pw[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
         double d = 0.0;
 #pragma unroll
@@ -367,9 +427,13 @@ extern "C" int b200clip_zeroshot_score(const void* x_bf16, long long ldx, long l
   p.argmax = argmax; p.mask = mask; p.mask_is_u32 = mask_is_u32; p.topk_idx = topk_idx; p.topk_val = topk_val;
   p.scores = scores; p.guard_count = guard_count;
   const long long nblk16 = (n + 15) / 16;
-  const long long want = (nblk16 + ZS_THREADS / 32 - 1) / (ZS_THREADS / 32);
-  const int grid = static_cast<int>(std::min<long long>(want, static_cast<long long>(num_sms()) * 2));
-  zeroshot_kernel<<<grid, ZS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const int grid = static_cast<int>(std::min<long long>(nblk16, static_cast<long long>(num_sms())));
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(zeroshot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ZS_SMEM_BYTES));
+    configured = true;
+  }
+  zeroshot_kernel<<<grid, ZS_THREADS2, ZS_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(p);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -1,0 +1,20 @@
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "clip-for-dl_b200"))
+from b200clip import ops
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(1234)
+N = 1_000_000
+X = torch.randn(N, 512, generator=g).to(torch.bfloat16).to(dev)
+P = torch.nn.functional.normalize(torch.randn(28, 512, generator=g), dim=1).to(torch.bfloat16).to(dev)
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+for guard in (None, 0.0):
+    for _ in range(3):
+        out = ops.zeroshot_score(X, P, pair_mode=True, temperature=0.07, thresholds=[0.5], guard=guard, count_guard=True)
+    tot = 0
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = ops.zeroshot_score(X, P, pair_mode=True, temperature=0.07, thresholds=[0.5], guard=guard, count_guard=True); e1.record()
+        torch.cuda.synchronize(); tot += e0.elapsed_time(e1)
+    print("guard", guard, "ms", tot / 10, "guard_rows", int(out["guard_rows"]))
