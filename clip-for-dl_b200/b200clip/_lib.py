@@ -24,14 +24,15 @@ SIGNATURES = {
     "b200clip_l2norm_bwd": (i32, [vp, vp, i32, ll, vp, vp, i32, ll, i32, f32, vp]),
     "b200clip_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, ll, i32, f32, f32, vp]),
     "b200clip_layernorm_bwd_workspace_bytes": (sz, [ll, i32]),
-    "b200clip_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, ll, i32, vp, sz, vp]),
+    "b200clip_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, ll, i32, f32, C.c_uint, vp, sz, vp]),
     "b200clip_colsum_workspace_bytes": (sz, [ll, i32]),
     "b200clip_colsum": (i32, [vp, i32, ll, ll, i32, vp, i32, vp, sz, vp]),
     "b200clip_cast_f32_bf16": (i32, [vp, vp, ll, vp]),
+    "b200clip_dropout_mask": (i32, [vp, ll, i32, f32, C.c_uint, vp]),
     "b200clip_sum_f32": (i32, [vp, ll, vp, vp]),
-    "b200clip_proj_fwd": (i32, [vp, ll, i32, i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "b200clip_proj_fwd": (i32, [vp, ll, i32, i32, vp, vp, vp, vp, vp, vp, f32, f32, C.c_uint, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "b200clip_proj_bwd_workspace_bytes": (sz, [ll, i32, i32]),
-    "b200clip_proj_bwd": (i32, [vp, vp, ll, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "b200clip_proj_bwd": (i32, [vp, vp, ll, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, C.c_uint, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "b200clip_infonce_workspace_bytes": (sz, [ll, ll]),
     "b200clip_infonce_fwd_stats": (i32, [vp, vp, i32, ll, ll, f32, vp, vp, vp, sz, vp]),
     "b200clip_infonce_loss": (i32, [vp, vp, i32, ll, ll, ll, f32, vp, vp, ll, ll, vp, vp, vp, vp, vp, sz, vp]),

@@ -32,7 +32,7 @@ _world, _rank = dp.world, dp.rank
 
 class ClipHeadFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, *params):
+    def forward(ctx, x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop_p, drop_seed, *params):
         (iw1, ib1, iw2, ib2, ig, ibeta, tw1, tb1, tw2, tb2, tg, tbeta, fw, fb) = params
         ops.require_cuda(x_img, x_txt, class_text, labels, iw1)
         W, rank = _world(group), _rank(group)
@@ -43,9 +43,12 @@ class ClipHeadFn(torch.autograd.Function):
         iw1b, iw2b, tw1b, tw2b = (ops.cast_bf16(w) for w in (iw1, iw2, tw1, tw2))
         f = ops._f32c
         # text first so its all-gather can overlap the image projection
-        y_txt, that_loc, inv_txt, saved_t = ops.proj_fwd(xt, tw1b, f(tb1), tw2b, f(tb2), f(tg), f(tbeta), want_yhat=True)
+        # independent dropout streams for the two projections (seed, seed+1)
+        y_txt, that_loc, inv_txt, saved_t = ops.proj_fwd(xt, tw1b, f(tb1), tw2b, f(tb2), f(tg), f(tbeta), want_yhat=True,
+                                                         drop_p=drop_p, drop_seed=drop_seed + 1)
         that_all, work = dp.gather_rows(that_loc, group, async_op=True)
-        y_img, ihat, inv_img, saved_i = ops.proj_fwd(xi, iw1b, f(ib1), iw2b, f(ib2), f(ig), f(ibeta), want_yhat=True)
+        y_img, ihat, inv_img, saved_i = ops.proj_fwd(xi, iw1b, f(ib1), iw2b, f(ib2), f(ig), f(ibeta), want_yhat=True,
+                                                     drop_p=drop_p, drop_seed=drop_seed)
         labels_f = f(labels)
         lsum = ops._label_sum(labels_f)
         if W > 1:
@@ -66,6 +69,7 @@ class ClipHeadFn(torch.autograd.Function):
                               *saved_i, *saved_t)
         ctx.meta = (tau_nce, tau_bce, group, W, row0, b_loc, b_glob, x_img.requires_grad, x_txt.requires_grad)
         ctx.in_dtypes = (x_img.dtype, x_txt.dtype)
+        ctx.drop = (float(drop_p), int(drop_seed))
         ctx.parts = (l_nce.detach(), l_bce.detach(), l_fc.detach())
         return loss
 
@@ -85,14 +89,15 @@ class ClipHeadFn(torch.autograd.Function):
                                  total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * fw.shape[0], grad_scale=g,
                                  dx_accum=dy_img, want_coef=True, finalize=False)
         dfw, dfb = ops.skinny_outer(coef, y_img, want_bias=True)
-        gi = ops.proj_bwd(dy_img, xi, iw1b, iw2b, ig, saved_i, need_dxi, ctx.in_dtypes[0])
+        gi = ops.proj_bwd(dy_img, xi, iw1b, iw2b, ig, saved_i, need_dxi, ctx.in_dtypes[0], drop_p=ctx.drop[0], drop_seed=ctx.drop[1])
         if work is not None:
             work.wait()
         dy_txt = ops.l2norm_bwd(d_that_loc, y_txt, inv_txt)
-        gt = ops.proj_bwd(dy_txt, xt, tw1b, tw2b, tg, saved_t, need_dxt, ctx.in_dtypes[1])
+        gt = ops.proj_bwd(dy_txt, xt, tw1b, tw2b, tg, saved_t, need_dxt, ctx.in_dtypes[1], drop_p=ctx.drop[0],
+                          drop_seed=ctx.drop[1] + 1)
         grads = [gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], gt[1], gt[2], gt[3], gt[4], gt[5], gt[6], dfw, dfb]
         grads = dp.allreduce_flat(grads, group)     # SUM, not mean: every loss term is normalised by the GLOBAL batch
-        return (gi[0], gt[0], None, None, None, None, None, *grads)
+        return (gi[0], gt[0], None, None, None, None, None, None, None, *grads)
 
 
 class ClipHead(nn.Module):
@@ -102,10 +107,12 @@ class ClipHead(nn.Module):
     def __init__(self, image_embedding_size=MODEL_CONFIG["image_embedding_size"],
                  text_embedding_size=MODEL_CONFIG["text_embedding_size"],
                  shared_embedding_size=MODEL_CONFIG["shared_embedding_size"], num_labels=MODEL_CONFIG["num_labels"],
-                 tau_nce: float = MODEL_CONFIG["temperature"], tau_bce: float = 1.0, group=None):
+                 tau_nce: float = MODEL_CONFIG["temperature"], tau_bce: float = 1.0, group=None,
+                 dropout_rate: float = 0.0):
         super().__init__()
-        self.image_projector = ImageProjection(image_embedding_size, shared_embedding_size, dropout_rate=0.0)
-        self.text_projector = TextProjection(text_embedding_size, shared_embedding_size, dropout_rate=0.0)
+        self.image_projector = ImageProjection(image_embedding_size, shared_embedding_size, dropout_rate=dropout_rate)
+        self.text_projector = TextProjection(text_embedding_size, shared_embedding_size, dropout_rate=dropout_rate)
+        self.dropout_rate = dropout_rate
         self.classifier = ClassificationAdapter(shared_embedding_size, num_labels)
         self.tau_nce, self.tau_bce, self.group = tau_nce, tau_bce, group
 
@@ -118,5 +125,8 @@ class ClipHead(nn.Module):
     def forward(self, image_embeddings, text_embeddings, class_text_features, labels):
         """One head step on this rank's local pairs; returns the global loss
         contrastive_loss(tau_nce) + multilabel_contrastive_loss(tau_bce) + BCEWithLogits(classifier)."""
+        p = float(self.dropout_rate) if self.training else 0.0
+        seed = ops.new_dropout_seed() if p > 0 else 0
+        self.last_dropout_seed = seed
         return ClipHeadFn.apply(image_embeddings, text_embeddings, class_text_features, labels, self.tau_nce, self.tau_bce,
-                                self.group, *self.params())
+                                self.group, p, seed, *self.params())

@@ -35,13 +35,15 @@ class _ProjectionBase(nn.Module):
     def forward(self, embeddings: torch.Tensor) -> torch.Tensor:
         if embeddings.dim() > 2:                                   # 0426/train.py:86-88
             embeddings = embeddings.reshape(embeddings.size(0), -1)
-        if self.training and self.dropout.p > 0:
-            raise RuntimeError(
-                "b200clip projection: train-mode dropout p>0 is not implemented by the fused kernels yet; call "
-                ".eval() or construct with dropout_rate=0 (parity with the reference is defined with dropout off)")
+        # nn.Dropout semantics (0426/train.py:81,93): active only in train mode; the mask comes from a counter-based hash of a
+        # fresh seed per call (torch's Philox stream cannot be reproduced in a fused epilogue), and
+        # `last_dropout_seed` lets a caller / test reconstruct it with ops.dropout_mask
+        p = float(self.dropout.p) if self.training else 0.0
+        seed = ops.new_dropout_seed() if p > 0 else 0
+        self.last_dropout_seed = seed
         first = getattr(self, self._first)
         return ops.ProjectionFn.apply(embeddings, first.weight, first.bias, self.fc.weight, self.fc.bias,
-                                      self.layer_norm.weight, self.layer_norm.bias)
+                                      self.layer_norm.weight, self.layer_norm.bias, p, seed)
 
 
 class ImageProjection(_ProjectionBase):

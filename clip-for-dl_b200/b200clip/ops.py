@@ -126,10 +126,22 @@ def normalize(x: torch.Tensor, dim: int = -1) -> torch.Tensor:
     return L2NormalizeFn.apply(x.reshape(-1, shp[-1])).reshape(shp)
 
 
+def dropout_mask(rows: int, cols: int, p: float, seed: int, device) -> torch.Tensor:
+    """The scaled keep-mask (keep ? 1/(1-p) : 0) the fused kernels apply for (p, seed) -- for tests and debugging."""
+    out = torch.empty((rows, cols), dtype=torch.float32, device=device)
+    check(load().b200clip_dropout_mask(ptr(out), rows, cols, float(p), int(seed) & 0xFFFFFFFF, stream_ptr()), "dropout_mask")
+    return out
+
+
+def new_dropout_seed() -> int:
+    """A fresh 32-bit seed from torch's CPU generator (honours torch.manual_seed; no device sync)."""
+    return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+
+
 # --------------------------------------------------------------------------------------------------------------
 # a-P1 / a-P2 projection block
 # --------------------------------------------------------------------------------------------------------------
-def proj_fwd(x_bf16, w1_bf16, b1, w2_bf16, b2, gamma, beta, want_yhat: bool):
+def proj_fwd(x_bf16, w1_bf16, b1, w2_bf16, b2, gamma, beta, want_yhat: bool, drop_p: float = 0.0, drop_seed: int = 0):
     B, E = x_bf16.shape
     D = w1_bf16.shape[0]
     dev = x_bf16.device
@@ -142,12 +154,14 @@ def proj_fwd(x_bf16, w1_bf16, b1, w2_bf16, b2, gamma, beta, want_yhat: bool):
     yhat = torch.empty((B, D), dtype=torch.bfloat16, device=dev) if want_yhat else None
     inv = torch.empty((B,), dtype=torch.float32, device=dev) if want_yhat else None
     check(load().b200clip_proj_fwd(ptr(x_bf16), B, E, D, ptr(w1_bf16), ptr(b1), ptr(w2_bf16), ptr(b2), ptr(gamma), ptr(beta),
-                                   LN_EPS, ptr(p), ptr(h), ptr(z), ptr(y), ptr(yhat), ptr(mean), ptr(rstd), ptr(inv),
+                                   LN_EPS, float(drop_p), int(drop_seed) & 0xFFFFFFFF, ptr(p), ptr(h), ptr(z), ptr(y), ptr(yhat),
+                                   ptr(mean), ptr(rstd), ptr(inv),
                                    stream_ptr()), "proj_fwd")
     return y, yhat, inv, (p, h, z, mean, rstd)
 
 
-def proj_bwd(dy, x_bf16, w1_bf16, w2_bf16, gamma, saved, need_dx: bool, dx_dtype=torch.float32):
+def proj_bwd(dy, x_bf16, w1_bf16, w2_bf16, gamma, saved, need_dx: bool, dx_dtype=torch.float32, drop_p: float = 0.0,
+             drop_seed: int = 0):
     p, h, z, mean, rstd = saved
     B, E = x_bf16.shape
     D = w1_bf16.shape[0]
@@ -161,22 +175,24 @@ def proj_bwd(dy, x_bf16, w1_bf16, w2_bf16, gamma, saved, need_dx: bool, dx_dtype
     nb = load().b200clip_proj_bwd_workspace_bytes(B, E, D)
     ws = _ws(nb, dev)
     check(load().b200clip_proj_bwd(ptr(dy), ptr(x_bf16), B, E, D, ptr(w1_bf16), ptr(w2_bf16), ptr(gamma), ptr(p), ptr(h), ptr(z),
-                                   ptr(mean), ptr(rstd), ptr(None if dx_bf else dx), ptr(dx if dx_bf else None), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dg), ptr(dbeta),
+                                   ptr(mean), ptr(rstd), float(drop_p), int(drop_seed) & 0xFFFFFFFF, ptr(None if dx_bf else dx), ptr(dx if dx_bf else None), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dg), ptr(dbeta),
                                    ptr(ws), ws.numel(), stream_ptr()), "proj_bwd")
     return dx, dw1, db1, dw2, db2, dg, dbeta
 
 
 class ProjectionFn(torch.autograd.Function):
-    """ImageProjection/TextProjection forward+backward (0426/train.py:84-96) with dropout off."""
+    """ImageProjection/TextProjection forward+backward (0426/train.py:84-96); dropout (p, seed) is fused into the second
+    GEMM's epilogue and regenerated in the backward pass from the same counter-based hash."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, gamma, beta):
+    def forward(ctx, x, w1, b1, w2, b2, gamma, beta, drop_p=0.0, drop_seed=0):
         require_cuda(x, w1)
         xb = cast_bf16(x)
         w1b, w2b = cast_bf16(w1), cast_bf16(w2)
         b1, b2, gamma, beta = _f32c(b1), _f32c(b2), _f32c(gamma), _f32c(beta)
-        y, _, _, saved = proj_fwd(xb, w1b, b1, w2b, b2, gamma, beta, want_yhat=False)
+        y, _, _, saved = proj_fwd(xb, w1b, b1, w2b, b2, gamma, beta, want_yhat=False, drop_p=drop_p, drop_seed=drop_seed)
         ctx.save_for_backward(xb, w1b, w2b, gamma, *saved)
+        ctx.drop = (float(drop_p), int(drop_seed))
         ctx.need_dx = x.requires_grad
         ctx.x_dtype = x.dtype
         return y
@@ -185,10 +201,11 @@ class ProjectionFn(torch.autograd.Function):
     def backward(ctx, dy):
         xb, w1b, w2b, gamma, p, h, z, mean, rstd = ctx.saved_tensors
         dx, dw1, db1, dw2, db2, dg, dbeta = proj_bwd(dy, xb, w1b, w2b, gamma, (p, h, z, mean, rstd), ctx.need_dx,
-                                                     torch.bfloat16 if ctx.x_dtype == torch.bfloat16 else torch.float32)
+                                                     torch.bfloat16 if ctx.x_dtype == torch.bfloat16 else torch.float32,
+                                                     drop_p=ctx.drop[0], drop_seed=ctx.drop[1])
         if dx is not None and dx.dtype != ctx.x_dtype:
             dx = dx.to(ctx.x_dtype)
-        return dx, dw1, db1, dw2, db2, dg, dbeta
+        return dx, dw1, db1, dw2, db2, dg, dbeta, None, None
 
 
 # --------------------------------------------------------------------------------------------------------------

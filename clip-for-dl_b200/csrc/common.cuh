@@ -51,6 +51,14 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// Counter-based dropout: keep(seed, row, col) is a pure function (murmur3 finaliser of the element index mixed with the
+// seed), so the backward pass regenerates the forward mask without storing it.  keep with probability 1 - p.
+__host__ __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t row, uint32_t col, uint32_t ncols, float p) {
+  uint32_t h = (row * ncols + col) * 0x9E3779B1u ^ seed;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return static_cast<float>(h >> 8) * (1.0f / 16777216.0f) >= p;
+}
+
 // ------------------------------------------------------------------------------------------------
 // mbarrier (shared::cta) with a watchdog: a protocol bug traps instead of hanging the GPU box.
 // ------------------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, int K, long long lda, long long ldb,
               int epi, float alpha, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
               const void* resid, long long ld_res, const float* aux, long long ld_aux, int split_k,
-              cudaStream_t stream) {
+              cudaStream_t stream, float drop_p, unsigned int drop_seed) {
   B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   B200_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
   B200_REQUIRE(out0 != nullptr && aligned16(out0), "gemm: out0 must be non-null and 16-byte aligned");
@@ -41,6 +41,7 @@ int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, in
   p.alpha = alpha;
   p.out0 = out0; p.ld0 = ld0; p.out1 = out1; p.ld1 = ld1; p.bias = bias;
   p.resid = reinterpret_cast<const __nv_bfloat16*>(resid); p.ld_res = ld_res; p.aux = aux; p.ld_aux = ld_aux;
+  p.drop_p = drop_p; p.drop_seed = drop_seed;
 
   CUtensorMap ta, tb;
   int rc;
@@ -78,5 +79,5 @@ extern "C" int b200clip_gemm_bf16(const void* a, const void* b, int a_mn_major, 
                                   void* out1, long long ld1, const float* bias, const void* resid, long long ld_res,
                                   const float* aux, long long ld_aux, int split_k, void* stream) {
   return b200::gemm_bf16(a, b, a_mn_major, b_mn_major, M, N, K, lda, ldb, epilogue, alpha, out0, ld0, out1, ld1, bias,
-                         resid, ld_res, aux, ld_aux, split_k, static_cast<cudaStream_t>(stream));
+                         resid, ld_res, aux, ld_aux, split_k, static_cast<cudaStream_t>(stream), 0.f, 0u);
 }

@@ -31,6 +31,8 @@ struct GemmParams {
   const float* bias;        // [N] or nullptr
   const __nv_bfloat16* resid; long long ld_res;
   const float* aux;         long long ld_aux;
+  float drop_p;             // EPI_BIAS_RESID_F32: dropout on (acc + bias) before the residual add (0 = off)
+  unsigned int drop_seed;
 };
 
 constexpr int GEMM_BM = 128;
@@ -212,6 +214,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
         const __nv_bfloat16* rs = p.resid + static_cast<long long>(row) * p.ld_res + col;
         float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
+        if (p.drop_p > 0.f) {                         // nn.Dropout between fc and the residual add (0426/train.py:93)
+          const float sc = 1.0f / (1.0f - p.drop_p);
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            f[i] = dropout_keep(p.drop_seed, static_cast<uint32_t>(row), static_cast<uint32_t>(col + i), static_cast<uint32_t>(p.N), p.drop_p) ? f[i] * sc : 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           const uint4 r4 = *reinterpret_cast<const uint4*>(rs + i);

@@ -13,7 +13,8 @@
 namespace b200 {
 int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, int K, long long lda, long long ldb,
               int epi, float alpha, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
-              const void* resid, long long ld_res, const float* aux, long long ld_aux, int split_k, cudaStream_t stream);
+              const void* resid, long long ld_res, const float* aux, long long ld_aux, int split_k, cudaStream_t stream,
+              float drop_p = 0.f, unsigned int drop_seed = 0u);
 }
 using namespace b200;
 
@@ -27,16 +28,18 @@ static int split_for(int M, int N, int K) {
 
 extern "C" int b200clip_proj_fwd(const void* x_bf16, long long B, int E, int D, const void* w1_bf16, const float* b1,
                                  const void* w2_bf16, const float* b2, const float* gamma, const float* beta,
-                                 float ln_eps, void* p_bf16, void* h_bf16, float* z_f32, float* y_f32, void* yhat_bf16,
-                                 float* mean, float* rstd, float* inv_norm, void* stream) {
+                                 float ln_eps, float drop_p, unsigned int drop_seed, void* p_bf16, void* h_bf16,
+                                 float* z_f32, float* y_f32, void* yhat_bf16, float* mean, float* rstd, float* inv_norm,
+                                 void* stream) {
   B200_REQUIRE(B > 0 && E > 0 && D > 0, "proj_fwd: empty problem");
+  B200_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "proj_fwd: dropout probability must be in [0,1)");
   B200_REQUIRE(E % 8 == 0 && D % 128 == 0 && D <= 1024, "proj_fwd: need E %% 8 == 0 and D %% 128 == 0, D <= 1024 (E=%d D=%d)", E, D);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rc = gemm_bf16(x_bf16, w1_bf16, 0, 0, (int)B, D, E, E, E, EPI_BIAS_GELU, 1.0f, p_bf16, D, h_bf16, D, b1, nullptr, 0,
                      nullptr, 0, 1, s);
   if (rc) return rc;
   rc = gemm_bf16(h_bf16, w2_bf16, 0, 0, (int)B, D, D, D, D, EPI_BIAS_RESID_F32, 1.0f, z_f32, D, nullptr, 0, b2, p_bf16, D,
-                 nullptr, 0, 1, s);
+                 nullptr, 0, 1, s, drop_p, drop_seed);
   if (rc) return rc;
   return b200clip_layernorm_fwd(z_f32, gamma, beta, y_f32, yhat_bf16, mean, rstd, inv_norm, B, D, ln_eps, 1e-12f, stream);
 }
@@ -53,7 +56,8 @@ extern "C" size_t b200clip_proj_bwd_workspace_bytes(long long B, int E, int D) {
 
 extern "C" int b200clip_proj_bwd(const float* dy, const void* x_bf16, long long B, int E, int D, const void* w1_bf16,
                                  const void* w2_bf16, const float* gamma, const void* p_bf16, const void* h_bf16,
-                                 const float* z_f32, const float* mean, const float* rstd, float* dx_f32, void* dx_bf16,
+                                 const float* z_f32, const float* mean, const float* rstd, float drop_p,
+                                 unsigned int drop_seed, float* dx_f32, void* dx_bf16,
                                  float* dw1, float* db1, float* dw2, float* db2, float* dgamma, float* dbeta, void* workspace,
                                  size_t workspace_bytes, void* stream) {
   B200_REQUIRE(B > 0 && E % 8 == 0 && D % 128 == 0 && D <= 1024, "proj_bwd: bad shape B=%lld E=%d D=%d", B, E, D);
@@ -69,7 +73,8 @@ extern "C" int b200clip_proj_bwd(const float* dy, const void* x_bf16, long long 
   const size_t cs_ws = b200clip_colsum_workspace_bytes(B, D);
   void* cs_work = carve(cs_ws);
 
-  int rc = b200clip_layernorm_bwd(dy, z_f32, mean, rstd, gamma, dz, dz_bf, dgamma, dbeta, db2, 0, B, D, ln_work, ln_ws, stream);
+  int rc = b200clip_layernorm_bwd(dy, z_f32, mean, rstd, gamma, dz, dz_bf, dgamma, dbeta, db2, 0, B, D, drop_p, drop_seed, ln_work,
+                                  ln_ws, stream);
   if (rc) return rc;
   // dW2[o][j] = sum_b dz[b][o] h[b][j]
   B200_CHECK_CUDA(cudaMemsetAsync(dw2, 0, static_cast<size_t>(D) * D * 4, s));

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_bwd_kernel(const float*
                                                                     float* __restrict__ dz_f32,
                                                                     __nv_bfloat16* __restrict__ dz_bf16,
                                                                     float* __restrict__ partial /*[grid][3][D]*/, int rows,
-                                                                    int D) {
+                                                                    int D, float drop_p, unsigned int drop_seed) {
   __shared__ float red[ROW_THREADS / 32][128];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -205,9 +205,18 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_bwd_kernel(const float*
       if (i < nv) {
         const float4 o = make_float4(rs * (g[i].x - s1 - zh[i].x * s2), rs * (g[i].y - s1 - zh[i].y * s2),
                                      rs * (g[i].z - s1 - zh[i].z * s2), rs * (g[i].w - s1 - zh[i].w * s2));
-        dzs[i].x += o.x; dzs[i].y += o.y; dzs[i].z += o.z; dzs[i].w += o.w;
-        if (dz_f32) st4(dz_f32 + row * D + i * 128 + lane * 4, o);
-        if (dz_bf16) st4(dz_bf16 + row * D + i * 128 + lane * 4, o);
+        if (dz_f32) st4(dz_f32 + row * D + i * 128 + lane * 4, o);             // residual branch: unmasked
+        float4 m = o;                                                          // fc branch: through the dropout mask
+        if (drop_p > 0.f) {
+          const float sc = 1.0f / (1.0f - drop_p);
+          const uint32_t c0 = i * 128 + lane * 4;
+          m.x = dropout_keep(drop_seed, (uint32_t)row, c0, (uint32_t)D, drop_p) ? o.x * sc : 0.f;
+          m.y = dropout_keep(drop_seed, (uint32_t)row, c0 + 1, (uint32_t)D, drop_p) ? o.y * sc : 0.f;
+          m.z = dropout_keep(drop_seed, (uint32_t)row, c0 + 2, (uint32_t)D, drop_p) ? o.z * sc : 0.f;
+          m.w = dropout_keep(drop_seed, (uint32_t)row, c0 + 3, (uint32_t)D, drop_p) ? o.w * sc : 0.f;
+        }
+        dzs[i].x += m.x; dzs[i].y += m.y; dzs[i].z += m.z; dzs[i].w += m.w;
+        if (dz_bf16) st4(dz_bf16 + row * D + i * 128 + lane * 4, m);
       }
   }
   // block reduction of the per-warp dgamma/dbeta partials, one 128-column slab at a time
@@ -293,6 +302,14 @@ __global__ void __launch_bounds__(ROW_THREADS) colsum_rows_kernel(const T* __res
   }
 }
 
+__global__ void dropout_mask_kernel(float* __restrict__ out, long long rows, int cols, float p, unsigned int seed) {
+  const long long n = rows * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = dropout_keep(seed, static_cast<uint32_t>(i / cols), static_cast<uint32_t>(i % cols), static_cast<uint32_t>(cols), p)
+                 ? 1.0f / (1.0f - p) : 0.f;
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -366,8 +383,8 @@ extern "C" size_t b200clip_layernorm_bwd_workspace_bytes(long long rows, int D) 
 
 extern "C" int b200clip_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd,
                                       const float* gamma, float* dz_f32, void* dz_bf16, float* dgamma, float* dbeta,
-                                      float* dz_colsum, int accumulate_params, long long rows, int D, void* workspace,
-                                      size_t workspace_bytes, void* stream) {
+                                      float* dz_colsum, int accumulate_params, long long rows, int D, float drop_p,
+                                      unsigned int drop_seed, void* workspace, size_t workspace_bytes, void* stream) {
   B200_REQUIRE(rows > 0 && D > 0 && D % 128 == 0 && D <= MAX_D, "layernorm_bwd: D=%d must be a multiple of 128, <= %d", D, MAX_D);
   const int grid = part_grid(rows);
   if (workspace_bytes < static_cast<size_t>(grid) * 3 * D * sizeof(float))
@@ -375,7 +392,7 @@ extern "C" int b200clip_layernorm_bwd(const float* dy, const float* z, const flo
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
   B200_DISPATCH_V(D, (layernorm_bwd_kernel<MAX_V><<<grid, ROW_THREADS, 0, s>>>(
-      dy, z, mean, rstd, gamma, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), partial, (int)rows, D)));
+      dy, z, mean, rstd, gamma, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), partial, (int)rows, D, drop_p, drop_seed)));
   B200_LAUNCH_CHECK();
   reduce_partials_kernel<<<(3 * D + 31) / 32, 256, 0, s>>>(partial, 3LL * D, grid, 3 * D, D, dgamma, dbeta, dz_colsum,
                                                          accumulate_params);
@@ -404,6 +421,16 @@ extern "C" int b200clip_colsum(const void* a, int a_is_bf16, long long lda, long
 #undef B200_COLSUM_LAUNCH
   B200_LAUNCH_CHECK();
   reduce_partials_kernel<<<(N + 31) / 32, 256, 0, s>>>(partial, N, grid, N, N, out, nullptr, nullptr, accumulate);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// the scaled keep-mask the fused kernels apply for (seed, p): mask[r][c] = keep ? 1/(1-p) : 0   (tests / debugging)
+extern "C" int b200clip_dropout_mask(float* out, long long rows, int cols, float p, unsigned int seed, void* stream) {
+  B200_REQUIRE(rows > 0 && cols > 0 && p >= 0.f && p < 1.f, "dropout_mask: bad arguments");
+  const long long n = rows * cols;
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, static_cast<long long>(num_sms()) * 16));
+  dropout_mask_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, rows, cols, p, seed);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -51,25 +51,29 @@ int b200clip_layernorm_fwd(const float* z, const float* gamma, const float* beta
 size_t b200clip_layernorm_bwd_workspace_bytes(long long rows, int D);
 int b200clip_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
                            float* dz_f32, void* dz_bf16, float* dgamma, float* dbeta, float* dz_colsum,
-                           int accumulate_params, long long rows, int D, void* workspace, size_t workspace_bytes,
-                           void* stream);
+                           int accumulate_params, long long rows, int D, float drop_p, unsigned int drop_seed,
+                           void* workspace, size_t workspace_bytes, void* stream);
 size_t b200clip_colsum_workspace_bytes(long long rows, int N);
 int b200clip_colsum(const void* a, int a_is_bf16, long long lda, long long rows, int N, float* out, int accumulate,
                     void* workspace, size_t workspace_bytes, void* stream);
 int b200clip_cast_f32_bf16(const float* in, void* out_bf16, long long n, void* stream);
+/* scaled keep-mask of the fused dropout (nn.Dropout, 0426/train.py:81,93): keep ? 1/(1-p) : 0, a pure function of (seed,row,col) */
+int b200clip_dropout_mask(float* out, long long rows, int cols, float p, unsigned int seed, void* stream);
 int b200clip_sum_f32(const float* a, long long n, float* out, void* stream);
 
 /* ---- a-P1 / a-P2: ImageProjection.forward 0426/train.py:84-96, TextProjection.forward :109-116 -----------------
- * Linear(E,D) -> GELU(erf) -> Linear(D,D) -> (dropout = identity) -> +residual -> LayerNorm [-> L2-normalised bf16].
- * Saved for backward (caller tensors): p, h (bf16), z (f32), mean, rstd. */
+ * Linear(E,D) -> GELU(erf) -> Linear(D,D) -> Dropout(drop_p; counter-based mask from drop_seed, 0 = off) -> +residual ->
+ * LayerNorm [-> L2-normalised bf16].  Saved for backward (caller tensors): p, h (bf16), z (f32), mean, rstd; the backward
+ * pass regenerates the dropout mask from (drop_p, drop_seed). */
 int b200clip_proj_fwd(const void* x_bf16, long long B, int E, int D, const void* w1_bf16, const float* b1,
                       const void* w2_bf16, const float* b2, const float* gamma, const float* beta, float ln_eps,
-                      void* p_bf16, void* h_bf16, float* z_f32, float* y_f32, void* yhat_bf16, float* mean, float* rstd,
+                      float drop_p, unsigned int drop_seed, void* p_bf16, void* h_bf16, float* z_f32, float* y_f32, void* yhat_bf16, float* mean, float* rstd,
                       float* inv_norm, void* stream);
 size_t b200clip_proj_bwd_workspace_bytes(long long B, int E, int D);
 int b200clip_proj_bwd(const float* dy, const void* x_bf16, long long B, int E, int D, const void* w1_bf16,
                       const void* w2_bf16, const float* gamma, const void* p_bf16, const void* h_bf16, const float* z_f32,
-                      const float* mean, const float* rstd, float* dx_f32, void* dx_bf16, float* dw1, float* db1, float* dw2,
+                      const float* mean, const float* rstd, float drop_p, unsigned int drop_seed, float* dx_f32, void* dx_bf16,
+                      float* dw1, float* db1, float* dw2,
                       float* db2, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a-N: contrastive_loss(image_features, text_features, temperature) -- 0426/train.py:154-176 ----------------

@@ -63,9 +63,39 @@ def test_projection_state_dict_keys_and_4d_input():
     m = m.to(dev()).eval()
     x = torch.randn(8, 2048, 1, 1, device=dev())
     assert m(x).shape == (8, 512)
-    m.train()
-    with pytest.raises(RuntimeError):
-        m(x)                                               # train-mode dropout is refused loudly, not skipped
+
+
+def test_projection_train_mode_dropout_matches_reference_with_same_mask():
+    """nn.Dropout(0.1) between fc and the residual (0426/train.py:93): the fused mask is a counter-based hash, so parity is
+    checked by feeding the SAME mask (ops.dropout_mask) to the oracle; the keep-rate is checked statistically."""
+    import b200clip
+    from b200clip import ops
+    B, E, D, pdrop = 300, 768, 512, 0.1
+    p = _round_params(synth.projection_params(100, E, D))
+    x = synth.bf16_round(synth.randn(7, B, E))
+    w = synth.randn(9, B, D)
+    mod = b200clip.TextProjection(E, D, dropout_rate=pdrop).to(dev()).train()
+    _load(mod, "text_projection", p)
+    xg = x.to(dev()).requires_grad_(True)
+    y = mod(xg)
+    (y * w.to(dev())).sum().backward()
+    mask = ops.dropout_mask(B, D, pdrop, mod.last_dropout_seed, dev()).cpu()
+    keep = (mask > 0).float().mean().item()
+    assert abs(keep - (1 - pdrop)) < 0.01 and torch.all((mask == 0) | (mask == 1 / (1 - pdrop)))
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    xr = x.clone().requires_grad_(True)
+    proj = xr @ pr["w1"].T + pr["b1"]
+    f = (R.gelu_erf(proj) @ pr["w2"].T + pr["b2"]) * mask
+    yref = torch.nn.functional.layer_norm(f + proj, (D,), pr["gamma"], pr["beta"], 1e-5)
+    (yref * w).sum().backward()
+    assert rel_l2(y, yref) < 1e-2
+    assert rel_l2(xg.grad, xr.grad) < 2e-2
+    assert rel_l2(mod.fc.weight.grad, pr["w2"].grad) < 2e-2
+    assert rel_l2(mod.fc.bias.grad, pr["b2"].grad) < 2e-2
+    assert rel_l2(mod.text_projection.weight.grad, pr["w1"].grad) < 2e-2
+    y2 = mod(xg)                                          # a new call draws a new mask
+    assert not torch.equal(y2, y)
+    assert torch.equal(mod.eval()(xg), mod(xg))           # eval: dropout off, deterministic
 
 
 @pytest.mark.parametrize("B,E_img", [(256, 2048), (1024, 768)])

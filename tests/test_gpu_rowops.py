@@ -64,7 +64,7 @@ def test_layernorm_fwd_bwd(rows, D):
     nb = lib.b200clip_layernorm_bwd_workspace_bytes(rows, D)
     ws = torch.empty(nb, dtype=torch.uint8, device=d)
     _lib.check(lib.b200clip_layernorm_bwd(_lib.ptr(dy), _lib.ptr(z), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma),
-                                          _lib.ptr(dz), _lib.ptr(dzb), _lib.ptr(dg), _lib.ptr(db), _lib.ptr(dzs), 0, rows, D, _lib.ptr(ws), nb,
+                                          _lib.ptr(dz), _lib.ptr(dzb), _lib.ptr(dg), _lib.ptr(db), _lib.ptr(dzs), 0, rows, D, 0.0, 0, _lib.ptr(ws), nb,
                                           _lib.stream_ptr()), "lnb")
     assert rel_l2(dz, zr.grad) < 1e-5
     assert rel_l2(dzb.float(), zr.grad) < 4e-3
