@@ -21,7 +21,7 @@ SIGNATURES = {
     "b200clip_launch_count": (C.c_ulonglong, []),
     "b200clip_gemm_bf16": (i32, [vp, vp, i32, i32, i32, i32, i32, ll, ll, i32, f32, vp, ll, vp, ll, vp, vp, ll, vp, ll, i32, vp]),
     "b200clip_l2norm_fwd": (i32, [vp, i32, ll, vp, vp, vp, ll, i32, f32, vp]),
-    "b200clip_l2norm_bwd": (i32, [vp, vp, i32, ll, vp, vp, i32, ll, i32, f32, vp]),
+    "b200clip_l2norm_bwd": (i32, [vp, vp, i32, ll, vp, vp, i32, ll, i32, f32, vp, vp, vp]),
     "b200clip_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, ll, i32, f32, f32, vp]),
     "b200clip_layernorm_bwd_workspace_bytes": (sz, [ll, i32]),
     "b200clip_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, ll, i32, f32, C.c_uint, vp, sz, vp]),
@@ -41,7 +41,7 @@ SIGNATURES = {
     "b200clip_mlbce_fwd_bwd": (i32, [vp, ll, vp, vp, i32, ll, ll, i32, i32, f32, vp, f64, vp, vp, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "b200clip_fc_bce_fwd_bwd": (i32, [vp, ll, vp, vp, vp, ll, ll, i32, i32, f64, f32, vp, vp, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "b200clip_bce_heads_fwd_bwd": (i32, [vp, ll, vp, i32, vp, vp, i32, vp, i32, ll, ll, i32, f32, vp, f64, f64, vp, vp, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
-    "b200clip_skinny_outer": (i32, [vp, i32, vp, ll, vp, ll, i32, vp, vp, i32, vp, sz, vp]),
+    "b200clip_skinny_outer": (i32, [vp, i32, vp, ll, vp, ll, i32, vp, vp, i32, vp, vp, sz, vp]),
     "b200clip_predict_multilabel": (i32, [vp, ll, vp, ll, i32, i32, f32, f32, vp, vp]),
     "b200clip_zeroshot_score": (i32, [vp, ll, ll, vp, i32, i32, i32, i32, f32, C.POINTER(f32), i32, f32, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp]),
 }

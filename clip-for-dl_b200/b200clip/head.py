@@ -57,16 +57,20 @@ class ClipHeadFn(torch.autograd.Function):
         l_nce, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, group=group if W > 1 else None)
         C = class_text.shape[0]
         Cf = fw.shape[0]
-        l_bce, l_fc, status, both, _ = ops.bce_heads(y_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
-                                                     total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
-                                                     finalize=(W == 1))
+        # one pass over y_img serves both BCE heads, forward AND backward: the input gradient d_bce (for upstream grad 1)
+        # and the FC coefficients are produced here; backward only scales them by the incoming gradient.
+        need_grad = any(t.requires_grad for t in (x_img, x_txt, *params) if t is not None)
+        d_bce = torch.empty_like(y_img) if need_grad else None
+        l_bce, l_fc, status, both, coef = ops.bce_heads(y_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
+                                                        total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
+                                                        dx_out=d_bce, want_coef=need_grad, finalize=(W == 1))
         if W > 1:
             dp.sum_across(both, group)
             l_bce, l_fc = dp.bce_losses_from_sums(both, lsum, float(b_glob) * C, float(b_glob) * Cf)
         loss = l_nce + l_bce + l_fc
-        ctx.save_for_backward(xi, xt, iw1b, iw2b, tw1b, tw2b, f(ig), f(tg), f(class_text), labels_f, lsum, y_img, y_txt, ihat,
-                              that_all, inv_img, inv_txt, rinvh, cinvh, f(fw), f(fb) if fb is not None else None,
-                              *saved_i, *saved_t)
+        ctx.save_for_backward(xi, xt, iw1b, iw2b, tw1b, tw2b, f(ig), f(tg), y_img, y_txt, ihat,
+                              that_all, inv_img, inv_txt, rinvh, cinvh, d_bce, coef, *saved_i, *saved_t)
+        ctx.has_fc_bias = fb is not None
         ctx.meta = (tau_nce, tau_bce, group, W, row0, b_loc, b_glob, x_img.requires_grad, x_txt.requires_grad)
         ctx.in_dtypes = (x_img.dtype, x_txt.dtype)
         ctx.drop = (float(drop_p), int(drop_seed))
@@ -75,20 +79,18 @@ class ClipHeadFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        (xi, xt, iw1b, iw2b, tw1b, tw2b, ig, tg, class_text, labels_f, lsum, y_img, y_txt, ihat, that_all, inv_img, inv_txt,
-         rinvh, cinvh, fw, fb, *rest) = ctx.saved_tensors
+        (xi, xt, iw1b, iw2b, tw1b, tw2b, ig, tg, y_img, y_txt, ihat, that_all, inv_img, inv_txt,
+         rinvh, cinvh, d_bce, coef, *rest) = ctx.saved_tensors
         saved_i, saved_t = tuple(rest[:5]), tuple(rest[5:])
         tau_nce, tau_bce, group, W, row0, b_loc, b_glob, need_dxi, need_dxt = ctx.meta
-        C = class_text.shape[0]
-        g = ops._f32c(g)
+        g = ops._f32c(g).reshape(())
         d_ihat, d_that = ops.infonce_backward(ihat, that_all, tau_nce, rinvh, cinvh, g, row0=row0)
         d_that_loc, work = dp.scatter_sum_rows(d_that, group, async_op=True)
-        # image side: through the L2 normalisation, then add the two BCE heads' gradients (they act on y_img itself)
-        dy_img = ops.l2norm_bwd(d_ihat, y_img, inv_img)
-        *_, coef = ops.bce_heads(y_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
-                                 total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * fw.shape[0], grad_scale=g,
-                                 dx_accum=dy_img, want_coef=True, finalize=False)
-        dfw, dfb = ops.skinny_outer(coef, y_img, want_bias=True)
+        # image side: through the L2 normalisation, plus g * (the two BCE heads' input gradient from the forward pass)
+        dy_img = ops.l2norm_bwd(d_ihat, y_img, inv_img, addend=d_bce, addend_scale=g)
+        dfw, dfb = ops.skinny_outer(coef, y_img, want_bias=True, out_scale=g)
+        if not ctx.has_fc_bias:
+            dfb = None
         gi = ops.proj_bwd(dy_img, xi, iw1b, iw2b, ig, saved_i, need_dxi, ctx.in_dtypes[0], drop_p=ctx.drop[0], drop_seed=ctx.drop[1])
         if work is not None:
             work.wait()

@@ -93,13 +93,15 @@ def l2norm_fwd(x: torch.Tensor, want_bf16: bool = True, want_f32: bool = False, 
 
 
 def l2norm_bwd(dy: torch.Tensor, x: torch.Tensor, inv: torch.Tensor, eps: float = L2_EPS, out: Optional[torch.Tensor] = None,
-               accumulate: bool = False) -> torch.Tensor:
+               accumulate: bool = False, addend: Optional[torch.Tensor] = None,
+               addend_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx = d normalize(x) . dy  [+ addend * addend_scale]  (addend [rows, D] f32, addend_scale a device scalar)."""
     dy = _f32c(dy)
     rows, D = x.shape
     if out is None:
         out = torch.empty((rows, D), dtype=torch.float32, device=x.device)
     check(load().b200clip_l2norm_bwd(ptr(dy), ptr(x), int(x.dtype == torch.bfloat16), D, ptr(inv), ptr(out), int(accumulate),
-                                     rows, D, eps, stream_ptr()), "l2norm_bwd")
+                                     rows, D, eps, ptr(addend), ptr(addend_scale), stream_ptr()), "l2norm_bwd")
     return out
 
 
@@ -329,7 +331,7 @@ def mlbce(image_features, text_features, labels, temperature, *, grad_scale=None
     return loss, status, sums, dx, coef, xinv, label_sum
 
 
-def skinny_outer(coef, x, row_scale=None, want_bias=False):
+def skinny_outer(coef, x, row_scale=None, want_bias=False, out_scale: Optional[torch.Tensor] = None):
     lib = load()
     B, Cn = coef.shape
     D = x.shape[1]
@@ -337,8 +339,8 @@ def skinny_outer(coef, x, row_scale=None, want_bias=False):
     out_w = torch.empty((Cn, D), dtype=torch.float32, device=dev)
     out_b = torch.empty((Cn,), dtype=torch.float32, device=dev) if want_bias else None
     ws = _ws(lib.b200clip_smallc_workspace_bytes(B, Cn, D), dev)
-    check(lib.b200clip_skinny_outer(ptr(coef), Cn, ptr(x), x.stride(0), ptr(row_scale), B, D, ptr(out_w), ptr(out_b), 0, ptr(ws),
-                                    ws.numel(), stream_ptr()), "skinny_outer")
+    check(lib.b200clip_skinny_outer(ptr(coef), Cn, ptr(x), x.stride(0), ptr(row_scale), B, D, ptr(out_w), ptr(out_b), 0,
+                                    ptr(out_scale), ptr(ws), ws.numel(), stream_ptr()), "skinny_outer")
     return out_w, out_b
 
 
@@ -445,8 +447,11 @@ class LinearSmallFn(torch.autograd.Function):
 
 
 def bce_heads(image_features, class_text, fc_weight, fc_bias, labels, temperature, *, label_sum, total_elems_text,
-              total_elems_fc, grad_scale=None, dx_accum=None, want_coef=False, finalize=True):
-    """Both BCE heads (a-B on the class texts + a-A FC adapter) in one pass over the image features."""
+              total_elems_fc, grad_scale=None, dx_accum=None, dx_out=None, want_coef=False, finalize=True):
+    """Both BCE heads (a-B on the class texts + a-A FC adapter) in one pass over the image features.
+    dx_accum: input gradient is ADDED to this tensor; dx_out: input gradient overwrites this tensor."""
+    assert dx_accum is None or dx_out is None
+    dx_t = dx_accum if dx_accum is not None else dx_out
     lib = load()
     x, t, w = _f32c(image_features), _f32c(class_text), _f32c(fc_weight)
     b = _f32c(fc_bias) if fc_bias is not None else None
@@ -463,7 +468,7 @@ def bce_heads(image_features, class_text, fc_weight, fc_bias, labels, temperatur
     gs = _f32c(grad_scale.reshape(())) if grad_scale is not None else None
     check(lib.b200clip_bce_heads_fwd_bwd(ptr(x), x.stride(0), ptr(t), c1, ptr(w), ptr(b), c2, ptr(y), y.shape[1], y.stride(0), B, D,
                                          float(temperature), ptr(label_sum), float(total_elems_text), float(total_elems_fc),
-                                         ptr(gs), ptr(dx_accum), int(dx_accum is not None), ptr(coef), ptr(sums), ptr(l_text),
+                                         ptr(gs), ptr(dx_t), int(dx_accum is not None), ptr(coef), ptr(sums), ptr(l_text),
                                          ptr(l_fc), ptr(status), ptr(ws), ws.numel(), stream_ptr()), "bce_heads_fwd_bwd")
     return l_text, l_fc, status, sums, coef
 

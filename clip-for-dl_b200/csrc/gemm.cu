@@ -1,4 +1,6 @@
 // b200clip: C-ABI entry point for the tcgen05 GEMM (used by the projection block and by the parity tests).
+#include <algorithm>
+
 #include "gemm.cuh"
 #include "host.cuh"
 #include "../../include/b200clip.h"
@@ -15,8 +17,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((p.M + GEMM_BM - 1) / GEMM_BM, (p.N + BN - 1) / BN, splits);
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
+  GemmParams q = p;
+  q.splits = splits;
+  const int items = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN) * splits;
+  kern<<<std::min(items, num_sms()), GEMM_THREADS, smem, stream>>>(ta, tb, q);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -3,9 +3,9 @@
 // Operand storage (row-major global matrices, bf16):
 //   A K-major : a[M][K]   (rows of A are contiguous in K)       A MN-major: a[K][M]  (i.e. A^T stored)
 //   B K-major : b[N][K]   ("NT" GEMM, y = x W^T)                B MN-major: b[K][N]  ("NN" GEMM, y = x W)
-// One CTA computes one 128 x BN output tile over a K range (split-K via gridDim.z).
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (one elected thread), 2 = TMEM allocator, 4..7 = epilogue
-// (warp_idx % 4 selects the TMEM lane quadrant a warp may read).
+// A work item is one 128 x BN output tile over a K range (split-K); persistent CTAs walk the item list.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (one elected thread), 2 = TMEM allocator, 4..11 = epilogue
+// (warp_idx % 4 selects the TMEM lane quadrant a warp may read; warpgroup = column half).
 #pragma once
 #include "common.cuh"
 
@@ -24,7 +24,8 @@ enum GemmEpilogue : int {
 struct GemmParams {
   int M, N, K;              // logical problem size
   int k_chunks;             // ceil(K / 64)
-  int k_chunks_per_split;   // chunks handled by one blockIdx.z
+  int k_chunks_per_split;   // chunks handled by one split
+  int splits;               // number of K splits (work items = m_tiles * n_tiles * splits)
   float alpha;
   void* out0;  long long ld0;
   void* out1;  long long ld1;
@@ -37,7 +38,8 @@ struct GemmParams {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;          // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
+constexpr int GEMM_EPI_WARPS = 8;
 
 template <int BN>
 constexpr int gemm_stage_bytes() { return GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2; }
@@ -52,6 +54,97 @@ __device__ __forceinline__ float gelu_erf_grad_f(float x) {
   return cdf + x * pdf;
 }
 
+// one 32-column chunk of one output row: v = fp32 accumulator bits of columns [col, col+32)
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], int row, int col) {
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col + i);
+      f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+    }
+  }
+  if constexpr (EPI == EPI_STORE_F32) {
+    float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+  } else if constexpr (EPI == EPI_ATOMIC_F32) {
+    float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4)                 // 16-byte vector reductions: 8 instead of 32 L2 atomics per chunk
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "f"(f[i]), "f"(f[i + 1]), "f"(f[i + 2]), "f"(f[i + 3])
+                   : "memory");
+  } else if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_RELU_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
+    if constexpr (EPI == EPI_RELU_BF16) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 8)
+      *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf16x2(f[i], f[i + 1]), pack_bf16x2(f[i + 2], f[i + 3]),
+                                                    pack_bf16x2(f[i + 4], f[i + 5]), pack_bf16x2(f[i + 6], f[i + 7]));
+  } else if constexpr (EPI == EPI_BIAS_GELU) {
+    __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
+    __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(p.out1) + static_cast<long long>(row) * p.ld1 + col;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      *reinterpret_cast<uint4*>(o0 + i) = make_uint4(pack_bf16x2(f[i], f[i + 1]), pack_bf16x2(f[i + 2], f[i + 3]),
+                                                     pack_bf16x2(f[i + 4], f[i + 5]), pack_bf16x2(f[i + 6], f[i + 7]));
+      float g[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        // GELU is applied to the bf16-rounded p so that backward (which only sees the stored p) is consistent
+        const float pr = __bfloat162float(__float2bfloat16_rn(f[i + t]));
+        g[t] = gelu_erf_f(pr);
+      }
+      *reinterpret_cast<uint4*>(o1 + i) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
+                                                     pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+    }
+  } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
+    const __nv_bfloat16* rs = p.resid + static_cast<long long>(row) * p.ld_res + col;
+    float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
+    if (p.drop_p > 0.f) {                         // nn.Dropout between fc and the residual add (0426/train.py:93)
+      const float sc = 1.0f / (1.0f - p.drop_p);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        f[i] = dropout_keep(p.drop_seed, static_cast<uint32_t>(row), static_cast<uint32_t>(col + i), static_cast<uint32_t>(p.N), p.drop_p) ? f[i] * sc : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      const uint4 r4 = *reinterpret_cast<const uint4*>(rs + i);
+      f[i] += bf16_lo(r4.x); f[i + 1] += bf16_hi(r4.x); f[i + 2] += bf16_lo(r4.y); f[i + 3] += bf16_hi(r4.y);
+      f[i + 4] += bf16_lo(r4.z); f[i + 5] += bf16_hi(r4.z); f[i + 6] += bf16_lo(r4.w); f[i + 7] += bf16_hi(r4.w);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+  } else if constexpr (EPI == EPI_GELU_BWD) {
+    const __nv_bfloat16* rs = p.resid + static_cast<long long>(row) * p.ld_res + col;
+    const float* ax = p.aux + static_cast<long long>(row) * p.ld_aux + col;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      const uint4 r4 = *reinterpret_cast<const uint4*>(rs + i);
+      const float pv[8] = {bf16_lo(r4.x), bf16_hi(r4.x), bf16_lo(r4.y), bf16_hi(r4.y),
+                           bf16_lo(r4.z), bf16_hi(r4.z), bf16_lo(r4.w), bf16_hi(r4.w)};
+      const float4 a0 = *reinterpret_cast<const float4*>(ax + i);
+      const float4 a1 = *reinterpret_cast<const float4*>(ax + i + 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float g[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) g[t] = f[i + t] * gelu_erf_grad_f(pv[t]) + av[t];
+      *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
+                                                    pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+    }
+  }
+}
+
+// Persistent kernel: gridDim.x CTAs (<= one per SM) walk the list of (split, m-tile, n-tile) work items.  The fp32
+// accumulator is DOUBLE-BUFFERED in TMEM (2 x BN columns), so the epilogue of item i (8 warps: two warpgroups, each
+// owning half of the tile's columns) overlaps the TMA/MMA main loop of item i+1.
 template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -62,18 +155,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   constexpr int B_BYTES = BN * GEMM_BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int EPI_COLS = BN / 2;                  // columns per epilogue warpgroup
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = empty_bar + STAGES;          // 2
+  uint64_t* acc_empty = acc_full + 2;               // 2 (one arrival per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * GEMM_BM;
-  const int n0 = blockIdx.y * BN;
-  const int kc0 = blockIdx.z * p.k_chunks_per_split;
-  const int kc1 = min(p.k_chunks, kc0 + p.k_chunks_per_split);
-  const int nk = kc1 - kc0;                        // >= 1 guaranteed by the host
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int mn_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * n_tiles;
+  const int items = mn_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -84,11 +177,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], GEMM_EPI_WARPS);
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, 2 * BN);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -98,28 +194,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
-    {
-      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), smem0 = smem_u32(smem);
-      int s = 0;
-      uint32_t ph = 0;
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), smem0 = smem_u32(smem);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int z = it / mn_tiles, mn = it - z * mn_tiles;
+      const int m0 = (mn / n_tiles) * GEMM_BM, n0 = (mn % n_tiles) * BN;
+      const int kc0 = z * p.k_chunks_per_split;
+      const int nk = min(p.k_chunks, kc0 + p.k_chunks_per_split) - kc0;
       int k0 = kc0 * GEMM_BK;
       for (int i = 0; i < nk; ++i, k0 += GEMM_BK) {
         mbar_wait_a(empty0 + 8 * s, ph ^ 1);
         const uint32_t sa = smem0 + s * STAGE_BYTES, sb = sa + A_BYTES, fb = full0 + 8 * s;
         if (elect_one()) {
-        mbar_arrive_expect_tx_a(fb, STAGE_BYTES);
-        if constexpr (!A_MN) {
-          tma_load_2d_a(sa, &tmap_a, fb, k0, m0);                               // box {64 k, 128 m}
-        } else {
+          mbar_arrive_expect_tx_a(fb, STAGE_BYTES);
+          if constexpr (!A_MN) {
+            tma_load_2d_a(sa, &tmap_a, fb, k0, m0);                               // box {64 k, 128 m}
+          } else {
 #pragma unroll
-          for (int g = 0; g < GEMM_BM / 64; ++g) tma_load_2d_a(sa + g * 8192, &tmap_a, fb, m0 + g * 64, k0);   // {64 m, 64 k}
-        }
-        if constexpr (!B_MN) {
-          tma_load_2d_a(sb, &tmap_b, fb, k0, n0);                               // box {64 k, BN n}
-        } else {
+            for (int g = 0; g < GEMM_BM / 64; ++g) tma_load_2d_a(sa + g * 8192, &tmap_a, fb, m0 + g * 64, k0);   // {64 m, 64 k}
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_a(sb, &tmap_b, fb, k0, n0);                               // box {64 k, BN n}
+          } else {
 #pragma unroll
-          for (int g = 0; g < BN / 64; ++g) tma_load_2d_a(sb + g * 8192, &tmap_b, fb, n0 + g * 64, k0);        // {64 n, 64 k}
-        }
+            for (int g = 0; g < BN / 64; ++g) tma_load_2d_a(sb + g * 8192, &tmap_b, fb, n0 + g * 64, k0);        // {64 n, 64 k}
+          }
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -128,14 +228,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer: warp-uniform loop (descriptor words live in uniform registers), one
     // elected lane issues; one 32-bit add per operand per MMA =====================
-    {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
-      constexpr uint32_t A_STEP = (A_MN ? 2048 : 32) >> 4, B_STEP = (B_MN ? 2048 : 32) >> 4;
-      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
-      const uint32_t a_lo0 = desc_lo(smem_u32(smem), A_MN ? 8192 : 16);
-      const uint32_t b_lo0 = desc_lo(smem_u32(smem) + A_BYTES, B_MN ? 8192 : 16);
-      int s = 0;
-      uint32_t ph = 0;
+    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
+    constexpr uint32_t A_STEP = (A_MN ? 2048 : 32) >> 4, B_STEP = (B_MN ? 2048 : 32) >> 4;
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    const uint32_t af0 = smem_u32(acc_full), ae0 = smem_u32(acc_empty);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem), A_MN ? 8192 : 16);
+    const uint32_t b_lo0 = desc_lo(smem_u32(smem) + A_BYTES, B_MN ? 8192 : 16);
+    int s = 0;
+    uint32_t ph = 0;
+    int local = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++local) {
+      const int z = it / mn_tiles;
+      const int kc0 = z * p.k_chunks_per_split;
+      const int nk = min(p.k_chunks, kc0 + p.k_chunks_per_split) - kc0;
+      const int buf = local & 1;
+      mbar_wait_a(ae0 + 8 * buf, ((local >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * BN;
       for (int i = 0; i < nk; ++i) {
         mbar_wait_a(full0 + 8 * s, ph);
         tc_fence_after();
@@ -143,116 +252,49 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (elect_one()) {
 #pragma unroll
           for (int j = 0; j < GEMM_BK / 16; ++j)
-            mma_ss_lo(tmem_base, a_lo + j * A_STEP, b_lo + j * B_STEP, idesc, (i | j) != 0);
+            mma_ss_lo(d_tmem, a_lo + j * A_STEP, b_lo + j * B_STEP, idesc, (i | j) != 0);
           tc_commit_a(empty0 + 8 * s);                // frees the smem stage once these MMAs have read it
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      if (elect_one()) tc_commit(accum_bar);          // accumulator complete
+      if (elect_one()) tc_commit_a(af0 + 8 * buf);    // accumulator complete
       __syncwarp();
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: TMEM -> registers -> global =====================
+    // ===================== epilogue: TMEM -> registers -> global (2 warpgroups x half the columns) =====================
     const int q = warp & 3;                           // TMEM lane quadrant of this warp
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const bool row_ok = row < p.M;
+    const int wg = (warp - 4) >> 2;
+    const uint32_t af0 = smem_u32(acc_full), ae0 = smem_u32(acc_empty);
+    int local = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++local) {
+      const int z = it / mn_tiles, mn = it - z * mn_tiles;
+      const int m0 = (mn / n_tiles) * GEMM_BM, n0 = (mn % n_tiles) * BN;
+      const int buf = local & 1;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait_a(af0 + 8 * buf, (local >> 1) & 1);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      tmem_ld_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
-      tmem_ld_wait();
-      const int col = n0 + c;
-      if (!row_ok || col >= p.N) continue;            // N is a multiple of 32 (host-checked)
-      float f[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
-      if (p.bias != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col + i);
-          f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+      for (int c = wg * EPI_COLS; c < (wg + 1) * EPI_COLS; c += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + c, v);
+        tmem_ld_wait();
+        if (c + 32 == (wg + 1) * EPI_COLS) {          // last TMEM read of this item: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(ae0 + 8 * buf);
         }
-      }
-      if constexpr (EPI == EPI_STORE_F32) {
-        float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-      } else if constexpr (EPI == EPI_ATOMIC_F32) {
-        float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) atomicAdd(o + i, f[i]);
-      } else if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_RELU_BF16) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
-        if constexpr (EPI == EPI_RELU_BF16) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 8)
-          *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf16x2(f[i], f[i + 1]), pack_bf16x2(f[i + 2], f[i + 3]),
-                                                        pack_bf16x2(f[i + 4], f[i + 5]), pack_bf16x2(f[i + 6], f[i + 7]));
-      } else if constexpr (EPI == EPI_BIAS_GELU) {
-        __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
-        __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(p.out1) + static_cast<long long>(row) * p.ld1 + col;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          *reinterpret_cast<uint4*>(o0 + i) = make_uint4(pack_bf16x2(f[i], f[i + 1]), pack_bf16x2(f[i + 2], f[i + 3]),
-                                                         pack_bf16x2(f[i + 4], f[i + 5]), pack_bf16x2(f[i + 6], f[i + 7]));
-          float g[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            // GELU is applied to the bf16-rounded p so that backward (which only sees the stored p) is consistent
-            const float pr = __bfloat162float(__float2bfloat16_rn(f[i + t]));
-            g[t] = gelu_erf_f(pr);
-          }
-          *reinterpret_cast<uint4*>(o1 + i) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
-                                                         pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
-        }
-      } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
-        const __nv_bfloat16* rs = p.resid + static_cast<long long>(row) * p.ld_res + col;
-        float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
-        if (p.drop_p > 0.f) {                         // nn.Dropout between fc and the residual add (0426/train.py:93)
-          const float sc = 1.0f / (1.0f - p.drop_p);
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            f[i] = dropout_keep(p.drop_seed, static_cast<uint32_t>(row), static_cast<uint32_t>(col + i), static_cast<uint32_t>(p.N), p.drop_p) ? f[i] * sc : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          const uint4 r4 = *reinterpret_cast<const uint4*>(rs + i);
-          f[i] += bf16_lo(r4.x); f[i + 1] += bf16_hi(r4.x); f[i + 2] += bf16_lo(r4.y); f[i + 3] += bf16_hi(r4.y);
-          f[i + 4] += bf16_lo(r4.z); f[i + 5] += bf16_hi(r4.z); f[i + 6] += bf16_lo(r4.w); f[i + 7] += bf16_hi(r4.w);
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-      } else if constexpr (EPI == EPI_GELU_BWD) {
-        const __nv_bfloat16* rs = p.resid + static_cast<long long>(row) * p.ld_res + col;
-        const float* ax = p.aux + static_cast<long long>(row) * p.ld_aux + col;
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          const uint4 r4 = *reinterpret_cast<const uint4*>(rs + i);
-          const float pv[8] = {bf16_lo(r4.x), bf16_hi(r4.x), bf16_lo(r4.y), bf16_hi(r4.y),
-                               bf16_lo(r4.z), bf16_hi(r4.z), bf16_lo(r4.w), bf16_hi(r4.w)};
-          const float4 a0 = *reinterpret_cast<const float4*>(ax + i);
-          const float4 a1 = *reinterpret_cast<const float4*>(ax + i + 4);
-          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-          float g[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) g[t] = f[i + t] * gelu_erf_grad_f(pv[t]) + av[t];
-          *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
-                                                        pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
-        }
+        const int col = n0 + c;
+        if (!row_ok || col >= p.N) continue;          // N is a multiple of 32 (host-checked)
+        gemm_epilogue_chunk<EPI>(p, v, row, col);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, BN);
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 }  // namespace b200

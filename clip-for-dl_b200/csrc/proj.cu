@@ -21,7 +21,7 @@ using namespace b200;
 static int split_for(int M, int N, int K) {
   const int tiles = ((M + 127) / 128) * ((N + 255) / 256);
   const int kchunks = (K + 63) / 64;
-  int s = (num_sms() + tiles - 1) / tiles;
+  int s = num_sms() / tiles;                       // floor: tiles * s <= #SMs, i.e. ONE wave of the persistent GEMM
   if (s > kchunks) s = kchunks;
   return s < 1 ? 1 : s;
 }

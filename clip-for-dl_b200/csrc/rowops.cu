@@ -60,15 +60,18 @@ __global__ void __launch_bounds__(ROW_THREADS) l2norm_fwd_kernel(const TIn* __re
   }
 }
 
-// a-L2 backward: dx (+)= inv * (dy - yhat * (yhat . dy)),  yhat = x * inv.   If the norm was clamped (inv == 1/eps)
-// the clamp has zero gradient and dx = dy * inv.
+// a-L2 backward: dx (+)= inv * (dy - yhat * (yhat . dy)) [+ addend * *addend_scale],  yhat = x * inv.   If the norm was
+// clamped (inv == 1/eps) the clamp has zero gradient and dx = dy * inv.  The addend carries gradients that reach x
+// directly (the BCE heads' input gradient computed in the forward pass, scaled by the upstream dLoss).
 template <typename TIn, int MAX_V>
 __global__ void __launch_bounds__(ROW_THREADS) l2norm_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x,
                                                                  long long ldx, const float* __restrict__ inv_norm,
                                                                  float* __restrict__ dx, int accumulate, int rows, int D,
-                                                                 float eps) {
+                                                                 float eps, const float* __restrict__ addend,
+                                                                 const float* __restrict__ addend_scale) {
   const int lane = threadIdx.x & 31;
   const int nv = D >> 7;
+  const float ascale = (addend && addend_scale) ? *addend_scale : 1.0f;
   for (long long row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); row < rows;
        row += static_cast<long long>(gridDim.x) * (ROW_THREADS / 32)) {
     const float inv = inv_norm[row];
@@ -93,6 +96,10 @@ __global__ void __launch_bounds__(ROW_THREADS) l2norm_bwd_kernel(const float* __
         if (accumulate) {
           const float4 old = ld4(d);
           o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        if (addend) {
+          const float4 a = ld4(addend + row * D + i * 128 + lane * 4);
+          o.x += a.x * ascale; o.y += a.y * ascale; o.z += a.z * ascale; o.w += a.w * ascale;
         }
         st4(d, o);
       }
@@ -350,17 +357,18 @@ extern "C" int b200clip_l2norm_fwd(const void* x, int x_is_bf16, long long ldx, 
 }
 
 extern "C" int b200clip_l2norm_bwd(const float* dy, const void* x, int x_is_bf16, long long ldx, const float* inv_norm,
-                                   float* dx, int accumulate, long long rows, int D, float eps, void* stream) {
+                                   float* dx, int accumulate, long long rows, int D, float eps, const float* addend,
+                                   const float* addend_scale, void* stream) {
   B200_REQUIRE(rows >= 0 && D > 0 && D % 128 == 0 && D <= MAX_D, "l2norm_bwd: D=%d must be a multiple of 128, <= %d", D, MAX_D);
-  B200_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx), "l2norm_bwd: pointers must be 16-byte aligned");
+  B200_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(addend), "l2norm_bwd: pointers must be 16-byte aligned");
   if (rows == 0) return B200_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (x_is_bf16)
     B200_DISPATCH_V(D, (l2norm_bwd_kernel<__nv_bfloat16, MAX_V><<<row_grid(rows), ROW_THREADS, 0, s>>>(
-        dy, static_cast<const __nv_bfloat16*>(x), ldx, inv_norm, dx, accumulate, (int)rows, D, eps)));
+        dy, static_cast<const __nv_bfloat16*>(x), ldx, inv_norm, dx, accumulate, (int)rows, D, eps, addend, addend_scale)));
   else
     B200_DISPATCH_V(D, (l2norm_bwd_kernel<float, MAX_V><<<row_grid(rows), ROW_THREADS, 0, s>>>(
-        dy, static_cast<const float*>(x), ldx, inv_norm, dx, accumulate, (int)rows, D, eps)));
+        dy, static_cast<const float*>(x), ldx, inv_norm, dx, accumulate, (int)rows, D, eps, addend, addend_scale)));
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -58,8 +58,15 @@ struct ScParams {
   int* status;                        // non-finite / >1000 guard flag (0426/train.py:224) or null
 };
 
-template <int MODE, int MAX_V>
-__global__ void __launch_bounds__(SC_THREADS) smallc_kernel(const ScParams p) {
+// Register blocking: a warp owns SC_R = 4 rows at a time.  Every 128-bit read of a class vector from shared memory is
+// used for 4 rows (16 FMAs per LDS.128 instead of 4): the one-row-per-warp version was shared-memory-bandwidth bound
+// (234 us at B=32768, C=32; ncu profiles/r1_launches_summary_v4.txt).  Scores are reduced 32 values at a time
+// (SC_R rows x 32/SC_R classes) with the halving exchange, so after chunk k lane L holds (row L / JC, class JC*k + L % JC);
+// SC_R = 4 for D <= 512, 2 for D <= 1024 (register budget).
+template <int MODE, int MAX_V, int SC_R>
+__global__ void __launch_bounds__(SC_THREADS, 2) smallc_kernel(const ScParams p) {
+  constexpr int JC = 32 / SC_R;                         // classes per reduction chunk
+  constexpr int NCH = SC_MAXC / JC;                     // chunks
   extern __shared__ float s_cls[];                      // [C][D]
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -89,142 +96,184 @@ __global__ void __launch_bounds__(SC_THREADS) smallc_kernel(const ScParams p) {
     Nsum = static_cast<float>(p.total_elems - static_cast<double>(Psum));
   }
   double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+  const int my_r = lane / JC, my_j = lane % JC;
+  const float kt = (MODE == SC_MLBCE || MODE == SC_HEAD2) ? p.inv_tau : 1.0f;
 
-  const long long row_stride = static_cast<long long>(gridDim.x) * (SC_THREADS / 32);
-  long long row = blockIdx.x * (SC_THREADS / 32) + warp;
-  float4 xn[MAX_V];                                       // software prefetch of the next row
+  const long long row_stride = static_cast<long long>(gridDim.x) * (SC_THREADS / 32) * SC_R;
+  for (long long row0 = (static_cast<long long>(blockIdx.x) * (SC_THREADS / 32) + warp) * SC_R; row0 < p.B; row0 += row_stride) {
+    float4 xv[SC_R][MAX_V];
+    float inv[SC_R];
 #pragma unroll
-  for (int i = 0; i < MAX_V; ++i)
-    if (i < nv && row < p.B) xn[i] = *reinterpret_cast<const float4*>(p.x + row * p.ldx + i * 128 + lane * 4);
-  for (; row < p.B; row += row_stride) {
-    float4 xv[MAX_V];
-    float ss = 0.f;
+    for (int r = 0; r < SC_R; ++r) {
+      const bool ok = row0 + r < p.B;
+      float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAX_V; ++i)
-      if (i < nv) {
-        xv[i] = xn[i];
-        ss += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+      for (int i = 0; i < MAX_V; ++i) {
+        xv[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < nv && ok) xv[r][i] = *reinterpret_cast<const float4*>(p.x + (row0 + r) * p.ldx + i * 128 + lane * 4);
+        ss += xv[r][i].x * xv[r][i].x + xv[r][i].y * xv[r][i].y + xv[r][i].z * xv[r][i].z + xv[r][i].w * xv[r][i].w;
       }
-    if (row + row_stride < p.B) {
-#pragma unroll
-      for (int i = 0; i < MAX_V; ++i)
-        if (i < nv) xn[i] = *reinterpret_cast<const float4*>(p.x + (row + row_stride) * p.ldx + i * 128 + lane * 4);
-    }
-    float inv = 1.0f;
-    if (p.normalize_x) {
-      ss = warp_sum(ss);
-      inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-      if (lane == 0 && p.xinv) p.xinv[row] = inv;
-    }
-    float part[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      part[c] = 0.f;
-      if (c < C) {
-        float a = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAX_V; ++i)
-          if (i < nv) {
-            const float4 t = *reinterpret_cast<const float4*>(&s_cls[c * D + i * 128 + lane * 4]);
-            a += xv[i].x * t.x + xv[i].y * t.y + xv[i].z * t.z + xv[i].w * t.w;
-          }
-        part[c] = a;
+      inv[r] = 1.0f;
+      if (p.normalize_x) {
+        ss = warp_sum(ss);
+        inv[r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+        if (lane == 0 && p.xinv && ok) p.xinv[row0 + r] = inv[r];
       }
     }
-    const float dot_raw = warp_colsum32_sc(part, lane);
-    const float dot = (MODE == SC_HEAD2 && lane >= c1) ? dot_raw : dot_raw * inv;   // lane c: <x_hat, cls_c> (FC rows: raw x)
-    const bool active = lane < C;
-    float y = 0.f;
-    if (MODE == SC_HEAD2) {
-      const int lc = lane < c1 ? lane : lane - c1;
-      if (active && lc < p.label_cols) y = p.labels[row * p.ld_labels + lc];
-    } else if (active && p.labels && lane < p.label_cols) y = p.labels[row * p.ld_labels + lane];
-    float coef = 0.f;                                            // d loss / d score_c (score = logit fed to sigmoid)
-    if (MODE == SC_MLBCE || (MODE == SC_HEAD2 && lane < c1)) {
-      const float s = dot * p.inv_tau;                           // :195
-      const float sc = fminf(fmaxf(s, -50.f), 50.f);             // :213
-      const float pp = 1.0f / (1.0f + expf(-sc));              // :214
-      const float qq = 1.0f - pp;                                // :215
-      if (active) {
-        acc0 += static_cast<double>(logf(pp + 1e-8f) * y);       // :218 numerator
-        acc1 += static_cast<double>(logf(qq + 1e-8f) * (1.0f - y));   // :219 numerator
-        const float inside = (fabsf(s) <= 50.f) ? 1.f : 0.f;
-        const float dpos = -y * pp * qq / ((pp + 1e-8f) * (Psum + 1e-8f));
-        const float dneg = (1.0f - y) * pp * qq / ((qq + 1e-8f) * (Nsum + 1e-8f));
-        coef = 0.5f * (dpos + dneg) * inside * gscale;
-      }
-    } else if (MODE == SC_FCBCE || MODE == SC_HEAD2) {
-      const int fc_idx = (MODE == SC_HEAD2) ? lane - c1 : lane;
-      const float z = dot + (active && p.bias ? p.bias[fc_idx] : 0.f);
-      if (active) {
-        // BCEWithLogits: max(z,0) - z*y + log1p(exp(-|z|))
-        const double bce = static_cast<double>(fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z))));
-        if (MODE == SC_HEAD2) acc2 += bce; else acc0 += bce;
-        const float sg = 1.0f / (1.0f + expf(-z));
-        coef = (sg - y) * gscale / static_cast<float>(MODE == SC_HEAD2 ? p.total_elems2 : p.total_elems);
-        const int Cf = (MODE == SC_HEAD2) ? C - c1 : C;
-        if (p.pred) p.pred[row * Cf + fc_idx] = sg > p.threshold ? 1.f : 0.f;
-        if (p.logits) p.logits[row * Cf + fc_idx] = z;
-      }
-    } else {
-      if (active) {
-        const float s = dot * p.inv_tau;                         // :881
-        const float pr = 1.0f / (1.0f + expf(-s));             // :883
-        p.pred[row * C + lane] = pr > p.threshold ? 1.f : 0.f;   // :885
-        if (p.labels) {                                          // :441-447 accuracy counters
-          acc0 += ((pr > p.threshold ? 1.f : 0.f) == y) ? 1.0 : 0.0;
-        }
-      }
-    }
-    if (MODE != SC_PREDICT) {
-      if (MODE == SC_HEAD2) {
-        if (p.coef && active && lane >= c1) p.coef[row * (C - c1) + (lane - c1)] = coef;    // FC rows only (feeds dW, db)
-      } else if (p.coef && active) p.coef[row * C + lane] = coef;
-      if (p.dx) {
-        // d x_hat = sum_c coef_c * cls_c * (1/tau) ; then through the normalisation
-        float4 g[MAX_V], g2[MAX_V];                              // g: through the normalisation ; g2: acts on x itself (HEAD2 FC rows)
+    float my_inv = inv[0];
 #pragma unroll
-        for (int i = 0; i < MAX_V; ++i) g[i] = g2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        float sdot = 0.f;                                        // <x_hat, d x_hat>
-        const float kt = (MODE == SC_MLBCE || MODE == SC_HEAD2) ? p.inv_tau : 1.0f;
-        for (int c = 0; c < c1; ++c) {
-          const float cc = __shfl_sync(0xffffffffu, coef, c) * kt;
-          const float dc = __shfl_sync(0xffffffffu, dot, c);
-          sdot += cc * dc;
+    for (int r = 1; r < SC_R; ++r) my_inv = (my_r == r) ? inv[r] : my_inv;
+    const long long row = row0 + my_r;                    // the row this lane post-processes
+    const bool row_ok = row < p.B;
+
+    float dotk[NCH], coefk[NCH];                            // chunk k: (row my_r, class JC*k + my_j)
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      dotk[k] = 0.f;
+      coefk[k] = 0.f;
+      if (JC * k >= C) continue;                            // uniform
+      float part[32];
+#pragma unroll
+      for (int j = 0; j < JC; ++j) {
+        const int c = JC * k + j;
+#pragma unroll
+        for (int r = 0; r < SC_R; ++r) part[r * JC + j] = 0.f;
+        if (c < C) {
 #pragma unroll
           for (int i = 0; i < MAX_V; ++i)
             if (i < nv) {
               const float4 t = *reinterpret_cast<const float4*>(&s_cls[c * D + i * 128 + lane * 4]);
-              g[i].x += cc * t.x; g[i].y += cc * t.y; g[i].z += cc * t.z; g[i].w += cc * t.w;
+#pragma unroll
+              for (int r = 0; r < SC_R; ++r)
+                part[r * JC + j] += xv[r][i].x * t.x + xv[r][i].y * t.y + xv[r][i].z * t.z + xv[r][i].w * t.w;
             }
         }
+      }
+      const float dot_raw = warp_colsum32_sc(part, lane);
+      const int cls_idx = JC * k + my_j;
+      const float dot = (MODE == SC_HEAD2 && cls_idx >= c1) ? dot_raw : dot_raw * my_inv;   // <x_hat, cls_c> (FC rows: raw x)
+      dotk[k] = dot;
+      const bool active = cls_idx < C && row_ok;
+      float y = 0.f;
+      if (MODE == SC_HEAD2) {
+        const int lc = cls_idx < c1 ? cls_idx : cls_idx - c1;
+        if (active && lc < p.label_cols) y = p.labels[row * p.ld_labels + lc];
+      } else if (active && p.labels && cls_idx < p.label_cols) y = p.labels[row * p.ld_labels + cls_idx];
+      float coef = 0.f;                                            // d loss / d score_c (score = logit fed to sigmoid)
+      if (MODE == SC_MLBCE || (MODE == SC_HEAD2 && cls_idx < c1)) {
+        const float s = dot * p.inv_tau;                           // :195
+        const float sc = fminf(fmaxf(s, -50.f), 50.f);             // :213
+        const float pp = 1.0f / (1.0f + expf(-sc));              // :214
+        const float qq = 1.0f - pp;                                // :215
+        if (active) {
+          acc0 += static_cast<double>(logf(pp + 1e-8f) * y);       // :218 numerator
+          acc1 += static_cast<double>(logf(qq + 1e-8f) * (1.0f - y));   // :219 numerator
+          const float inside = (fabsf(s) <= 50.f) ? 1.f : 0.f;
+          const float dpos = -y * pp * qq / ((pp + 1e-8f) * (Psum + 1e-8f));
+          const float dneg = (1.0f - y) * pp * qq / ((qq + 1e-8f) * (Nsum + 1e-8f));
+          coef = 0.5f * (dpos + dneg) * inside * gscale;
+        }
+      } else if (MODE == SC_FCBCE || MODE == SC_HEAD2) {
+        const int fc_idx = (MODE == SC_HEAD2) ? cls_idx - c1 : cls_idx;
+        const float z = dot + ((cls_idx < C) && p.bias ? p.bias[fc_idx] : 0.f);
+        if (active) {
+          // BCEWithLogits: max(z,0) - z*y + log1p(exp(-|z|))
+          const double bce = static_cast<double>(fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z))));
+          if (MODE == SC_HEAD2) acc2 += bce; else acc0 += bce;
+          const float sg = 1.0f / (1.0f + expf(-z));
+          coef = (sg - y) * gscale / static_cast<float>(MODE == SC_HEAD2 ? p.total_elems2 : p.total_elems);
+          const int Cf = (MODE == SC_HEAD2) ? C - c1 : C;
+          if (p.pred) p.pred[row * Cf + fc_idx] = sg > p.threshold ? 1.f : 0.f;
+          if (p.logits) p.logits[row * Cf + fc_idx] = z;
+        }
+      } else {
+        if (active) {
+          const float s = dot * p.inv_tau;                         // :881
+          const float pr = 1.0f / (1.0f + expf(-s));             // :883
+          p.pred[row * C + cls_idx] = pr > p.threshold ? 1.f : 0.f;   // :885
+          if (p.labels) {                                          // :441-447 accuracy counters
+            acc0 += ((pr > p.threshold ? 1.f : 0.f) == y) ? 1.0 : 0.0;
+          }
+        }
+      }
+      coefk[k] = coef;
+      if (MODE != SC_PREDICT && p.coef && active) {
         if (MODE == SC_HEAD2) {
-          for (int c = c1; c < C; ++c) {
-            const float cc = __shfl_sync(0xffffffffu, coef, c);
+          if (cls_idx >= c1) p.coef[row * (C - c1) + (cls_idx - c1)] = coef;    // FC rows only (feeds dW, db)
+        } else p.coef[row * C + cls_idx] = coef;
+      }
+    }
+
+    if (MODE != SC_PREDICT && p.dx) {
+      // d x_hat = sum_c coef_c * cls_c * (1/tau), then through the normalisation;  FC rows (HEAD2) act on x itself.
+      // <x_hat, d x_hat> per row: the JC lanes of one group hold the row's classes
+      float sd = 0.f;
 #pragma unroll
-            for (int i = 0; i < MAX_V; ++i)
-              if (i < nv) {
-                const float4 t = *reinterpret_cast<const float4*>(&s_cls[c * D + i * 128 + lane * 4]);
-                g2[i].x += cc * t.x; g2[i].y += cc * t.y; g2[i].z += cc * t.z; g2[i].w += cc * t.w;
+      for (int k = 0; k < NCH; ++k)
+        if (JC * k + my_j < c1) sd += coefk[k] * kt * dotk[k];
+#pragma unroll
+      for (int o = 1; o < JC; o <<= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+      float sdot[SC_R];
+#pragma unroll
+      for (int r = 0; r < SC_R; ++r) sdot[r] = __shfl_sync(0xffffffffu, sd, r * JC);
+#pragma unroll
+      for (int i0 = 0; i0 < MAX_V; i0 += 2) {               // two float4 column groups at a time (register budget)
+        if (i0 >= nv) continue;
+        float4 g[SC_R][2];
+#pragma unroll
+        for (int r = 0; r < SC_R; ++r) g[r][0] = g[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {              // pass 0: classes [0,c1) (through the normalisation); 1: [c1,C)
+          if (pass == 1 && MODE != SC_HEAD2) continue;
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+#pragma unroll
+            for (int j = 0; j < JC; ++j) {
+              const int c = JC * k + j;
+              const bool take = pass == 0 ? (c < c1) : (c >= c1 && c < C);   // uniform
+              if (!take) continue;
+              float cc[SC_R];
+#pragma unroll
+              for (int r = 0; r < SC_R; ++r) cc[r] = __shfl_sync(0xffffffffu, coefk[k], r * JC + j) * (pass == 0 ? kt : 1.0f);
+#pragma unroll
+              for (int ii = 0; ii < 2; ++ii) {
+                if (i0 + ii >= nv) continue;
+                const float4 t = *reinterpret_cast<const float4*>(&s_cls[c * D + (i0 + ii) * 128 + lane * 4]);
+#pragma unroll
+                for (int r = 0; r < SC_R; ++r) {
+                  g[r][ii].x += cc[r] * t.x; g[r][ii].y += cc[r] * t.y; g[r][ii].z += cc[r] * t.z; g[r][ii].w += cc[r] * t.w;
+                }
+              }
+            }
+          }
+          if (pass == 0 && p.normalize_x) {
+#pragma unroll
+            for (int r = 0; r < SC_R; ++r)
+#pragma unroll
+              for (int ii = 0; ii < 2; ++ii) {
+                if (i0 + ii >= MAX_V) continue;
+                const float4 xr = xv[r][i0 + ii];
+                const float a = inv[r], b = inv[r] * sdot[r];
+                g[r][ii].x = a * (g[r][ii].x - xr.x * b); g[r][ii].y = a * (g[r][ii].y - xr.y * b);
+                g[r][ii].z = a * (g[r][ii].z - xr.z * b); g[r][ii].w = a * (g[r][ii].w - xr.w * b);
               }
           }
         }
 #pragma unroll
-        for (int i = 0; i < MAX_V; ++i)
-          if (i < nv) {
-            float4 o = g[i];
-            if (p.normalize_x) {
-              o.x = inv * (g[i].x - xv[i].x * inv * sdot); o.y = inv * (g[i].y - xv[i].y * inv * sdot);
-              o.z = inv * (g[i].z - xv[i].z * inv * sdot); o.w = inv * (g[i].w - xv[i].w * inv * sdot);
-            }
-            if (MODE == SC_HEAD2) { o.x += g2[i].x; o.y += g2[i].y; o.z += g2[i].z; o.w += g2[i].w; }
-            float* d = p.dx + row * D + i * 128 + lane * 4;
+        for (int r = 0; r < SC_R; ++r) {
+          if (row0 + r >= p.B) continue;
+#pragma unroll
+          for (int ii = 0; ii < 2; ++ii) {
+            if (i0 + ii >= nv) continue;
+            float4 o = g[r][ii];
+            float* d = p.dx + (row0 + r) * D + (i0 + ii) * 128 + lane * 4;
             if (p.dx_accumulate) {
               const float4 old = *reinterpret_cast<const float4*>(d);
               o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
             }
             *reinterpret_cast<float4*>(d) = o;
           }
+        }
       }
     }
   }
@@ -272,45 +321,48 @@ __global__ void __launch_bounds__(SC_THREADS) smallc_kernel(const ScParams p) {
 }
 
 // out[c][d] (+)= sum_rows coef[row][c] * x[row][d] * (row_scale[row] if given) ; bias_out[c] (+)= sum_rows coef[row][c]
-// Two-stage and deterministic: each block owns a slab of rows, then reduce_partials.
+// Two-stage and deterministic: each block owns a slab of rows (coefficients staged in shared memory, padded to 32
+// classes so one broadcast LDS.128 serves 4 classes), each thread owns 2 columns d, d + 256; then reduce_partials2.
+constexpr int SO_ROWS = 256;                            // rows per block
 __global__ void __launch_bounds__(256) skinny_outer_partial_kernel(const float* __restrict__ coef, int C,
                                                                    const float* __restrict__ x, long long ldx,
                                                                    const float* __restrict__ row_scale, int rows, int D,
-                                                                   int rows_per_block, float* __restrict__ partial /*[grid][C*D + C]*/) {
-  extern __shared__ float s_coef[];                    // [rows_per_block][C]
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = min(rows, r0 + rows_per_block);
-  const int nr = r1 - r0;
-  for (int i = threadIdx.x; i < nr * C; i += blockDim.x) {
-    const int r = i / C;
-    s_coef[i] = coef[static_cast<long long>(r0) * C + i] * (row_scale ? row_scale[r0 + r] : 1.0f);
+                                                                   float* __restrict__ partial /*[grid][C*D + C]*/) {
+  __shared__ __align__(16) float s_coef[SO_ROWS][SC_MAXC];
+  const int r0 = blockIdx.x * SO_ROWS;
+  const int nr = min(rows, r0 + SO_ROWS) - r0;
+  for (int i = threadIdx.x; i < SO_ROWS * SC_MAXC; i += blockDim.x) {
+    const int r = i / SC_MAXC, c = i % SC_MAXC;
+    s_coef[r][c] = (r < nr && c < C) ? coef[static_cast<long long>(r0 + r) * C + c] * (row_scale ? row_scale[r0 + r] : 1.0f) : 0.f;
   }
   __syncthreads();
   float* out = partial + static_cast<long long>(blockIdx.x) * (static_cast<long long>(C) * D + C);
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float acc[SC_MAXC];
+  const int C4 = (C + 3) >> 2;
+  for (int d = threadIdx.x; d < D; d += 2 * blockDim.x) {
+    const int d2 = d + blockDim.x;
+    const bool has2 = d2 < D;
+    float acc0[SC_MAXC], acc1[SC_MAXC];
 #pragma unroll
-    for (int c = 0; c < SC_MAXC; ++c) acc[c] = 0.f;
-    int r = 0;
-    for (; r + 8 <= nr; r += 8) {
-      float xv[8];
+    for (int c = 0; c < SC_MAXC; ++c) acc0[c] = acc1[c] = 0.f;
+#pragma unroll 2
+    for (int r = 0; r < nr; ++r) {
+      const float* xr = x + static_cast<long long>(r0 + r) * ldx;
+      const float x0 = xr[d], x1 = has2 ? xr[d2] : 0.f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) xv[u] = x[static_cast<long long>(r0 + r + u) * ldx + d];
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int c = 0; c < SC_MAXC; ++c)
-          if (c < C) acc[c] += s_coef[(r + u) * C + c] * xv[u];
-    }
-    for (; r < nr; ++r) {
-      const float xv = x[static_cast<long long>(r0 + r) * ldx + d];
-#pragma unroll
-      for (int c = 0; c < SC_MAXC; ++c)
-        if (c < C) acc[c] += s_coef[r * C + c] * xv;
+      for (int c4 = 0; c4 < SC_MAXC / 4; ++c4) {
+        if (c4 < C4) {
+          const float4 k = *reinterpret_cast<const float4*>(&s_coef[r][c4 * 4]);
+          acc0[c4 * 4] += k.x * x0; acc0[c4 * 4 + 1] += k.y * x0; acc0[c4 * 4 + 2] += k.z * x0; acc0[c4 * 4 + 3] += k.w * x0;
+          acc1[c4 * 4] += k.x * x1; acc1[c4 * 4 + 1] += k.y * x1; acc1[c4 * 4 + 2] += k.z * x1; acc1[c4 * 4 + 3] += k.w * x1;
+        }
+      }
     }
 #pragma unroll
     for (int c = 0; c < SC_MAXC; ++c)
-      if (c < C) out[static_cast<long long>(c) * D + d] = acc[c];
+      if (c < C) {
+        out[static_cast<long long>(c) * D + d] = acc0[c];
+        if (has2) out[static_cast<long long>(c) * D + d2] = acc1[c];
+      }
   }
   if (threadIdx.x < C) {                                // bias grads use the UNSCALED coefficients
     float a = 0.f;
@@ -320,7 +372,8 @@ __global__ void __launch_bounds__(256) skinny_outer_partial_kernel(const float* 
 }
 
 __global__ void __launch_bounds__(256) reduce_partials2_kernel(const float* __restrict__ partial, long long part_stride,
-                                                               int nparts, float* __restrict__ out, int n, int accumulate) {
+                                                               int nparts, float* __restrict__ out, int n, int accumulate,
+                                                               const float* __restrict__ scale) {
   __shared__ float red[8][33];
   const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
@@ -333,6 +386,7 @@ __global__ void __launch_bounds__(256) reduce_partials2_kernel(const float* __re
     float v = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) v += red[k][cx];
+    if (scale) v *= *scale;
     out[col] = accumulate ? out[col] + v : v;
   }
 }
@@ -366,8 +420,9 @@ __global__ void __launch_bounds__(1024) sum_f32_kernel(const float* __restrict__
 }
 
 static int sc_grid(long long rows) {
-  const long long want = (rows + SC_THREADS / 32 - 1) / (SC_THREADS / 32);
-  const long long cap = static_cast<long long>(num_sms()) * 4;
+  const long long per_block = (SC_THREADS / 32) * 4;
+  const long long want = (rows + per_block - 1) / per_block;
+  const long long cap = static_cast<long long>(num_sms()) * 2;
   return static_cast<int>(std::max<long long>(1, std::min(want, cap)));
 }
 
@@ -376,11 +431,11 @@ static int launch_smallc(const ScParams& p, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(p.C) * p.D * sizeof(float);
   const int grid = sc_grid(p.B);
   if (p.D <= 512) {
-    auto k = smallc_kernel<MODE, 4>;
+    auto k = smallc_kernel<MODE, 4, 4>;
     B200_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, SC_THREADS, smem, s>>>(p);
   } else {
-    auto k = smallc_kernel<MODE, 8>;
+    auto k = smallc_kernel<MODE, 8, 2>;
     B200_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, SC_THREADS, smem, s>>>(p);
   }
@@ -402,7 +457,7 @@ using namespace b200;
 
 extern "C" size_t b200clip_smallc_workspace_bytes(long long rows, int C, int D) {
   const size_t loss_part = static_cast<size_t>(sc_grid(rows)) * 3 * sizeof(double) + 256;
-  const int rpb = 64;
+  const int rpb = SO_ROWS;
   const size_t outer = static_cast<size_t>((rows + rpb - 1) / rpb) * (static_cast<size_t>(C) * D + C) * sizeof(float);
   return loss_part + outer + 256;
 }
@@ -471,22 +526,22 @@ extern "C" int b200clip_predict_multilabel(const float* image_features, long lon
 
 // out_w[C,D] (+)= coef^T (x * row_scale) ; out_b[C] (+)= column sums of coef
 extern "C" int b200clip_skinny_outer(const float* coef, int C, const float* x, long long ldx, const float* row_scale,
-                                     long long rows, int D, float* out_w, float* out_b, int accumulate, void* workspace,
-                                     size_t workspace_bytes, void* stream) {
+                                     long long rows, int D, float* out_w, float* out_b, int accumulate,
+                                     const float* out_scale, void* workspace, size_t workspace_bytes, void* stream) {
   B200_REQUIRE(rows > 0 && C > 0 && C <= SC_MAXC && D > 0, "skinny_outer: bad shape");
   if (workspace_bytes < b200clip_smallc_workspace_bytes(rows, C, D)) return fail(B200_ERR_WORKSPACE, "skinny_outer: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int rpb = 64;
+  const int rpb = SO_ROWS;
   const int nblk = static_cast<int>((rows + rpb - 1) / rpb);
   float* partial = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + static_cast<size_t>(sc_grid(rows)) * 3 * sizeof(double) + 256);
   const long long stride = static_cast<long long>(C) * D + C;
-  skinny_outer_partial_kernel<<<nblk, 256, rpb * C * sizeof(float), s>>>(coef, C, x, ldx, row_scale, (int)rows, D, rpb, partial);
+  skinny_outer_partial_kernel<<<nblk, 256, 0, s>>>(coef, C, x, ldx, row_scale, (int)rows, D, partial);
   B200_LAUNCH_CHECK();
   const int nw = C * D;
-  reduce_partials2_kernel<<<(nw + 31) / 32, 256, 0, s>>>(partial, stride, nblk, out_w, nw, accumulate);
+  reduce_partials2_kernel<<<(nw + 31) / 32, 256, 0, s>>>(partial, stride, nblk, out_w, nw, accumulate, out_scale);
   B200_LAUNCH_CHECK();
   if (out_b) {
-    reduce_partials2_kernel<<<1, 256, 0, s>>>(partial + nw, stride, nblk, out_b, C, accumulate);
+    reduce_partials2_kernel<<<1, 256, 0, s>>>(partial + nw, stride, nblk, out_b, C, accumulate, out_scale);
     B200_LAUNCH_CHECK();
   }
   return B200_OK;

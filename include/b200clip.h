@@ -41,8 +41,10 @@ int b200clip_gemm_bf16(const void* a, const void* b, int a_mn_major, int b_mn_ma
 /* ---- a-L2: F.normalize(x, dim=-1), eps 1e-12 -- 0426/train.py:191-192, :971; 0426/disease_analysis.py:332 ----- */
 int b200clip_l2norm_fwd(const void* x, int x_is_bf16, long long ldx, void* y_bf16, float* y_f32, float* inv_norm,
                         long long rows, int D, float eps, void* stream);
+/* dx (+)= d/dx normalize(x) . dy  [+ addend * *addend_scale]   (addend [rows,D] f32 and its device scalar are optional) */
 int b200clip_l2norm_bwd(const float* dy, const void* x, int x_is_bf16, long long ldx, const float* inv_norm, float* dx,
-                        int accumulate, long long rows, int D, float eps, void* stream);
+                        int accumulate, long long rows, int D, float eps, const float* addend, const float* addend_scale,
+                        void* stream);
 
 /* ---- LayerNorm tail of the projection block -- nn.LayerNorm(512), 0426/train.py:82,95 ------------------------ */
 int b200clip_layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y_f32, void* yhat_bf16,
@@ -112,9 +114,10 @@ int b200clip_fc_bce_fwd_bwd(const float* x, long long ldx, const float* weight, 
                             const float* grad_scale, float* d_x, int d_x_accumulate, float* coef, float* pred,
                             float* logits, double* sums, float* loss, void* workspace, size_t workspace_bytes,
                             void* stream);
+/* out_w[C,D] (+)= *out_scale * coef^T (x * row_scale) ; out_b[C] (+)= *out_scale * colsum(coef)   (out_scale optional) */
 int b200clip_skinny_outer(const float* coef, int C, const float* x, long long ldx, const float* row_scale, long long rows,
-                          int D, float* out_w, float* out_b, int accumulate, void* workspace, size_t workspace_bytes,
-                          void* stream);
+                          int D, float* out_w, float* out_b, int accumulate, const float* out_scale, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* a-B + a-A fused for the head step: one pass over the image features serves both BCE heads (classes [0,c1) = class
  * texts, [c1,c1+c2) = FC adapter rows).  sums[3] = {text pos numerator, text neg numerator, FC BCE sum}. */
