@@ -8,7 +8,7 @@ from .modules import MODEL_CONFIG, ClassificationAdapter, ImageProjection, TextP
 from .losses import contrastive_loss, fc_adapter_bce, multilabel_contrastive_loss, predict_multilabel  # noqa: F401
 from .zero_shot import (predict_zero_shot, unpack_mask, zero_shot_posneg, zero_shot_threshold,  # noqa: F401
                         zero_shot_topk)
-from .head import ClipHead, ClipHeadFn  # noqa: F401
+from .head import ClipHead, ClipHeadFn, GraphedHeadStep  # noqa: F401
 from .ops import normalize  # noqa: F401
 from .install import install  # noqa: F401
 

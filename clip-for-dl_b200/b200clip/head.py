@@ -30,76 +30,97 @@ PARAM_ORDER = ("iw1", "ib1", "iw2", "ib2", "ig", "ibeta", "tw1", "tb1", "tw2", "
 _world, _rank = dp.world, dp.rank
 
 
+def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop_p, drop_seed, params, need_grad,
+                 need_dx=(True, True)):
+    """Forward pass of the fused head on this rank's local pairs.  Returns (loss, parts, state); `state` is what
+    head_backward needs (None when need_grad is False).  Plain function: ClipHeadFn wraps it for autograd,
+    GraphedHeadStep calls it directly while capturing."""
+    (iw1, ib1, iw2, ib2, ig, ibeta, tw1, tb1, tw2, tb2, tg, tbeta, fw, fb) = params
+    ops.require_cuda(x_img, x_txt, class_text, labels, iw1)
+    W, rank = _world(group), _rank(group)
+    b_loc = x_img.shape[0]
+    b_glob = b_loc * W
+    row0 = rank * b_loc
+    xi, xt = ops.cast_bf16(x_img), ops.cast_bf16(x_txt)
+    iw1b, iw2b, tw1b, tw2b = (ops.cast_bf16(w) for w in (iw1, iw2, tw1, tw2))
+    f = ops._f32c
+    # text first so its all-gather can overlap the image projection
+    # independent dropout streams for the two projections (seed, seed+1)
+    y_txt, that_loc, inv_txt, saved_t = ops.proj_fwd(xt, tw1b, f(tb1), tw2b, f(tb2), f(tg), f(tbeta), want_yhat=True,
+                                                     drop_p=drop_p, drop_seed=drop_seed + 1)
+    that_all, work = dp.gather_rows(that_loc, group, async_op=True)
+    y_img, ihat, inv_img, saved_i = ops.proj_fwd(xi, iw1b, f(ib1), iw2b, f(ib2), f(ig), f(ibeta), want_yhat=True,
+                                                 drop_p=drop_p, drop_seed=drop_seed)
+    labels_f = f(labels)
+    lsum = ops._label_sum(labels_f)
+    if W > 1:
+        dp.sum_across(lsum, group)
+        work.wait()
+    l_nce, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, group=group if W > 1 else None)
+    C = class_text.shape[0]
+    Cf = fw.shape[0]
+    # one pass over y_img serves both BCE heads, forward AND backward: the input gradient d_bce (for upstream grad 1)
+    # and the FC coefficients are produced here; backward only scales them by the incoming gradient.
+    d_bce = torch.empty_like(y_img) if need_grad else None
+    l_bce, l_fc, status, both, coef = ops.bce_heads(y_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
+                                                    total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
+                                                    dx_out=d_bce, want_coef=need_grad, finalize=(W == 1))
+    if W > 1:
+        dp.sum_across(both, group)
+        l_bce, l_fc = dp.bce_losses_from_sums(both, lsum, float(b_glob) * C, float(b_glob) * Cf)
+    loss = l_nce + l_bce + l_fc
+    parts = (l_nce.detach(), l_bce.detach(), l_fc.detach())
+    if not need_grad:
+        return loss, parts, None
+    tensors = (xi, xt, iw1b, iw2b, tw1b, tw2b, f(ig), f(tg), y_img, y_txt, ihat, that_all, inv_img, inv_txt, rinvh, cinvh,
+               d_bce, coef, *saved_i, *saved_t)
+    meta = dict(tau_nce=tau_nce, group=group, W=W, row0=row0, need_dx=tuple(need_dx), in_dtypes=(x_img.dtype, x_txt.dtype),
+                drop=(float(drop_p), int(drop_seed)), has_fc_bias=fb is not None)
+    return loss, parts, (tensors, meta)
+
+
+def head_backward(tensors, meta, g):
+    """Backward pass: returns (d_x_img, d_x_txt, [14 parameter gradients in PARAM_ORDER])."""
+    (xi, xt, iw1b, iw2b, tw1b, tw2b, ig, tg, y_img, y_txt, ihat, that_all, inv_img, inv_txt, rinvh, cinvh, d_bce, coef,
+     *rest) = tensors
+    saved_i, saved_t = tuple(rest[:5]), tuple(rest[5:])
+    group, row0 = meta["group"], meta["row0"]
+    need_dxi, need_dxt = meta["need_dx"]
+    drop_p, drop_seed = meta["drop"]
+    g = ops._f32c(g).reshape(())
+    d_ihat, d_that = ops.infonce_backward(ihat, that_all, meta["tau_nce"], rinvh, cinvh, g, row0=row0)
+    d_that_loc, work = dp.scatter_sum_rows(d_that, group, async_op=True)
+    # image side: through the L2 normalisation, plus g * (the two BCE heads' input gradient from the forward pass)
+    dy_img = ops.l2norm_bwd(d_ihat, y_img, inv_img, addend=d_bce, addend_scale=g)
+    dfw, dfb = ops.skinny_outer(coef, y_img, want_bias=True, out_scale=g)
+    gi = ops.proj_bwd(dy_img, xi, iw1b, iw2b, ig, saved_i, need_dxi, meta["in_dtypes"][0], drop_p=drop_p, drop_seed=drop_seed)
+    if work is not None:
+        work.wait()
+    dy_txt = ops.l2norm_bwd(d_that_loc, y_txt, inv_txt)
+    gt = ops.proj_bwd(dy_txt, xt, tw1b, tw2b, tg, saved_t, need_dxt, meta["in_dtypes"][1], drop_p=drop_p, drop_seed=drop_seed + 1)
+    grads = [gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], gt[1], gt[2], gt[3], gt[4], gt[5], gt[6], dfw, dfb]
+    grads = dp.allreduce_flat(grads, group)     # SUM, not mean: every loss term is normalised by the GLOBAL batch
+    if not meta["has_fc_bias"]:
+        grads[-1] = None
+    return gi[0], gt[0], grads
+
+
 class ClipHeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop_p, drop_seed, *params):
-        (iw1, ib1, iw2, ib2, ig, ibeta, tw1, tb1, tw2, tb2, tg, tbeta, fw, fb) = params
-        ops.require_cuda(x_img, x_txt, class_text, labels, iw1)
-        W, rank = _world(group), _rank(group)
-        b_loc = x_img.shape[0]
-        b_glob = b_loc * W
-        row0 = rank * b_loc
-        xi, xt = ops.cast_bf16(x_img), ops.cast_bf16(x_txt)
-        iw1b, iw2b, tw1b, tw2b = (ops.cast_bf16(w) for w in (iw1, iw2, tw1, tw2))
-        f = ops._f32c
-        # text first so its all-gather can overlap the image projection
-        # independent dropout streams for the two projections (seed, seed+1)
-        y_txt, that_loc, inv_txt, saved_t = ops.proj_fwd(xt, tw1b, f(tb1), tw2b, f(tb2), f(tg), f(tbeta), want_yhat=True,
-                                                         drop_p=drop_p, drop_seed=drop_seed + 1)
-        that_all, work = dp.gather_rows(that_loc, group, async_op=True)
-        y_img, ihat, inv_img, saved_i = ops.proj_fwd(xi, iw1b, f(ib1), iw2b, f(ib2), f(ig), f(ibeta), want_yhat=True,
-                                                     drop_p=drop_p, drop_seed=drop_seed)
-        labels_f = f(labels)
-        lsum = ops._label_sum(labels_f)
-        if W > 1:
-            dp.sum_across(lsum, group)
-            work.wait()
-        l_nce, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, group=group if W > 1 else None)
-        C = class_text.shape[0]
-        Cf = fw.shape[0]
-        # one pass over y_img serves both BCE heads, forward AND backward: the input gradient d_bce (for upstream grad 1)
-        # and the FC coefficients are produced here; backward only scales them by the incoming gradient.
-        need_grad = any(t.requires_grad for t in (x_img, x_txt, *params) if t is not None)
-        d_bce = torch.empty_like(y_img) if need_grad else None
-        l_bce, l_fc, status, both, coef = ops.bce_heads(y_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
-                                                        total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
-                                                        dx_out=d_bce, want_coef=need_grad, finalize=(W == 1))
-        if W > 1:
-            dp.sum_across(both, group)
-            l_bce, l_fc = dp.bce_losses_from_sums(both, lsum, float(b_glob) * C, float(b_glob) * Cf)
-        loss = l_nce + l_bce + l_fc
-        ctx.save_for_backward(xi, xt, iw1b, iw2b, tw1b, tw2b, f(ig), f(tg), y_img, y_txt, ihat,
-                              that_all, inv_img, inv_txt, rinvh, cinvh, d_bce, coef, *saved_i, *saved_t)
-        ctx.has_fc_bias = fb is not None
-        ctx.meta = (tau_nce, tau_bce, group, W, row0, b_loc, b_glob, x_img.requires_grad, x_txt.requires_grad)
-        ctx.in_dtypes = (x_img.dtype, x_txt.dtype)
-        ctx.drop = (float(drop_p), int(drop_seed))
-        ctx.parts = (l_nce.detach(), l_bce.detach(), l_fc.detach())
+        need_grad = any(t is not None and t.requires_grad for t in (x_img, x_txt, *params))
+        loss, parts, state = head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop_p, drop_seed, params,
+                                          need_grad, need_dx=(x_img.requires_grad, x_txt.requires_grad))
+        if state is not None:
+            ctx.save_for_backward(*state[0])
+            ctx.meta = state[1]
+        ctx.parts = parts
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        (xi, xt, iw1b, iw2b, tw1b, tw2b, ig, tg, y_img, y_txt, ihat, that_all, inv_img, inv_txt,
-         rinvh, cinvh, d_bce, coef, *rest) = ctx.saved_tensors
-        saved_i, saved_t = tuple(rest[:5]), tuple(rest[5:])
-        tau_nce, tau_bce, group, W, row0, b_loc, b_glob, need_dxi, need_dxt = ctx.meta
-        g = ops._f32c(g).reshape(())
-        d_ihat, d_that = ops.infonce_backward(ihat, that_all, tau_nce, rinvh, cinvh, g, row0=row0)
-        d_that_loc, work = dp.scatter_sum_rows(d_that, group, async_op=True)
-        # image side: through the L2 normalisation, plus g * (the two BCE heads' input gradient from the forward pass)
-        dy_img = ops.l2norm_bwd(d_ihat, y_img, inv_img, addend=d_bce, addend_scale=g)
-        dfw, dfb = ops.skinny_outer(coef, y_img, want_bias=True, out_scale=g)
-        if not ctx.has_fc_bias:
-            dfb = None
-        gi = ops.proj_bwd(dy_img, xi, iw1b, iw2b, ig, saved_i, need_dxi, ctx.in_dtypes[0], drop_p=ctx.drop[0], drop_seed=ctx.drop[1])
-        if work is not None:
-            work.wait()
-        dy_txt = ops.l2norm_bwd(d_that_loc, y_txt, inv_txt)
-        gt = ops.proj_bwd(dy_txt, xt, tw1b, tw2b, tg, saved_t, need_dxt, ctx.in_dtypes[1], drop_p=ctx.drop[0],
-                          drop_seed=ctx.drop[1] + 1)
-        grads = [gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], gt[1], gt[2], gt[3], gt[4], gt[5], gt[6], dfw, dfb]
-        grads = dp.allreduce_flat(grads, group)     # SUM, not mean: every loss term is normalised by the GLOBAL batch
-        return (gi[0], gt[0], None, None, None, None, None, None, None, *grads)
+        dxi, dxt, grads = head_backward(ctx.saved_tensors, ctx.meta, g)
+        return (dxi, dxt, None, None, None, None, None, None, None, *grads)
 
 
 class ClipHead(nn.Module):
@@ -132,3 +153,79 @@ class ClipHead(nn.Module):
         self.last_dropout_seed = seed
         return ClipHeadFn.apply(image_embeddings, text_embeddings, class_text_features, labels, self.tau_nce, self.tau_bce,
                                 self.group, p, seed, *self.params())
+
+
+class GraphedHeadStep:
+    """One head step (forward + backward, collectives included) captured ONCE into a CUDA graph and replayed.
+
+    At per-rank batches of a few thousand pairs the step is ~40 kernels of 5-100 us each: launched one by one from Python
+    the host, not the GPU, sets the step time (~0.9 ms of enqueue work per step, tools/host_overhead.py).  Replaying the
+    captured graph costs one launch.  Shapes are fixed at capture; inputs are copied into static device buffers (host or
+    device tensors accepted), gradients land in the parameters' .grad and in `grad_image` / `grad_text`:
+
+        step = GraphedHeadStep(head, x_img, x_txt, class_text, labels)
+        loss = step(x_img, x_txt, class_text, labels)      # same semantics as head(...) followed by loss.backward()
+
+    Parameter gradients are OVERWRITTEN by each replay (equivalent to zero_grad + backward).  Dropout must be off
+    (the keep-mask seed is a launch argument and would be frozen into the graph)."""
+
+    def __init__(self, head: "ClipHead", image_embeddings, text_embeddings, class_text_features, labels, warmup: int = 3,
+                 input_grads: bool = True):
+        if head.training and head.dropout_rate > 0:
+            raise RuntimeError("GraphedHeadStep: dropout seeds cannot be captured; use head.eval() or dropout_rate=0")
+        ops.require_cuda(image_embeddings, text_embeddings, class_text_features, labels)
+        self.head = head
+        self.x_img = image_embeddings.detach().clone()
+        self.x_txt = text_embeddings.detach().clone()
+        self.class_text = class_text_features.detach().clone()
+        self.labels = labels.detach().clone()
+        self.input_grads = input_grads
+        self._one = torch.ones((), dtype=torch.float32, device=self.x_img.device)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.x_img.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):               # lazy init (function attributes, NCCL channels) outside capture
+                self._run()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.loss, self.grad_image, self.grad_text, grads = self._run()
+        self._param_grads = list(zip(self.head.params(), grads))
+        self.bind_grads()
+
+    @torch.no_grad()
+    def _run(self):
+        """forward + backward as plain calls (no autograd engine: its worker thread and AccumulateGrad streams do not
+        belong in a capture)."""
+        h = self.head
+        loss, parts, (tensors, meta) = head_forward(self.x_img, self.x_txt, self.class_text, self.labels, h.tau_nce, h.tau_bce,
+                                                    h.group, 0.0, 0, h.params(), True,
+                                                    need_dx=(self.input_grads, self.input_grads))
+        dxi, dxt, grads = head_backward(tensors, meta, self._one)
+        return loss, dxi, dxt, grads
+
+    def bind_grads(self):
+        """Point every parameter's .grad at the tensor the graph writes (again, if something re-bound .grad since the
+        capture: optimizer.zero_grad(set_to_none=True) or an eager backward)."""
+        for p, g in self._param_grads:
+            if p is not None:
+                p.grad = g
+
+    def close(self):
+        """Release the captured graph.  Call before torch.distributed.destroy_process_group(): NCCL waits for every graph
+        that holds its kernels, so tearing the communicator down with a live graph hangs."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+
+    def __call__(self, image_embeddings=None, text_embeddings=None, class_text_features=None, labels=None):
+        with torch.no_grad():
+            for dst, src in ((self.x_img, image_embeddings), (self.x_txt, text_embeddings),
+                             (self.class_text, class_text_features), (self.labels, labels)):
+                if src is not None and src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss

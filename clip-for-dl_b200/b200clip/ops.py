@@ -225,7 +225,7 @@ def infonce_forward(i_hat: torch.Tensor, t_hat: torch.Tensor, temperature: float
     c = torch.empty((b_glob,), dtype=torch.float32, device=dev)
     ev = KERNEL_EVENTS["infonce_fwd"]
     if ev is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = _timing_events()
         e0.record()
     check(lib.b200clip_infonce_fwd_stats(ptr(i_hat), ptr(t_hat), D, b_loc, b_glob, temperature, ptr(r), ptr(c), ptr(ws),
                                          ws.numel(), stream_ptr()), "infonce_fwd_stats")
@@ -252,6 +252,13 @@ def infonce_forward(i_hat: torch.Tensor, t_hat: torch.Tensor, temperature: float
 KERNEL_EVENTS = {"infonce_bwd": None, "infonce_fwd": None}
 
 
+def _timing_events():
+    """Timing event pair; inside a CUDA-graph capture they become external event-record nodes, re-recorded by every
+    replay, so the kernel between them can be timed on the launching stream while the graph runs."""
+    ext = torch.cuda.is_current_stream_capturing()
+    return (torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext))
+
+
 def infonce_backward(i_hat, t_hat, temperature, rinvh, cinvh, grad_scale: Optional[torch.Tensor], row0: int = 0):
     """Returns d_i [b_loc, D] f32 and d_t_partial [b_glob, D] f32 (this rank's contribution)."""
     b_loc, D = i_hat.shape
@@ -264,7 +271,7 @@ def infonce_backward(i_hat, t_hat, temperature, rinvh, cinvh, grad_scale: Option
         gs = _f32c(grad_scale.reshape(()))
     ev = KERNEL_EVENTS["infonce_bwd"]
     if ev is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = _timing_events()
         e0.record()
     check(load().b200clip_infonce_bwd(ptr(i_hat), ptr(t_hat), D, b_loc, b_glob, row0, temperature, ptr(rinvh), ptr(cinvh),
                                       ptr(gs), ptr(d_i), ptr(d_t), stream_ptr()), "infonce_bwd")

@@ -20,7 +20,9 @@ LIB = os.path.join(OUT_DIR, "libb200clip.so")
 SOURCES = ["gemm.cu", "rowops.cu", "smallc.cu", "zeroshot.cu", "infonce.cu", "proj.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DNDEBUG"]
+         "-Xcompiler", "-fPIC", "-DNDEBUG"]
+if os.environ.get("B200CLIP_NCE_PROF"):          # wait-cycle instrumentation of the InfoNCE backward (tools/nce_prof.py)
+    FLAGS.append("-DB200CLIP_NCE_PROF")
 
 
 def _digest() -> str:

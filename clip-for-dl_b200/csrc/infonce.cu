@@ -293,7 +293,40 @@ struct NceBwdParams {
   float k1, k2;
   float out_scale;          // 1 / (B_glob * tau)
   const float* grad_scale;  // optional device scalar multiplied into out_scale (upstream dLoss)
+  long long* prof;          // debug: per-role wait-cycle counters of one cluster (b200clip_debug_set_nce_prof) or null
 };
+
+// debug instrumentation (build with B200CLIP_NCE_PROF=1 python build.py): cycles spent inside each wait, accumulated per
+// role, and a per-tile timeline, for one cluster.  Compiled out of the product build.
+#ifdef B200CLIP_NCE_PROF
+#define NCE_PW(k, call)                      \
+  do {                                       \
+    if (prof_on) {                           \
+      const long long t0_ = clock64();       \
+      call;                                  \
+      wacc[k] += clock64() - t0_;            \
+    } else {                                 \
+      call;                                  \
+    }                                        \
+  } while (0)
+#define NCE_TS(n, k)                                                                             \
+  do {                                                                                             \
+    if (prof_on && lane == 0 && (n) >= 512 && (n) < 544) p.prof[128 + h * 256 + ((n)-512) * 8 + (k)] = clock64(); \
+  } while (0)
+#define NCE_PROF_BEGIN() long long wacc[4] = {0, 0, 0, 0}; const long long tstart_ = prof_on ? clock64() : 0
+#define NCE_PROF_END(role)                                                              \
+  do {                                                                                  \
+    if (prof_on && lane == 0) {                                                         \
+      long long* o_ = p.prof + ((h * 8 + (role)) * 8);                                  \
+      o_[0] = clock64() - tstart_; o_[1] = wacc[0]; o_[2] = wacc[1]; o_[3] = wacc[2]; o_[4] = wacc[3]; \
+    }                                                                                   \
+  } while (0)
+#else
+#define NCE_PW(k, call) call
+#define NCE_TS(n, k) do { } while (0)
+#define NCE_PROF_BEGIN() do { } while (0)
+#define NCE_PROF_END(role) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 nce_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constant__ CUtensorMap tmap_y0,
@@ -610,6 +643,9 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef B200CLIP_NCE_PROF
+  const bool prof_on = p.prof != nullptr && dir == 0 && rb == 100;
+#endif
   const int nt = (ncols + BWD_BN - 1) / BWD_BN;     // all tiles
   const int nown = (nt - h + 1) / 2;                // tiles owned by this CTA: n = 2m + h
 
@@ -659,8 +695,10 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
     const int k_in = h * 256, k_out = (1 - h) * 256;
+    NCE_PROF_BEGIN();
     for (int n = 0; n < nt; ++n) {
-      mbar_wait_a(be0 + 8 * ib, pb ^ 1);
+      NCE_PW(0, mbar_wait_a(be0 + 8 * ib, pb ^ 1));
+      NCE_TS(n, 0);
       if (elect_one()) {
         mbar_arrive_expect_tx_a(bf0 + 8 * ib, BWD_GROUP_BYTES);
 #pragma unroll
@@ -670,7 +708,7 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
       __syncwarp();
       if (++ib == BWD4_TB) { ib = 0; pb ^= 1; }
       if ((n & 1) == h) {
-        mbar_wait_a(ae0 + 8 * ia, pa ^ 1);
+        NCE_PW(1, mbar_wait_a(ae0 + 8 * ia, pa ^ 1));
         if (elect_one()) {
           mbar_arrive_expect_tx_a(af0 + 8 * ia, BWD_GROUP_BYTES);
 #pragma unroll
@@ -681,6 +719,7 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
         if (++ia == BWD4_TA) { ia = 0; pa ^= 1; }
       }
     }
+    NCE_PROF_END(0);
   } else if (warp == 1) {
     // ===================== S-MMA issuer (own tiles only) =====================
     constexpr uint32_t idesc_s = make_idesc_bf16(128, BWD_BN, false, false);
@@ -697,10 +736,12 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
     int ib = 0;
     uint32_t pb = 0;
     if (h == 1) { ib = 1 % BWD4_TB; }                 // first own tile is n = 1
+    NCE_PROF_BEGIN();
     for (int m = 0; m < nown; ++m) {
       const int buf = m & 1;
-      mbar_wait_a(se0 + 8 * buf, ((m >> 1) & 1) ^ 1);
-      mbar_wait_a(bf0 + 8 * ib, pb);
+      NCE_PW(0, mbar_wait_a(se0 + 8 * buf, ((m >> 1) & 1) ^ 1));
+      NCE_PW(1, mbar_wait_a(bf0 + 8 * ib, pb));
+      NCE_TS(2 * m + h, 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_s + buf * BWD_BN;
       if (elect_one()) {
@@ -712,7 +753,7 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
             mma_ts_lo(d_tmem, tmem_x + c * 32 + j * 8, yb + c * (BWD_SLOT_BYTES >> 4) + 2 * j, idesc_s, (c | j) != 0);
       }
       __syncwarp();
-      mbar_wait_a(af0 + 8 * ia, pa);
+      NCE_PW(2, mbar_wait_a(af0 + 8 * ia, pa));
       tc_fence_after();
       if (elect_one()) {
         const uint32_t ya = a_lo0 + ia * (BWD_GROUP_BYTES >> 4);
@@ -725,12 +766,14 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
         tc_commit_a(sf0 + 8 * buf);
       }
       __syncwarp();
+      NCE_TS(2 * m + h, 2);
       if (++ia == BWD4_TA) { ia = 0; pa ^= 1; }
       // advance the ring-B cursor by two tiles
 #pragma unroll
       for (int t = 0; t < 2; ++t)
         if (++ib == BWD4_TB) { ib = 0; pb ^= 1; }
     }
+    NCE_PROF_END(1);
   } else if (warp == 2) {
     // ===================== dX-MMA issuer (every tile, this CTA's D-half) =====================
     constexpr uint32_t idesc_g = make_idesc_bf16(128, 256, false, true);
@@ -739,13 +782,16 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
     const uint32_t y_lo0 = desc_lo(smem_u32(sB), BWD_SLOT_BYTES);
     int ib = 0;
     uint32_t pb = 0;
+    NCE_PROF_BEGIN();
     for (int n = 0; n < nt; ++n) {
       const int par = n & 1, kbuf = (n >> 1) & 1;
       const int slot = par * 2 + kbuf;
       if (elect_one()) mbar_arrive_expect_tx_a(gf0 + 8 * slot, 128 * 64);   // arm: the G tile arrives as 128 x 64 B of st.async
       __syncwarp();
-      mbar_wait_a(bf0 + 8 * ib, pb);                // tiles owned by the peer were never waited on by the S issuer
-      mbar_wait_cluster_a(gf0 + 8 * slot, (n >> 2) & 1);
+      NCE_PW(0, mbar_wait_a(bf0 + 8 * ib, pb));     // tiles owned by the peer were never waited on by the S issuer
+      if (par == h) NCE_PW(1, mbar_wait_cluster_a(gf0 + 8 * slot, (n >> 2) & 1));
+      else NCE_PW(2, mbar_wait_cluster_a(gf0 + 8 * slot, (n >> 2) & 1));
+      NCE_TS(n, 5);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t yb = y_lo0 + ib * (BWD_GROUP_BYTES >> 4);
@@ -756,8 +802,10 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
         tc_commit_multicast_a(ge0 + 8 * slot, 0x3);   // both CTAs' g_empty[slot]: the owner refills once BOTH have read it
       }
       __syncwarp();
+      NCE_TS(n, 6);
       if (++ib == BWD4_TB) { ib = 0; pb ^= 1; }
     }
+    NCE_PROF_END(2);
     if (elect_one()) tc_commit(acc_full);
     __syncwarp();
   } else if (warp >= 4) {
@@ -796,6 +844,7 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
       mbar_arrive_a(smem_u32(xt_full));
     }
     uint32_t ph = 0;
+    NCE_PROF_BEGIN();
     for (int m = w; m < nown; m += 2) {
       const int n = 2 * m + h;
       const int col0 = n * BWD_BN;
@@ -812,11 +861,12 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 32; ++i) cs[i] = (col0 + i < ncols) ? cstat[col0 + i] : 0.f;
       }
-      mbar_wait_a(sf, ph);
+      NCE_PW(0, mbar_wait_a(sf, ph));
+      if (q == 0) NCE_TS(n, 3);
       tc_fence_after();
       uint32_t v[32];
       tmem_ld_x32(tmem_s + lane_base + w * BWD_BN, v);
-      tmem_ld_wait();
+      NCE_PW(2, tmem_ld_wait());
       tc_fence_before();
       mbar_arrive_a(se);
       uint32_t packed[16];
@@ -842,7 +892,7 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
         }
       }
       // slot (h, w) is reused every second own tile: wait until BOTH CTAs' dX MMAs of its previous use have read it
-      mbar_wait_cluster_a(ge, ((m >> 1) & 1) ^ 1);
+      NCE_PW(1, mbar_wait_cluster_a(ge, ((m >> 1) & 1) ^ 1));
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint32_t off = static_cast<uint32_t>(((h * 4 + c) ^ (row_l & 7)) << 4);
@@ -850,8 +900,10 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
         st_async_v4(g_row_mine + off, val, gf_mine);
         st_async_v4(g_row_peer + off, val, gf_peer);
       }
+      if (q == 0) NCE_TS(n, 4);
       ph ^= 1;
     }
+    if (q == 0) NCE_PROF_END(3 + w);
     mbar_wait(acc_full, 0);
     tc_fence_after();
     float scale = p.out_scale;
@@ -1061,6 +1113,10 @@ extern "C" int b200clip_infonce_loss(const void* i_hat, const void* t_hat, int D
   return B200_OK;
 }
 
+static long long* g_nce_prof = nullptr;
+// debug only: device buffer of 128 int64 receiving the wait-cycle counters of one cluster of the next backward launches
+extern "C" void b200clip_debug_set_nce_prof(void* buf) { g_nce_prof = static_cast<long long*>(buf); }
+
 extern "C" int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D, long long b_loc, long long b_glob,
                                     long long row0, float temperature, const float* rinvh, const float* cinvh,
                                     const float* grad_scale, float* d_i, float* d_t_partial, void* stream) {
@@ -1082,6 +1138,7 @@ extern "C" int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D,
   p.k1 = LOG2E / temperature; p.k2 = LOG2E / temperature;
   p.out_scale = 1.0f / (static_cast<float>(b_glob) * temperature);
   p.grad_scale = grad_scale;
+  p.prof = g_nce_prof;
   constexpr int smem = nce_bwd_smem_bytes();
   static bool configured = false;
   static int variant = 4;            // 4: CTA-pair kernel (default); 1: independent D-half CTAs (B200CLIP_BWD_VARIANT=1)

@@ -27,6 +27,9 @@ int b200clip_version(void);
 const char* b200clip_last_error_string(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long b200clip_launch_count(void);
+/* debug: device buffer (1024 x int64) that receives per-role mbarrier wait-cycle counters of one cluster of the InfoNCE
+ * backward kernel on the following launches; NULL switches it off (tools/nce_prof.py) */
+void b200clip_debug_set_nce_prof(void* device_buf);
 
 /* ---- generic tensor-core GEMM (tcgen05/TMEM, TMA) ------------------------------------------------------------
  * D[M,N] = A*B, bf16 operands, fp32 accumulate.  a_mn_major=0: a[M][K], =1: a[K][M];  b_mn_major=0: b[N][K]

@@ -32,7 +32,14 @@ torch.cuda.synchronize()
 out = {"loss": loss.item(), "dxi": xi.grad.float().cpu(), "dxt": xt.grad.float().cpu(),
        "gw": head.image_projector.fc.weight.grad.cpu(), "gt": head.text_projector.text_projection.weight.grad.cpu(),
        "gf": head.classifier.weight.grad.cpu()}
+# the same step captured in a CUDA graph (collectives included) must agree with the eager step
+for p in head.parameters(): p.grad = None
+gstep = b200clip.GraphedHeadStep(head, xi.detach(), xt.detach(), class_text.to(dev), labels[sl].to(dev))
+gl = gstep(xi.detach(), xt.detach(), class_text.to(dev), labels[sl].to(dev))
+torch.cuda.synchronize()
+out["g_loss"] = gl.item(); out["g_dxi"] = gstep.grad_image.float().cpu(); out["g_gw"] = head.image_projector.fc.weight.grad.cpu()
 torch.save(out, os.path.join(OUT, f"dp_r{rank}.pt"))
+gstep.close()
 dist.destroy_process_group()
 '''
 
@@ -46,7 +53,7 @@ def test_two_rank_head_equals_single_gpu(tmp_path):
     script.write_text(f"ROOT = {ROOT!r}\nOUT = {str(tmp_path)!r}\n" + WORKER)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                    "--master-port", "29533", str(script)], check=True, env=env, timeout=600)
+                    "--master-port", "29533", str(script)], check=True, env=env, timeout=240)
     dev = torch.device("cuda:0")
     B, E, D, C = 1024, 768, 512, 16
     torch.manual_seed(0)
@@ -68,3 +75,6 @@ def test_two_rank_head_equals_single_gpu(tmp_path):
         assert rel(o["gw"], head.image_projector.fc.weight.grad.cpu()) < 1e-2
         assert rel(o["gt"], head.text_projector.text_projection.weight.grad.cpu()) < 1e-2
         assert rel(o["gf"], head.classifier.weight.grad.cpu()) < 1e-2
+        assert abs(o["g_loss"] - o["loss"]) <= 1e-6 * abs(o["loss"])
+        assert rel(o["g_dxi"], o["dxi"]) < 1e-5
+        assert rel(o["g_gw"], o["gw"]) < 1e-4
