@@ -19,6 +19,7 @@ SIGNATURES = {
     "b200clip_version": (i32, []),
     "b200clip_last_error_string": (C.c_char_p, []),
     "b200clip_launch_count": (C.c_ulonglong, []),
+    "b200clip_head_loss_finalize": (i32, [vp, vp, f32, f64, f64, f64, vp, vp, vp, vp]),
     "b200clip_debug_set_nce_prof": (None, [vp]),
     "b200clip_gemm_bf16": (i32, [vp, vp, i32, i32, i32, i32, i32, ll, ll, i32, f32, vp, ll, vp, ll, vp, vp, ll, vp, ll, i32, vp]),
     "b200clip_l2norm_fwd": (i32, [vp, i32, ll, vp, vp, vp, ll, i32, f32, vp]),

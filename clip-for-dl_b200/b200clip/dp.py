@@ -39,6 +39,18 @@ def sum_across(t: torch.Tensor, group=None) -> torch.Tensor:
     return t
 
 
+def sum_across_async(t: torch.Tensor, group=None):
+    """all_reduce(SUM) in place without making the compute stream wait; returns a work handle (None at world 1)."""
+    if world(group) > 1:
+        return dist.all_reduce(t, group=group, async_op=True)
+    return None
+
+
+def wait(work) -> None:
+    if work is not None:
+        work.wait()
+
+
 def scatter_sum_rows(full: torch.Tensor, group=None, async_op: bool = False):
     """reduce_scatter(SUM) along dim 0: every rank contributes a [B, ...] partial and keeps its own row block."""
     W = world(group)
@@ -54,18 +66,18 @@ def scatter_sum_rows(full: torch.Tensor, group=None, async_op: bool = False):
     return out, (work if async_op else None)
 
 
-def allreduce_flat(tensors: Sequence[torch.Tensor], group=None) -> List[torch.Tensor]:
-    """One bucket for all head parameter gradients (~2 M floats): SUM is exact because every loss term is already
-    normalised by the GLOBAL batch."""
+def allreduce_flat(tensors: Sequence[torch.Tensor], group=None, async_op: bool = False):
+    """One bucket of parameter gradients: SUM is exact because every loss term is already normalised by the GLOBAL
+    batch.  Returns the reduced tensors (views of the bucket); with async_op=True returns (tensors, work)."""
     if world(group) == 1:
-        return list(tensors)
+        return (list(tensors), None) if async_op else list(tensors)
     flat = torch.cat([t.reshape(-1) for t in tensors])
-    dist.all_reduce(flat, group=group)
+    work = dist.all_reduce(flat, group=group, async_op=async_op)
     out, o = [], 0
     for t in tensors:
         out.append(flat[o:o + t.numel()].view_as(t))
         o += t.numel()
-    return out
+    return (out, work) if async_op else out
 
 
 def infonce_loss_from_sums(sums: torch.Tensor, temperature: float, b_glob: int) -> torch.Tensor:

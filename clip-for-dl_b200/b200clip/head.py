@@ -31,10 +31,12 @@ _world, _rank = dp.world, dp.rank
 
 
 def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop_p, drop_seed, params, need_grad,
-                 need_dx=(True, True)):
+                 need_dx=(True, True), defer_loss=False):
     """Forward pass of the fused head on this rank's local pairs.  Returns (loss, parts, state); `state` is what
-    head_backward needs (None when need_grad is False).  Plain function: ClipHeadFn wraps it for autograd,
-    GraphedHeadStep calls it directly while capturing."""
+    head_backward needs (None when need_grad is False); parts = [InfoNCE, text BCE, FC BCE].  With defer_loss the loss is
+    not finalised here: loss is None and parts is a callable returning (loss, parts, status), to be called after the
+    backward kernels are enqueued.  Plain function: ClipHeadFn wraps it for autograd, GraphedHeadStep calls it directly
+    while capturing."""
     (iw1, ib1, iw2, ib2, ig, ibeta, tw1, tb1, tw2, tb2, tg, tbeta, fw, fb) = params
     ops.require_cuda(x_img, x_txt, class_text, labels, iw1)
     W, rank = _world(group), _rank(group)
@@ -44,6 +46,9 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
     xi, xt = ops.cast_bf16(x_img), ops.cast_bf16(x_txt)
     iw1b, iw2b, tw1b, tw2b = (ops.cast_bf16(w) for w in (iw1, iw2, tw1, tw2))
     f = ops._f32c
+    labels_f = f(labels)
+    lsum = ops._label_sum(labels_f)
+    lsum_work = dp.sum_across_async(lsum, group)          # global label count, needed only by the BCE heads
     # text first so its all-gather can overlap the image projection
     # independent dropout streams for the two projections (seed, seed+1)
     y_txt, that_loc, inv_txt, saved_t = ops.proj_fwd(xt, tw1b, f(tb1), tw2b, f(tb2), f(tg), f(tbeta), want_yhat=True,
@@ -51,25 +56,32 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
     that_all, work = dp.gather_rows(that_loc, group, async_op=True)
     y_img, ihat, inv_img, saved_i = ops.proj_fwd(xi, iw1b, f(ib1), iw2b, f(ib2), f(ig), f(ibeta), want_yhat=True,
                                                  drop_p=drop_p, drop_seed=drop_seed)
-    labels_f = f(labels)
-    lsum = ops._label_sum(labels_f)
-    if W > 1:
-        dp.sum_across(lsum, group)
-        work.wait()
-    l_nce, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, group=group if W > 1 else None)
     C = class_text.shape[0]
     Cf = fw.shape[0]
+    sums6 = torch.empty((6,), dtype=torch.float64, device=x_img.device)   # rank-local loss numerators (NCE 3 | BCE 3)
     # one pass over y_img serves both BCE heads, forward AND backward: the input gradient d_bce (for upstream grad 1)
-    # and the FC coefficients are produced here; backward only scales them by the incoming gradient.
+    # and the FC coefficients are produced here; backward only scales them by the incoming gradient.  The heads do not
+    # depend on the gathered texts, so they run while the all-gather is still in flight.
+    dp.wait(lsum_work)
     d_bce = torch.empty_like(y_img) if need_grad else None
-    l_bce, l_fc, status, both, coef = ops.bce_heads(y_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
-                                                    total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
-                                                    dx_out=d_bce, want_coef=need_grad, finalize=(W == 1))
-    if W > 1:
-        dp.sum_across(both, group)
-        l_bce, l_fc = dp.bce_losses_from_sums(both, lsum, float(b_glob) * C, float(b_glob) * Cf)
-    loss = l_nce + l_bce + l_fc
-    parts = (l_nce.detach(), l_bce.detach(), l_fc.detach())
+    *_, coef = ops.bce_heads(y_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
+                             total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
+                             dx_out=d_bce, want_coef=need_grad, finalize=False, sums_out=sums6[3:])
+    dp.wait(work)
+    _, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, group=group if W > 1 else None,
+                                          sums_out=sums6[:3])
+    # The loss VALUE needs the six numerators summed over ranks; nothing in the backward pass does.  One small
+    # all-reduce, off the critical path: `finish` waits for it and runs the one-thread finalisation kernel.
+    sums_work = dp.sum_across_async(sums6, group)
+
+    def finish():
+        dp.wait(sums_work)
+        return ops.head_loss_finalize(sums6, lsum, tau_nce, b_glob, float(b_glob) * C, float(b_glob) * Cf)
+
+    if defer_loss:
+        loss, parts = None, finish
+    else:
+        loss, parts, _status = finish()
     if not need_grad:
         return loss, parts, None
     tensors = (xi, xt, iw1b, iw2b, tw1b, tw2b, f(ig), f(tg), y_img, y_txt, ihat, that_all, inv_img, inv_txt, rinvh, cinvh,
@@ -94,12 +106,15 @@ def head_backward(tensors, meta, g):
     dy_img = ops.l2norm_bwd(d_ihat, y_img, inv_img, addend=d_bce, addend_scale=g)
     dfw, dfb = ops.skinny_outer(coef, y_img, want_bias=True, out_scale=g)
     gi = ops.proj_bwd(dy_img, xi, iw1b, iw2b, ig, saved_i, need_dxi, meta["in_dtypes"][0], drop_p=drop_p, drop_seed=drop_seed)
-    if work is not None:
-        work.wait()
+    # image-side parameter gradients travel while the text side is still computing (SUM, not mean: every loss term is
+    # normalised by the GLOBAL batch)
+    img_grads, img_work = dp.allreduce_flat([gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], dfw, dfb], group, async_op=True)
+    dp.wait(work)
     dy_txt = ops.l2norm_bwd(d_that_loc, y_txt, inv_txt)
     gt = ops.proj_bwd(dy_txt, xt, tw1b, tw2b, tg, saved_t, need_dxt, meta["in_dtypes"][1], drop_p=drop_p, drop_seed=drop_seed + 1)
-    grads = [gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], gt[1], gt[2], gt[3], gt[4], gt[5], gt[6], dfw, dfb]
-    grads = dp.allreduce_flat(grads, group)     # SUM, not mean: every loss term is normalised by the GLOBAL batch
+    txt_grads = dp.allreduce_flat([gt[1], gt[2], gt[3], gt[4], gt[5], gt[6]], group)
+    dp.wait(img_work)
+    grads = [*img_grads[:6], *txt_grads, img_grads[6], img_grads[7]]
     if not meta["has_fc_bias"]:
         grads[-1] = None
     return gi[0], gt[0], grads
@@ -200,10 +215,11 @@ class GraphedHeadStep:
         """forward + backward as plain calls (no autograd engine: its worker thread and AccumulateGrad streams do not
         belong in a capture)."""
         h = self.head
-        loss, parts, (tensors, meta) = head_forward(self.x_img, self.x_txt, self.class_text, self.labels, h.tau_nce, h.tau_bce,
-                                                    h.group, 0.0, 0, h.params(), True,
-                                                    need_dx=(self.input_grads, self.input_grads))
+        _, finish, (tensors, meta) = head_forward(self.x_img, self.x_txt, self.class_text, self.labels, h.tau_nce, h.tau_bce,
+                                                  h.group, 0.0, 0, h.params(), True,
+                                                  need_dx=(self.input_grads, self.input_grads), defer_loss=True)
         dxi, dxt, grads = head_backward(tensors, meta, self._one)
+        loss, self.parts, self.status = finish()          # loss value: after the backward kernels, off the critical path
         return loss, dxi, dxt, grads
 
     def bind_grads(self):

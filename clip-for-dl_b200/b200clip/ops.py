@@ -213,8 +213,11 @@ class ProjectionFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------------------------
 # a-N symmetric InfoNCE
 # --------------------------------------------------------------------------------------------------------------
-def infonce_forward(i_hat: torch.Tensor, t_hat: torch.Tensor, temperature: float, row0: int = 0, group=None):
-    """i_hat: local rows [b_loc, D] bf16; t_hat: all rows [b_glob, D] bf16.  Returns (loss, rinvh, cinvh)."""
+def infonce_forward(i_hat: torch.Tensor, t_hat: torch.Tensor, temperature: float, row0: int = 0, group=None,
+                    sums_out: Optional[torch.Tensor] = None):
+    """i_hat: local rows [b_loc, D] bf16; t_hat: all rows [b_glob, D] bf16.  Returns (loss, rinvh, cinvh).
+    With sums_out (3 doubles) the rank-local loss numerators are written there and loss is None (the fused head sums
+    them over ranks together with the BCE numerators and finalises once)."""
     lib = load()
     b_loc, D = i_hat.shape
     b_glob = t_hat.shape[0]
@@ -237,13 +240,14 @@ def infonce_forward(i_hat: torch.Tensor, t_hat: torch.Tensor, temperature: float
         dp.sum_across(c, group)                               # partial column sums -> global
     rinvh = torch.empty_like(r)
     cinvh = torch.empty_like(c)
-    sums = torch.empty((3,), dtype=torch.float64, device=dev)
-    loss = torch.empty((), dtype=torch.float32, device=dev)
+    deferred = sums_out is not None
+    sums = sums_out if deferred else torch.empty((3,), dtype=torch.float64, device=dev)
+    loss = None if deferred else torch.empty((), dtype=torch.float32, device=dev)
     c_lo, c_hi = (row0, row0 + b_loc) if world > 1 else (0, b_glob)
     check(lib.b200clip_infonce_loss(ptr(i_hat), ptr(t_hat), D, b_loc, b_glob, row0, temperature, ptr(r), ptr(c), c_lo, c_hi,
-                                    ptr(rinvh), ptr(cinvh), ptr(sums), ptr(loss) if world == 1 else None, ptr(ws), ws.numel(),
-                                    stream_ptr()), "infonce_loss")
-    if world > 1:
+                                    ptr(rinvh), ptr(cinvh), ptr(sums), ptr(loss) if (world == 1 and not deferred) else None,
+                                    ptr(ws), ws.numel(), stream_ptr()), "infonce_loss")
+    if world > 1 and not deferred:
         loss = dp.infonce_loss_from_sums(dp.sum_across(sums, group), temperature, b_glob)
     return loss, rinvh, cinvh
 
@@ -454,7 +458,8 @@ class LinearSmallFn(torch.autograd.Function):
 
 
 def bce_heads(image_features, class_text, fc_weight, fc_bias, labels, temperature, *, label_sum, total_elems_text,
-              total_elems_fc, grad_scale=None, dx_accum=None, dx_out=None, want_coef=False, finalize=True):
+              total_elems_fc, grad_scale=None, dx_accum=None, dx_out=None, want_coef=False, finalize=True,
+              sums_out: Optional[torch.Tensor] = None):
     """Both BCE heads (a-B on the class texts + a-A FC adapter) in one pass over the image features.
     dx_accum: input gradient is ADDED to this tensor; dx_out: input gradient overwrites this tensor."""
     assert dx_accum is None or dx_out is None
@@ -467,7 +472,7 @@ def bce_heads(image_features, class_text, fc_weight, fc_bias, labels, temperatur
     c1, c2 = t.shape[0], w.shape[0]
     dev = x.device
     coef = torch.empty((B, c2), dtype=torch.float32, device=dev) if want_coef else None
-    sums = torch.empty((3,), dtype=torch.float64, device=dev)
+    sums = sums_out if sums_out is not None else torch.empty((3,), dtype=torch.float64, device=dev)
     l_text = torch.empty((), dtype=torch.float32, device=dev) if finalize else None
     l_fc = torch.empty((), dtype=torch.float32, device=dev) if finalize else None
     status = torch.zeros((), dtype=torch.int32, device=dev) if finalize else None
@@ -478,6 +483,18 @@ def bce_heads(image_features, class_text, fc_weight, fc_bias, labels, temperatur
                                          ptr(gs), ptr(dx_t), int(dx_accum is not None), ptr(coef), ptr(sums), ptr(l_text),
                                          ptr(l_fc), ptr(status), ptr(ws), ws.numel(), stream_ptr()), "bce_heads_fwd_bwd")
     return l_text, l_fc, status, sums, coef
+
+
+def head_loss_finalize(sums6, label_sum, tau_nce, b_glob, total_text, total_fc):
+    """loss, parts[3] (InfoNCE, text BCE, FC BCE), status from the six numerators (already summed over ranks)."""
+    dev = sums6.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    parts = torch.empty((3,), dtype=torch.float32, device=dev)
+    status = torch.empty((), dtype=torch.int32, device=dev)
+    check(load().b200clip_head_loss_finalize(ptr(sums6), ptr(label_sum), float(tau_nce), float(b_glob), float(total_text),
+                                             float(total_fc), ptr(loss), ptr(parts), ptr(status), stream_ptr()),
+          "head_loss_finalize")
+    return loss, parts, status
 
 
 # --------------------------------------------------------------------------------------------------------------

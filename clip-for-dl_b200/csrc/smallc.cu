@@ -419,6 +419,24 @@ __global__ void __launch_bounds__(1024) sum_f32_kernel(const float* __restrict__
   }
 }
 
+// loss of the fused head from the six (all-reduced) numerators: sums6 = {sum log r, sum log c, sum S_ii, text BCE pos
+// numerator, text BCE neg numerator, FC BCE sum}.  One thread; replaces a dozen scalar tensor ops per step.
+__global__ void head_loss_finalize_kernel(const double* __restrict__ sums6, const float* __restrict__ label_sum,
+                                          double inv_tau_nce, double b_glob, double total_text, double total_fc,
+                                          float* __restrict__ loss, float* __restrict__ parts, int* __restrict__ status) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double l_nce = inv_tau_nce + (sums6[0] + sums6[1]) / (2.0 * b_glob) - sums6[2] / b_glob;   // fixed shift m = 1/tau
+  const float Psum = *label_sum;
+  const float Nsum = static_cast<float>(total_text - static_cast<double>(Psum));
+  const float pos = static_cast<float>(-sums6[3]) / (Psum + 1e-8f);                 // 0426/train.py:218
+  const float neg = static_cast<float>(-sums6[4]) / (Nsum + 1e-8f);                 // :219
+  const float l_text = (pos + neg) * 0.5f;                                          // :221
+  const float l_fc = static_cast<float>(sums6[5] / total_fc);
+  if (status) *status = (isnan(l_text) || isinf(l_text) || l_text > 1000.f) ? 1 : 0;   // :224
+  parts[0] = static_cast<float>(l_nce); parts[1] = l_text; parts[2] = l_fc;
+  *loss = static_cast<float>(l_nce) + l_text + l_fc;
+}
+
 static int sc_grid(long long rows) {
   const long long per_block = (SC_THREADS / 32) * 4;
   const long long want = (rows + per_block - 1) / per_block;
@@ -460,6 +478,16 @@ extern "C" size_t b200clip_smallc_workspace_bytes(long long rows, int C, int D) 
   const int rpb = SO_ROWS;
   const size_t outer = static_cast<size_t>((rows + rpb - 1) / rpb) * (static_cast<size_t>(C) * D + C) * sizeof(float);
   return loss_part + outer + 256;
+}
+
+extern "C" int b200clip_head_loss_finalize(const double* sums6, const float* label_sum, float temperature_nce, double b_glob,
+                                           double total_elems_text, double total_elems_fc, float* loss, float* parts3,
+                                           int* status, void* stream) {
+  B200_REQUIRE(sums6 && label_sum && loss && parts3 && temperature_nce > 0.f && b_glob > 0, "head_loss_finalize: bad arguments");
+  head_loss_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(sums6, label_sum, 1.0 / static_cast<double>(temperature_nce),
+                                                                             b_glob, total_elems_text, total_elems_fc, loss, parts3, status);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
 }
 
 extern "C" int b200clip_sum_f32(const float* a, long long n, float* out, void* stream) {

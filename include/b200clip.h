@@ -122,6 +122,12 @@ int b200clip_skinny_outer(const float* coef, int C, const float* x, long long ld
                           int D, float* out_w, float* out_b, int accumulate, const float* out_scale, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* loss of the fused head step from its six numerators (summed over ranks): sums6 = {sum_i log r_i, sum_j log c_j,
+ * sum_i S_ii, text-BCE pos numerator, text-BCE neg numerator, FC-BCE sum}; parts3 = {InfoNCE, text BCE, FC BCE}. */
+int b200clip_head_loss_finalize(const double* sums6, const float* label_sum, float temperature_nce, double b_glob,
+                                double total_elems_text, double total_elems_fc, float* loss, float* parts3, int* status,
+                                void* stream);
+
 /* a-B + a-A fused for the head step: one pass over the image features serves both BCE heads (classes [0,c1) = class
  * texts, [c1,c1+c2) = FC adapter rows).  sums[3] = {text pos numerator, text neg numerator, FC BCE sum}. */
 int b200clip_bce_heads_fwd_bwd(const float* image_features, long long ldx, const float* text_features, int c1,
