@@ -63,10 +63,17 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
     # and the FC coefficients are produced here; backward only scales them by the incoming gradient.  The heads do not
     # depend on the gathered texts, so they run while the all-gather is still in flight.
     dp.wait(lsum_work)
-    d_bce = torch.empty_like(y_img) if need_grad else None
-    *_, coef = ops.bce_heads(y_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
-                             total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
-                             dx_out=d_bce, want_coef=need_grad, finalize=False, sums_out=sums6[3:])
+    fast_heads = ops.heads_mma_supported(y_img.shape[1], C, Cf)
+    if fast_heads:        # tensor-core path: reads the bf16 normalised features LayerNorm wrote for InfoNCE
+        d_bce, coef, db_raw = ops.bce_heads_mma(ihat, inv_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
+                                                total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
+                                                sums_out=sums6[3:], want_grad=need_grad)
+    else:
+        db_raw = None
+        d_bce = torch.empty_like(y_img) if need_grad else None
+        *_, coef = ops.bce_heads(y_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
+                                 total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
+                                 dx_out=d_bce, want_coef=need_grad, finalize=False, sums_out=sums6[3:])
     dp.wait(work)
     _, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, group=group if W > 1 else None,
                                           sums_out=sums6[:3])
@@ -85,7 +92,7 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
     if not need_grad:
         return loss, parts, None
     tensors = (xi, xt, iw1b, iw2b, tw1b, tw2b, f(ig), f(tg), y_img, y_txt, ihat, that_all, inv_img, inv_txt, rinvh, cinvh,
-               d_bce, coef, *saved_i, *saved_t)
+               d_bce, coef, db_raw, *saved_i, *saved_t)
     meta = dict(tau_nce=tau_nce, group=group, W=W, row0=row0, need_dx=tuple(need_dx), in_dtypes=(x_img.dtype, x_txt.dtype),
                 drop=(float(drop_p), int(drop_seed)), has_fc_bias=fb is not None)
     return loss, parts, (tensors, meta)
@@ -94,7 +101,7 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
 def head_backward(tensors, meta, g):
     """Backward pass: returns (d_x_img, d_x_txt, [14 parameter gradients in PARAM_ORDER])."""
     (xi, xt, iw1b, iw2b, tw1b, tw2b, ig, tg, y_img, y_txt, ihat, that_all, inv_img, inv_txt, rinvh, cinvh, d_bce, coef,
-     *rest) = tensors
+     db_raw, *rest) = tensors
     saved_i, saved_t = tuple(rest[:5]), tuple(rest[5:])
     group, row0 = meta["group"], meta["row0"]
     need_dxi, need_dxt = meta["need_dx"]
@@ -104,7 +111,10 @@ def head_backward(tensors, meta, g):
     d_that_loc, work = dp.scatter_sum_rows(d_that, group, async_op=True)
     # image side: through the L2 normalisation, plus g * (the two BCE heads' input gradient from the forward pass)
     dy_img = ops.l2norm_bwd(d_ihat, y_img, inv_img, addend=d_bce, addend_scale=g)
-    dfw, dfb = ops.skinny_outer(coef, y_img, want_bias=True, out_scale=g)
+    if db_raw is not None:
+        dfw, dfb = ops.skinny_outer_mma(coef, ihat, db_raw, out_scale=g)
+    else:
+        dfw, dfb = ops.skinny_outer(coef, y_img, want_bias=True, out_scale=g)
     gi = ops.proj_bwd(dy_img, xi, iw1b, iw2b, ig, saved_i, need_dxi, meta["in_dtypes"][0], drop_p=drop_p, drop_seed=drop_seed)
     # image-side parameter gradients travel while the text side is still computing (SUM, not mean: every loss term is
     # normalised by the GLOBAL batch)

@@ -485,6 +485,44 @@ def bce_heads(image_features, class_text, fc_weight, fc_bias, labels, temperatur
     return l_text, l_fc, status, sums, coef
 
 
+def heads_mma_supported(D: int, c1: int, c2: int) -> bool:
+    return D == 512 and c1 == 16 and c2 == 16
+
+
+def bce_heads_mma(yhat_bf16, inv_norm, class_text, fc_weight, fc_bias, labels, temperature, *, label_sum, total_elems_text,
+                  total_elems_fc, sums_out, want_grad=True):
+    """Both BCE heads on tensor cores from the normalised bf16 features (head step fast path, D=512, 16+16 classes).
+    Returns (d_y [B,D] f32 for upstream gradient 1, coefn [B,16] bf16, db_raw [16] f32); sums_out receives 3 doubles."""
+    lib = load()
+    B, D = yhat_bf16.shape
+    dev = yhat_bf16.device
+    t, w = _f32c(class_text), _f32c(fc_weight)
+    b = _f32c(fc_bias) if fc_bias is not None else None
+    y = _f32c(labels)
+    d_y = torch.empty((B, D), dtype=torch.float32, device=dev) if want_grad else None
+    coefn = torch.empty((B, 16), dtype=torch.bfloat16, device=dev) if want_grad else None
+    db = torch.empty((16,), dtype=torch.float32, device=dev) if want_grad else None
+    ws = _ws(lib.b200clip_bce_heads_mma_workspace_bytes(B), dev)
+    check(lib.b200clip_bce_heads_mma_fwd(ptr(yhat_bf16), ptr(inv_norm), B, D, ptr(t), t.shape[0], ptr(w), ptr(b), w.shape[0], ptr(y),
+                                         y.shape[1], y.stride(0), float(temperature), ptr(label_sum), float(total_elems_text),
+                                         float(total_elems_fc), ptr(d_y), ptr(coefn), ptr(db), ptr(sums_out), ptr(ws), ws.numel(),
+                                         stream_ptr()), "bce_heads_mma_fwd")
+    return d_y, coefn, db
+
+
+def skinny_outer_mma(coefn, yhat_bf16, db_raw, out_scale=None):
+    """dW_fc [16, D] = out_scale * coefn^T yhat and db = out_scale * db_raw."""
+    lib = load()
+    B, D = yhat_bf16.shape
+    dev = yhat_bf16.device
+    out_w = torch.empty((16, D), dtype=torch.float32, device=dev)
+    out_b = torch.empty((16,), dtype=torch.float32, device=dev)
+    ws = _ws(lib.b200clip_bce_heads_mma_workspace_bytes(B), dev)
+    check(lib.b200clip_skinny_outer_mma(ptr(coefn), ptr(yhat_bf16), B, D, 16, ptr(out_scale), ptr(out_w), ptr(db_raw), ptr(out_b),
+                                        ptr(ws), ws.numel(), stream_ptr()), "skinny_outer_mma")
+    return out_w, out_b
+
+
 def head_loss_finalize(sums6, label_sum, tau_nce, b_glob, total_text, total_fc):
     """loss, parts[3] (InfoNCE, text BCE, FC BCE), status from the six numerators (already summed over ranks)."""
     dev = sums6.device

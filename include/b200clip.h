@@ -122,6 +122,20 @@ int b200clip_skinny_outer(const float* coef, int C, const float* x, long long ld
                           int D, float* out_w, float* out_b, int accumulate, const float* out_scale, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* a-B + a-A on warp-level tensor cores (head step, D = 512, 16 class texts + 16 FC rows): reads the L2-normalised bf16
+ * features and 1/||y||; writes sums[3] as above, d_y [B,D] = d(text BCE + FC BCE)/dy for upstream gradient 1, the FC
+ * coefficients times ||y|| in bf16 (coefn [B,16], feeds b200clip_skinny_outer_mma) and db_fc[16] = sum_rows dL/dz. */
+size_t b200clip_bce_heads_mma_workspace_bytes(long long rows);
+int b200clip_bce_heads_mma_fwd(const void* yhat_bf16, const float* inv_norm, long long B, int D, const float* class_text,
+                               int c1, const float* fc_weight, const float* fc_bias, int c2, const float* labels,
+                               int label_cols, long long ld_labels, float temperature, const float* label_sum,
+                               double total_elems_text, double total_elems_fc, float* d_y, void* coefn_bf16, float* db_fc,
+                               double* sums, void* workspace, size_t workspace_bytes, void* stream);
+/* out_w[16,D] = *out_scale * coefn^T yhat ; db_out[16] = *out_scale * db_raw   (nn.Linear(512,16) weight/bias gradient) */
+int b200clip_skinny_outer_mma(const void* coefn_bf16, const void* yhat_bf16, long long rows, int D, int C,
+                              const float* out_scale, float* out_w, const float* db_raw, float* db_out, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* loss of the fused head step from its six numerators (summed over ranks): sums6 = {sum_i log r_i, sum_j log c_j,
  * sum_i S_ii, text-BCE pos numerator, text-BCE neg numerator, FC-BCE sum}; parts3 = {InfoNCE, text BCE, FC BCE}. */
 int b200clip_head_loss_finalize(const double* sums6, const float* label_sum, float temperature_nce, double b_glob,

@@ -85,3 +85,43 @@ def test_predict_multilabel(B, thr):
     assert out.dtype == torch.float32 and out.shape == ref.shape
     assert torch.equal(out.cpu()[safe], ref[safe])
     assert safe.float().mean() > 0.999
+
+
+@pytest.mark.parametrize("B,tau", [(1000, 1.0), (4096, 0.07), (37, 1.0)])
+def test_bce_heads_tensor_core_path_vs_oracle(B, tau):
+    """heads_mma.cu (both BCE heads on mma.sync from the bf16 normalised features) vs the reference ops in fp32/autograd
+    on the same bf16-rounded normalised features: F.normalize + class-text BCE (0426/train.py:178-230) and
+    Linear(512,16) + BCEWithLogits (NB02 c28:50-52)."""
+    from b200clip import ops
+    d = dev()
+    C, D = 16, 512
+    y = synth.randn(31, B, D) * 1.7
+    ct = synth.randn(32, C, D)
+    W = synth.uniform(33, -0.044, 0.044, C, D)
+    bias = synth.uniform(34, -0.044, 0.044, C)
+    lab = synth.labels(35, B, C, density=0.1)
+    nrm = y.norm(dim=1)
+    yhat_b = (y / nrm[:, None]).to(torch.bfloat16)
+    inv = (1.0 / nrm).float()
+    # reference on y_eff = yhat_b * ||y|| (what the kernel reconstructs); ||yhat_b|| differs from 1 by bf16 rounding only
+    y_eff = (yhat_b.float() * nrm[:, None]).requires_grad_(True)
+    Wr, br = W.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    l_text = R.multilabel_contrastive_loss(y_eff, ct, lab, tau)
+    l_fc = torch.nn.functional.binary_cross_entropy_with_logits(y_eff @ Wr.t() + br, lab)
+    (l_text + l_fc).backward()
+    lsum = lab.sum().float().to(d)
+    sums = torch.empty(3, dtype=torch.float64, device=d)
+    d_y, coefn, db = ops.bce_heads_mma(yhat_b.to(d), inv.to(d), ct.to(d), W.to(d), bias.to(d), lab.to(d), tau, label_sum=lsum,
+                                      total_elems_text=float(B * C), total_elems_fc=float(B * C), sums_out=sums)
+    g = torch.full((), 2.0, device=d)
+    dW, dB = ops.skinny_outer_mma(coefn, yhat_b.to(d), db, out_scale=g)
+    torch.cuda.synchronize()
+    P = float(lab.sum())
+    s = sums.cpu()
+    got_text = 0.5 * (-s[0] / (P + 1e-8) - s[1] / (B * C - P + 1e-8))
+    got_fc = s[2] / (B * C)
+    assert abs(float(got_text) - l_text.item()) <= 1e-3 * abs(l_text.item())
+    assert abs(float(got_fc) - l_fc.item()) <= 1e-3 * abs(l_fc.item())
+    assert rel_l2(d_y, y_eff.grad) < 2e-2
+    assert rel_l2(dW, 2.0 * Wr.grad) < 2e-2
+    assert rel_l2(dB, 2.0 * br.grad) < 2e-2
