@@ -272,11 +272,16 @@ constexpr int BWD_TB = 3;                   // ring B depth in tiles (the 4 Y K-
 constexpr int BWD_SLOT_BYTES = BWD_BN * 128;            // one [32 x 64] bf16 chunk
 constexpr int BWD_GROUP_BYTES = 4 * BWD_SLOT_BYTES;     // 4 chunks = half a Y tile
 constexpr int BWD_G_BYTES = 128 * 128;      // [128 rows x 64 bf16]: even tiles use K cols 0-31, odd tiles 32-63
-constexpr int BWD4_TA = 3;                  // version 4: 3 A groups, 5 B groups, two G buffers
-constexpr int BWD4_TB = 5;
+#ifndef B200CLIP_BWD4_NSB
+#define B200CLIP_BWD4_NSB 1
+#endif
+constexpr int BWD4_NSB = B200CLIP_BWD4_NSB; // S buffers in TMEM (32 columns each): 1 leaves room for one more X chunk in TMEM
+constexpr int BWD4_XS = BWD4_NSB;           // out-of-half X K-chunks kept in shared memory (SS MMAs); the other 4 - XS live in TMEM
+constexpr int BWD4_TA = 4;                  // version 4: A groups (16 KB each) -- the smem X chunks moved to TMEM buy ring depth
+constexpr int BWD4_TB = 5 + (4 - BWD4_XS) - 1;   // B groups
 constexpr int BWD_THREADS = 384;            // warp 0 TMA, 1 S-MMA issuer, 2 TMEM alloc + dX-MMA issuer, 3 idle, 4-11 epilogue
 constexpr int nce_bwd4_smem_bytes() {
-  return 4 * X_CHUNK_BYTES + (BWD4_TA + BWD4_TB) * BWD_GROUP_BYTES + 2 * BWD_G_BYTES + 512 + 1024;
+  return BWD4_XS * X_CHUNK_BYTES + (BWD4_TA + BWD4_TB) * BWD_GROUP_BYTES + 2 * BWD_G_BYTES + 512 + 1024;
 }
 constexpr int nce_bwd_smem_bytes() {
   return NCE_KC * X_CHUNK_BYTES + (BWD_TA + BWD_TB) * BWD_GROUP_BYTES + BWD_G_BYTES + 512 + 1024;
@@ -602,7 +607,7 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constan
 //    memory for a 5-tile ring B / 3-group ring A -- the S -> G -> dX -> free-slot pipeline is bound by ring depth.
 //  * Y traffic per CTA: in-half K-chunks of every tile (ring B, also the MN-major B operand of the dX MMA) + out-of-half
 //    chunks of its own tiles (ring A).
-// TMEM: acc [0,256) | S 2 x 32 [256,320) | X in-half K range [320,448).
+// TMEM: acc [0,256) | S NSB x 32 | X in-half K range (128 columns) | the first 4 - XS out-of-half X chunks (32 columns each).
 // Experiments that lost (kept in git history): 64-column tiles with a bulk DSMEM copy of G (4.85 ms vs 4.42 ms at
 // B=32768: rings too shallow), pairing own tiles / splitting the dX accumulator to interleave independent accumulators.
 // ------------------------------------------------------------------------------------------------
@@ -624,7 +629,7 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX = smem;
-  uint8_t* sA = sX + 4 * X_CHUNK_BYTES;             // sX holds only the OUT-of-half K range of X (4 chunks)
+  uint8_t* sA = sX + BWD4_XS * X_CHUNK_BYTES;       // sX holds only the LAST BWD4_XS chunks of the out-of-half K range of X
   uint8_t* sB = sA + BWD4_TA * BWD_GROUP_BYTES;
   uint8_t* sG = sB + BWD4_TB * BWD_GROUP_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 2 * BWD_G_BYTES);   // two G buffers: slot (owner, k) -> buffer k, K half owner
@@ -666,7 +671,7 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
       mbar_init(&g_empty[b], 2);
     }
     mbar_init(acc_full, 1);
-    mbar_init(xt_full, 128);
+    mbar_init(xt_full, 256);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -678,8 +683,9 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_acc = tmem_base;
-  const uint32_t tmem_s = tmem_base + 256;          // 2 x 32 columns
-  const uint32_t tmem_x = tmem_base + 320;          // 128 columns: X[:, h*256 .. +256) as packed bf16 pairs
+  const uint32_t tmem_s = tmem_base + 256;          // NSB x 32 columns
+  const uint32_t tmem_x = tmem_s + BWD4_NSB * BWD_BN;   // 128 columns: X[:, h*256 .. +256) as packed bf16 pairs
+  const uint32_t tmem_x2 = tmem_x + 128;            // 32 * (4 - XS) columns: the first 4 - XS out-of-half chunks of X
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -687,9 +693,10 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
     const uint32_t af0 = smem_u32(a_full), ae0 = smem_u32(a_empty), bf0 = smem_u32(b_full), be0 = smem_u32(b_empty);
     const uint32_t sa = smem_u32(sA), sb = smem_u32(sB), sx = smem_u32(sX);
     if (elect_one()) {
-      mbar_arrive_expect_tx_a(xf, 4 * X_CHUNK_BYTES);
+      mbar_arrive_expect_tx_a(xf, BWD4_XS * X_CHUNK_BYTES);
 #pragma unroll
-      for (int kc = 0; kc < 4; ++kc) tma_load_2d_a(sx + kc * X_CHUNK_BYTES, tmap_x, xf, (1 - h) * 256 + kc * 64, rb * 128);
+      for (int kc = 0; kc < BWD4_XS; ++kc)
+        tma_load_2d_a(sx + kc * X_CHUNK_BYTES, tmap_x, xf, (1 - h) * 256 + (4 - BWD4_XS + kc) * 64, rb * 128);
     }
     __syncwarp();
     int ia = 0, ib = 0;
@@ -738,12 +745,16 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
     if (h == 1) { ib = 1 % BWD4_TB; }                 // first own tile is n = 1
     NCE_PROF_BEGIN();
     for (int m = 0; m < nown; ++m) {
-      const int buf = m & 1;
-      NCE_PW(0, mbar_wait_a(se0 + 8 * buf, ((m >> 1) & 1) ^ 1));
+      const int buf = m & 1;                      // s_full / s_empty barrier pair (one per epilogue warpgroup)
+      if (BWD4_NSB == 2) {
+        NCE_PW(0, mbar_wait_a(se0 + 8 * buf, ((m >> 1) & 1) ^ 1));       // tile m-2 (same buffer) has been read
+      } else if (m > 0) {
+        NCE_PW(0, mbar_wait_a(se0 + 8 * (buf ^ 1), ((m - 1) >> 1) & 1));   // single buffer: tile m-1 has been read
+      }
       NCE_PW(1, mbar_wait_a(bf0 + 8 * ib, pb));
       NCE_TS(2 * m + h, 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_s + buf * BWD_BN;
+      const uint32_t d_tmem = tmem_s + (BWD4_NSB == 2 ? buf * BWD_BN : 0);
       if (elect_one()) {
         const uint32_t yb = b_lo0 + ib * (BWD_GROUP_BYTES >> 4);
 #pragma unroll
@@ -758,10 +769,15 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
       if (elect_one()) {
         const uint32_t ya = a_lo0 + ia * (BWD_GROUP_BYTES >> 4);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 4 - BWD4_XS; ++c)       // out-of-half chunks whose X lives in TMEM
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            mma_ss_lo(d_tmem, x_out + c * (X_CHUNK_BYTES >> 4) + 2 * j, ya + c * (BWD_SLOT_BYTES >> 4) + 2 * j, idesc_s, true);
+            mma_ts_lo(d_tmem, tmem_x2 + c * 32 + j * 8, ya + c * (BWD_SLOT_BYTES >> 4) + 2 * j, idesc_s, true);
+#pragma unroll
+        for (int c = 4 - BWD4_XS; c < 4; ++c)       // the rest: X from shared memory
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            mma_ss_lo(d_tmem, x_out + (c - (4 - BWD4_XS)) * (X_CHUNK_BYTES >> 4) + 2 * j, ya + c * (BWD_SLOT_BYTES >> 4) + 2 * j, idesc_s, true);
         tc_commit_a(ae0 + 8 * ia);
         tc_commit_a(sf0 + 8 * buf);
       }
@@ -826,18 +842,22 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
     const uint32_t gf_mine = mapa_u32(gf, static_cast<uint32_t>(h)), gf_peer = mapa_u32(gf, peer);
     const uint32_t g_row = smem_u32(sG) + w * BWD_G_BYTES + row_l * 128;
     const uint32_t g_row_mine = mapa_u32(g_row, static_cast<uint32_t>(h)), g_row_peer = mapa_u32(g_row, peer);
-    if (w == 0) {
-      // X[row, h*256 .. +256) -> TMEM columns tmem_x .. +128 of this thread's lane (bf16 pairs, K ascending)
-      const uint4* xsrc = reinterpret_cast<const uint4*>((dir ? p.xmat[1] : p.xmat[0]) + static_cast<long long>(row_ok ? row : 0) * NCE_D + h * 256);
+    {
+      // warpgroup 0: X[row, h*256 .. +256) -> TMEM columns tmem_x .. +128 of this thread's lane (bf16 pairs, K ascending)
+      // warpgroup 1: the first 4 - XS out-of-half chunks X[row, (1-h)*256 .. ) -> tmem_x2
+      const int k0 = (w == 0) ? h * 256 : (1 - h) * 256;
+      const int nch = (w == 0) ? 4 : 4 - BWD4_XS;
+      const uint32_t dst = (w == 0) ? tmem_x : tmem_x2;
+      const uint4* xsrc = reinterpret_cast<const uint4*>((dir ? p.xmat[1] : p.xmat[0]) + static_cast<long long>(row_ok ? row : 0) * NCE_D + k0);
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < nch; ++c) {
         uint32_t xr[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint4 t = row_ok ? __ldg(xsrc + c * 8 + i) : make_uint4(0u, 0u, 0u, 0u);
           xr[4 * i] = t.x; xr[4 * i + 1] = t.y; xr[4 * i + 2] = t.z; xr[4 * i + 3] = t.w;
         }
-        tmem_st_x32(tmem_x + lane_base + c * 32, xr);
+        tmem_st_x32(dst + lane_base + c * 32, xr);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -865,7 +885,7 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
       if (q == 0) NCE_TS(n, 3);
       tc_fence_after();
       uint32_t v[32];
-      tmem_ld_x32(tmem_s + lane_base + w * BWD_BN, v);
+      tmem_ld_x32(tmem_s + lane_base + (BWD4_NSB == 2 ? w * BWD_BN : 0), v);
       NCE_PW(2, tmem_ld_wait());
       tc_fence_before();
       mbar_arrive_a(se);
