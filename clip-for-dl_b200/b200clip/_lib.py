@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libb200clip.so")
+LIB_PATH = os.environ.get("B200CLIP_LIB_PATH") or os.path.join(_HERE, "_lib", "libb200clip.so")   # env: experiment builds
 
 vp, ll, i32, f32, f64, sz = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_double, C.c_size_t
 

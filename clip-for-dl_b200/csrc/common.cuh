@@ -169,6 +169,16 @@ __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint4 v, uint
                ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_bar)
                : "memory");
 }
+// bulk copy from this CTA's shared memory into a (possibly remote) CTA of the cluster; completes `bytes` tx-bytes on the
+// mbarrier at `cluster_bar` (same CTA as the destination).  Source, destination and size are multiples of 16 bytes.
+__device__ __forceinline__ void bulk_copy_s2s_cluster(uint32_t cluster_dst, uint32_t cta_src, uint32_t bytes, uint32_t cluster_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(cluster_dst), "r"(cta_src), "r"(bytes), "r"(cluster_bar)
+               : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 // tcgen05.commit that arrives on the barrier at the same offset in every CTA of `cta_mask`
 __device__ __forceinline__ void tc_commit_multicast_a(uint32_t bar_addr, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -280,6 +290,9 @@ __device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t smem_addr, uint3
 // Lean form for issue loops: a descriptor is {lo, hi} with hi constant for every 128B-swizzled tile
 // (SBO = 1024 B, version 1, layout SW128) and lo = (addr >> 4) | (LBO >> 4) << 16, so advancing along K is ONE 32-bit add.
 constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (LAYOUT_SW128 << 29);
+constexpr uint32_t LAYOUT_SW64 = 4;
+// 64B-swizzled K-major tile: rows of 64 B (32 bf16 of K), 8-row atoms of 512 B; 16-byte chunk index XOR ((row >> 1) & 3)
+constexpr uint32_t DESC_HI_SW64 = (512u >> 4) | (1u << 14) | (LAYOUT_SW64 << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
   return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
 }
@@ -291,6 +304,19 @@ __device__ __forceinline__ void mma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32
       "mov.b64 db, {%2, %5};\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
       ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(static_cast<uint32_t>(accumulate)), "r"(DESC_HI_SW128)
+      : "memory");
+}
+
+// same with separate descriptor high words for A and B (different swizzle modes)
+__device__ __forceinline__ void mma_ss_lo_ab(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(static_cast<uint32_t>(accumulate)), "r"(a_hi), "r"(b_hi)
       : "memory");
 }
 

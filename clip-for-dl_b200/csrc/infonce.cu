@@ -272,6 +272,7 @@ constexpr int BWD_TB = 3;                   // ring B depth in tiles (the 4 Y K-
 constexpr int BWD_SLOT_BYTES = BWD_BN * 128;            // one [32 x 64] bf16 chunk
 constexpr int BWD_GROUP_BYTES = 4 * BWD_SLOT_BYTES;     // 4 chunks = half a Y tile
 constexpr int BWD_G_BYTES = 128 * 128;      // [128 rows x 64 bf16]: even tiles use K cols 0-31, odd tiles 32-63
+constexpr int BWD_G_TILE_BYTES = 128 * 64;  // version 4: one [128 rows x 32 bf16] G tile per slot (64B-swizzled, contiguous)
 #ifndef B200CLIP_BWD4_NSB
 #define B200CLIP_BWD4_NSB 1
 #endif
@@ -667,7 +668,7 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
       mbar_init(&s_empty[b], 128);
     }
     for (int b = 0; b < 4; ++b) {
-      mbar_init(&g_full[b], 1);
+      mbar_init(&g_full[b], (b >> 1) == h ? 4 : 1);   // own slots: 4 epilogue warps arrive; peer slots: arming arrival + 8192 tx bytes
       mbar_init(&g_empty[b], 2);
     }
     mbar_init(acc_full, 1);
@@ -802,7 +803,8 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
     for (int n = 0; n < nt; ++n) {
       const int par = n & 1, kbuf = (n >> 1) & 1;
       const int slot = par * 2 + kbuf;
-      if (elect_one()) mbar_arrive_expect_tx_a(gf0 + 8 * slot, 128 * 64);   // arm: the G tile arrives as 128 x 64 B of st.async
+      // peer-owned slot: arm for the four 2 KB bulk copies of the G tile; own slot: the epilogue warps arrive themselves
+      if (par != h && elect_one()) mbar_arrive_expect_tx_a(gf0 + 8 * slot, BWD_G_TILE_BYTES);
       __syncwarp();
       NCE_PW(0, mbar_wait_a(bf0 + 8 * ib, pb));     // tiles owned by the peer were never waited on by the S issuer
       if (par == h) NCE_PW(1, mbar_wait_cluster_a(gf0 + 8 * slot, (n >> 2) & 1));
@@ -813,7 +815,8 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
         const uint32_t yb = y_lo0 + ib * (BWD_GROUP_BYTES >> 4);
 #pragma unroll
         for (int jj = 0; jj < BWD_BN / 16; ++jj)
-          mma_ss_lo(tmem_acc, g_lo + kbuf * (BWD_G_BYTES >> 4) + par * 4 + jj * 2, yb + jj * (2048 >> 4), idesc_g, (n | jj) != 0);
+          mma_ss_lo_ab(tmem_acc, g_lo + slot * (BWD_G_TILE_BYTES >> 4) + jj * 2, DESC_HI_SW64, yb + jj * (2048 >> 4), DESC_HI_SW128,
+                       idesc_g, (n | jj) != 0);
         tc_commit_a(be0 + 8 * ib);
         tc_commit_multicast_a(ge0 + 8 * slot, 0x3);   // both CTAs' g_empty[slot]: the owner refills once BOTH have read it
       }
@@ -837,11 +840,14 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
     const int warp_diag_lo = rb * 128 + q * 32 + (dir ? p.diag_off[1] : p.diag_off[0]);
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t sf = smem_u32(s_full) + 8 * w, se = smem_u32(s_empty) + 8 * w;
-    // this warpgroup owns G slot (h, w): buffer w, K half h, in BOTH CTAs
+    // this warpgroup owns G slot (h, w) in BOTH CTAs: a [128 rows x 32 bf16] K-major tile, 64 B rows, 64B swizzle (8 KB,
+    // contiguous, so a warp's 32 rows are one 2 KB bulk copy)
     const uint32_t gf = smem_u32(g_full) + 8 * (2 * h + w), ge = smem_u32(g_empty) + 8 * (2 * h + w);
-    const uint32_t gf_mine = mapa_u32(gf, static_cast<uint32_t>(h)), gf_peer = mapa_u32(gf, peer);
-    const uint32_t g_row = smem_u32(sG) + w * BWD_G_BYTES + row_l * 128;
-    const uint32_t g_row_mine = mapa_u32(g_row, static_cast<uint32_t>(h)), g_row_peer = mapa_u32(g_row, peer);
+    const uint32_t gf_peer = mapa_u32(gf, peer);
+    const uint32_t g_tile = smem_u32(sG) + (2 * h + w) * BWD_G_TILE_BYTES;
+    const uint32_t g_row = g_tile + row_l * 64;
+    const uint32_t g_warp = g_tile + q * 2048, g_warp_peer = mapa_u32(g_warp, peer);
+    const uint32_t g_swz = static_cast<uint32_t>((row_l >> 1) & 3);
     {
       // warpgroup 0: X[row, h*256 .. +256) -> TMEM columns tmem_x .. +128 of this thread's lane (bf16 pairs, K ascending)
       // warpgroup 1: the first 4 - XS out-of-half chunks X[row, (1-h)*256 .. ) -> tmem_x2
@@ -914,11 +920,14 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
       // slot (h, w) is reused every second own tile: wait until BOTH CTAs' dX MMAs of its previous use have read it
       NCE_PW(1, mbar_wait_cluster_a(ge, ((m >> 1) & 1) ^ 1));
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t off = static_cast<uint32_t>(((h * 4 + c) ^ (row_l & 7)) << 4);
-        const uint4 val = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
-        st_async_v4(g_row_mine + off, val, gf_mine);
-        st_async_v4(g_row_peer + off, val, gf_peer);
+      for (int c = 0; c < 4; ++c)
+        st_shared_v4(g_row + ((static_cast<uint32_t>(c) ^ g_swz) << 4),
+                     make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]));
+      fence_proxy_async_smem();                       // generic stores -> visible to tcgen05.mma and the bulk copy (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_a(gf);                            // local dX issuer: 1 of 4 warps
+        bulk_copy_s2s_cluster(g_warp_peer, g_warp, 2048, gf_peer);   // this warp's 32 rows to the peer CTA
       }
       if (q == 0) NCE_TS(n, 4);
       ph ^= 1;

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int iters)
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  for (int i = threadIdx.x; i < 196 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   if (warp == 0) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
   fence_proxy_async_smem();
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int iters)
     // A: 8 chunks of [128 x 64] (16 KB each) at smem+0 ; B: chunks of [N x 64] at smem + 128 KB (K-major) ;
     // MN-major B ([16 K-rows] x N): 64-element groups 2048 B apart like the backward kernel
     const uint32_t a_lo = desc_lo(smem_u32(smem), 16);
-    const uint32_t b_lo = (MODE == 2) ? desc_lo(smem_u32(smem + 128 * 1024), 2048) : desc_lo(smem_u32(smem + 128 * 1024), 16);
+    const uint32_t b_lo = (MODE == 2) ? desc_lo(smem_u32(smem + 64 * 1024), 4096) : desc_lo(smem_u32(smem + 64 * 1024), 16);
     long long t0 = 0, t1 = 0;
     for (int rep = 0; rep < 2; ++rep) {
       t0 = clock64();
@@ -41,7 +41,10 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int iters)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (MODE == 1) mma_ts_lo(tmem + 256, tmem + c * 32 + j * 8, b_lo + c * ((N * 128) >> 4) + 2 * j, idesc, true);
-              else if (MODE == 2) mma_ss_lo(tmem + 256, a_lo + c * (16384 >> 4) + 2 * j, b_lo + (c * 4 + j) * (2048 >> 4) % 1024, idesc, true);
+              else if (MODE == 2) {                     // the dX MMA of nce_bwd4: G tile (A, K-major) x Y in-half tile (B, MN-major)
+                const int t = (c * 4 + j) >> 1, jj = j & 1;
+                mma_ss_lo(tmem, a_lo + (t & 1) * 1024 + ((t >> 1) & 1) * 4 + jj * 2, b_lo + (t & 7) * 1024 + jj * 128, idesc, true);
+              }
               else mma_ss_lo(tmem + 256, a_lo + c * (16384 >> 4) + 2 * j, b_lo + c * ((N * 128) >> 4) + 2 * j, idesc, true);
             }
         }
@@ -85,7 +88,6 @@ int main() {
   run<0, 256>("SS  A,B K-major", d_out, iters);
   run<1, 256>("TS  A tmem", d_out, iters);
   run<2, 256>("SS  B MN-major (dX)", d_out, iters);
-  run<2, 128>("SS  B MN-major (dX)", d_out, iters);
   run<3, 128>("SS  A MN-major", d_out, iters);
   run<3, 256>("SS  A MN-major", d_out, iters);
   return 0;
