@@ -21,8 +21,7 @@ SOURCES = ["gemm.cu", "rowops.cu", "smallc.cu", "heads_mma.cu", "zeroshot.cu", "
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-DNDEBUG"]
-if os.environ.get("B200CLIP_NCE_EXP"):           # timing experiments (wrong results!), never for the product build
-    FLAGS.append("-DB200CLIP_NCE_EXP=" + os.environ["B200CLIP_NCE_EXP"])
+FLAGS += os.environ.get("B200CLIP_NVCC_FLAGS", "").split()      # e.g. -DB200CLIP_BWD4_NSB=2 for kernel experiments
 if os.environ.get("B200CLIP_NCE_PROF"):          # wait-cycle instrumentation of the InfoNCE backward (tools/nce_prof.py)
     FLAGS.append("-DB200CLIP_NCE_PROF")
 

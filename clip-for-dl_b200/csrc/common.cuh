@@ -93,11 +93,16 @@ static __device__ __noinline__ void mbar_watchdog_fire(uint32_t bar_addr, uint32
          blockIdx.z, threadIdx.x, bar_addr, parity);
   __trap();
 }
+#ifdef B200CLIP_POLL_WAIT
+#define B200_WAIT_OP "test_wait"      // non-blocking poll: the waiter spins instead of being suspended and woken up
+#else
+#define B200_WAIT_OP "try_wait"
+#endif
 __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier." B200_WAIT_OP ".parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
       : "r"(bar_addr), "r"(parity)
@@ -147,7 +152,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster_a(uint32_t bar_addr, uint3
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier." B200_WAIT_OP ".parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
       : "r"(bar_addr), "r"(parity)

@@ -598,19 +598,28 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constan
 // Pass 2, CTA-pair kernel (default).  The two D-half CTAs of a row block form a cluster (1x2x1).
 //  * Column tile n (32 columns) is OWNED by CTA (n & 1): only the owner recomputes S and forms G for it, so each logit is
 //    exponentiated once per direction instead of once per D-half (executed tensor work per direction: S once + dX).
-//  * The owner's epilogue warpgroup w = (own tile index & 1) owns G slot (owner, w) in BOTH CTAs and delivers the bf16
-//    tile with st.async: async-proxy stores that complete tx-bytes on the consumer CTA's g_full mbarrier, so no
-//    generic->async proxy fence and no release.cluster arrive sit on the S -> G -> dX critical chain.
-//  * g_full[slot]: 1 arming arrival (the local dX issuer) + 128 x 64 B of tx; g_empty[slot]: one multicast tcgen05.commit
-//    from each CTA's dX issuer (the slot may be refilled once BOTH CTAs have read it).  One barrier per slot and one
-//    waiter per barrier: every waiter sees consecutive phases (a barrier shared by two producers aliases parities).
-//  * The in-half K range of X lives in TMEM as the A operand of the S MMA (tcgen05.mma TS form): frees 64 KB of shared
-//    memory for a 5-tile ring B / 3-group ring A -- the S -> G -> dX -> free-slot pipeline is bound by ring depth.
-//  * Y traffic per CTA: in-half K-chunks of every tile (ring B, also the MN-major B operand of the dX MMA) + out-of-half
-//    chunks of its own tiles (ring A).
+//  * The owner's epilogue warpgroup w = (own tile index & 1) owns G slot (owner, w) in BOTH CTAs: an 8 KB [128 x 32] bf16
+//    tile, K-major with 64-byte rows and the 64B swizzle, so a warp's 32 rows are 2 KB contiguous.  Each warp writes its
+//    rows with st.shared.v4, fence.proxy.async, arrives on the local g_full and sends the same 2 KB to the peer CTA with ONE
+//    cp.async.bulk shared::cta -> shared::cluster that completes tx-bytes on the peer's g_full.  (The previous delivery,
+//    2 x 4 st.async of 16 B per thread, cost one shared-memory port transaction per 16 B on BOTH CTAs: 1024 transactions
+//    per tile pair, 4.08 ms; bulk delivery 3.35 ms.)
+//  * g_full[slot]: own slots count the 4 producing warps; peer slots 1 arming arrival (the local dX issuer) + 8192 tx bytes.
+//    g_empty[slot]: one multicast tcgen05.commit from each CTA's dX issuer (the slot may be refilled once BOTH CTAs have
+//    read it).  One barrier per slot and one waiter per barrier: every waiter sees consecutive phases (a barrier shared by
+//    two producers aliases parities).
+//  * X lives in TMEM as the A operand of the S MMA (tcgen05.mma TS form) for 7 of its 8 K-chunks: the in-half range (128
+//    columns) and the first 3 out-of-half chunks (96 columns); only the last chunk is read from shared memory.  Measured
+//    (tools/mma_rate.cu): an SS MMA at N = 32 costs 40 clk (its 4 KB A tile at 128 B/clk of shared-memory bandwidth), a TS
+//    MMA 17.8 clk (floor 16).  This leaves ONE 32-column S buffer: S(m+1) is issued once the epilogue has loaded S(m).
+//  * Y traffic per CTA: in-half K-chunks of every tile (ring B, 7 tiles deep, also the MN-major B operand of the dX MMA) +
+//    out-of-half chunks of its own tiles (ring A, 4 groups).
 // TMEM: acc [0,256) | S NSB x 32 | X in-half K range (128 columns) | the first 4 - XS out-of-half X chunks (32 columns each).
-// Experiments that lost (kept in git history): 64-column tiles with a bulk DSMEM copy of G (4.85 ms vs 4.42 ms at
-// B=32768: rings too shallow), pairing own tiles / splitting the dX accumulator to interleave independent accumulators.
+// Tensor-pipe floor per tile pair (tools/mma_rate.cu, both issuers running): 1219 clk; the kernel runs ~1750 (B=32768):
+// the rest is the S -> epilogue -> G -> dX dependency chain with two G slots per owner (wait-cycle breakdown:
+// tools/nce_prof.py with a B200CLIP_NCE_PROF=1 build).
+// Experiments that lost (kept in git history): 64-column tiles (rings too shallow), pairing own tiles / splitting the dX
+// accumulator, polling test_wait instead of try_wait (no change), two S buffers with 2 X chunks in smem (no change).
 // ------------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(1, 2, 1) __launch_bounds__(BWD_THREADS, 1)
 nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constant__ CUtensorMap tmap_y0,
