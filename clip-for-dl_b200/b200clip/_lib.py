@@ -26,7 +26,7 @@ SIGNATURES = {
     "b200clip_debug_set_nce_prof": (None, [vp]),
     "b200clip_gemm_bf16": (i32, [vp, vp, i32, i32, i32, i32, i32, ll, ll, i32, f32, vp, ll, vp, ll, vp, vp, ll, vp, ll, i32, vp]),
     "b200clip_l2norm_fwd": (i32, [vp, i32, ll, vp, vp, vp, ll, i32, f32, vp]),
-    "b200clip_l2norm_bwd": (i32, [vp, vp, i32, ll, vp, vp, i32, ll, i32, f32, vp, vp, vp]),
+    "b200clip_l2norm_bwd": (i32, [vp, i32, vp, i32, ll, vp, vp, i32, ll, i32, f32, vp, vp, vp]),
     "b200clip_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, ll, i32, f32, f32, vp]),
     "b200clip_layernorm_bwd_workspace_bytes": (sz, [ll, i32]),
     "b200clip_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, ll, i32, f32, C.c_uint, vp, sz, vp]),
@@ -41,7 +41,8 @@ SIGNATURES = {
     "b200clip_infonce_workspace_bytes": (sz, [ll, ll]),
     "b200clip_infonce_fwd_stats": (i32, [vp, vp, i32, ll, ll, f32, vp, vp, vp, sz, vp]),
     "b200clip_infonce_loss": (i32, [vp, vp, i32, ll, ll, ll, f32, vp, vp, ll, ll, vp, vp, vp, vp, vp, sz, vp]),
-    "b200clip_infonce_bwd": (i32, [vp, vp, i32, ll, ll, ll, f32, vp, vp, vp, vp, vp, vp]),
+    "b200clip_infonce_bwd_splits": (i32, [ll, ll]),
+    "b200clip_infonce_bwd": (i32, [vp, vp, i32, ll, ll, ll, f32, vp, vp, vp, vp, i32, vp, vp]),
     "b200clip_smallc_workspace_bytes": (sz, [ll, i32, i32]),
     "b200clip_mlbce_fwd_bwd": (i32, [vp, ll, vp, vp, i32, ll, ll, i32, i32, f32, vp, f64, vp, vp, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "b200clip_fc_bce_fwd_bwd": (i32, [vp, ll, vp, vp, vp, ll, ll, i32, i32, f64, f32, vp, vp, i32, vp, vp, vp, vp, vp, vp, sz, vp]),

@@ -107,7 +107,7 @@ def head_backward(tensors, meta, g):
     need_dxi, need_dxt = meta["need_dx"]
     drop_p, drop_seed = meta["drop"]
     g = ops._f32c(g).reshape(())
-    d_ihat, d_that = ops.infonce_backward(ihat, that_all, meta["tau_nce"], rinvh, cinvh, g, row0=row0)
+    d_ihat, d_that = ops.infonce_backward(ihat, that_all, meta["tau_nce"], rinvh, cinvh, g, row0=row0, allow_splits=True)
     d_that_loc, work = dp.scatter_sum_rows(d_that, group, async_op=True)
     # image side: through the L2 normalisation, plus g * (the two BCE heads' input gradient from the forward pass)
     dy_img = ops.l2norm_bwd(d_ihat, y_img, inv_img, addend=d_bce, addend_scale=g)

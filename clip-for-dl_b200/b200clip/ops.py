@@ -95,12 +95,14 @@ def l2norm_fwd(x: torch.Tensor, want_bf16: bool = True, want_f32: bool = False, 
 def l2norm_bwd(dy: torch.Tensor, x: torch.Tensor, inv: torch.Tensor, eps: float = L2_EPS, out: Optional[torch.Tensor] = None,
                accumulate: bool = False, addend: Optional[torch.Tensor] = None,
                addend_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dx = d normalize(x) . dy  [+ addend * addend_scale]  (addend [rows, D] f32, addend_scale a device scalar)."""
+    """dx = d normalize(x) . dy  [+ addend * addend_scale]  (addend [rows, D] f32, addend_scale a device scalar).
+    dy may be [S, rows, D]: S partial sums (the InfoNCE backward's column splits), added on the fly."""
     dy = _f32c(dy)
     rows, D = x.shape
+    parts = dy.shape[0] if dy.dim() == 3 else 1
     if out is None:
         out = torch.empty((rows, D), dtype=torch.float32, device=x.device)
-    check(load().b200clip_l2norm_bwd(ptr(dy), ptr(x), int(x.dtype == torch.bfloat16), D, ptr(inv), ptr(out), int(accumulate),
+    check(load().b200clip_l2norm_bwd(ptr(dy), parts, ptr(x), int(x.dtype == torch.bfloat16), D, ptr(inv), ptr(out), int(accumulate),
                                      rows, D, eps, ptr(addend), ptr(addend_scale), stream_ptr()), "l2norm_bwd")
     return out
 
@@ -263,12 +265,15 @@ def _timing_events():
     return (torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext))
 
 
-def infonce_backward(i_hat, t_hat, temperature, rinvh, cinvh, grad_scale: Optional[torch.Tensor], row0: int = 0):
-    """Returns d_i [b_loc, D] f32 and d_t_partial [b_glob, D] f32 (this rank's contribution)."""
+def infonce_backward(i_hat, t_hat, temperature, rinvh, cinvh, grad_scale: Optional[torch.Tensor], row0: int = 0,
+                     allow_splits: bool = False):
+    """Returns d_i [b_loc, D] f32 and d_t_partial [b_glob, D] f32 (this rank's contribution).  With allow_splits (data
+    parallel, b_loc << b_glob) d_i may come back as [S, b_loc, D] partial sums over column ranges (l2norm_bwd adds them)."""
     b_loc, D = i_hat.shape
     b_glob = t_hat.shape[0]
     dev = i_hat.device
-    d_i = torch.empty((b_loc, D), dtype=torch.float32, device=dev)
+    splits = int(load().b200clip_infonce_bwd_splits(b_loc, b_glob)) if allow_splits else 1
+    d_i = torch.empty((splits, b_loc, D) if splits > 1 else (b_loc, D), dtype=torch.float32, device=dev)
     d_t = torch.empty((b_glob, D), dtype=torch.float32, device=dev)
     gs = None
     if grad_scale is not None:
@@ -278,7 +283,7 @@ def infonce_backward(i_hat, t_hat, temperature, rinvh, cinvh, grad_scale: Option
         e0, e1 = _timing_events()
         e0.record()
     check(load().b200clip_infonce_bwd(ptr(i_hat), ptr(t_hat), D, b_loc, b_glob, row0, temperature, ptr(rinvh), ptr(cinvh),
-                                      ptr(gs), ptr(d_i), ptr(d_t), stream_ptr()), "infonce_bwd")
+                                      ptr(gs), ptr(d_i), splits, ptr(d_t), stream_ptr()), "infonce_bwd")
     if ev is not None:
         e1.record()
         ev.append((e0, e1))

@@ -57,24 +57,33 @@ struct NceFwdParams {
   float* r_part;        // [r_slots][nrows_pad]   zero-initialised by the host
   float* c_part;        // [row_blocks][ncols]
   int nrows_pad;
+  const __nv_bfloat16* x;   // X matrix (rows of the stationary operand), read by the TMEM-resident variant
 };
 
 // Issue loops below are WARP-UNIFORM (all 32 lanes run the loop, one elected lane issues TMA / tcgen05 instructions):
 // descriptor words then live in uniform registers and an MMA costs one 32-bit add per operand.  The first version
 // ran them under `if (lane == 0)`; ncu showed ~230 SASS instructions per 4 MMAs and the tensor pipe 14-33 % busy.
-template <int BN, int STAGES, int NWG>
+//
+// XT = true (experimental, off by default -- see FWD_XT below): the stationary X row block lives in TMEM (256 columns of packed bf16 pairs) and is the A operand of
+// tcgen05.mma in its TS form.  With X in shared memory every N = 128 MMA read 8 KB of operands per 64 clk -- exactly the
+// 128 B/clk the shared-memory port delivers (tools/mma_rate.cu) -- while TMA wrote another 64 B/clk of Y into the same
+// memory: the kernel was shared-memory-bound at ~56 % of the MMA rate.  TS form: operand reads drop to the Y tile
+// (64 B/clk), the 128 KB of X leave shared memory (24-stage Y ring), S tiles are 128 x 64 (4 TMEM buffers x 64 columns).
+// X is (re)loaded at every row-block switch by warps 0-3 (one TMEM lane quadrant each) straight from global memory.
+template <int BN, int STAGES, int NWG, bool XT>
 constexpr int nce_fwd_smem_bytes() {
-  return NCE_KC * X_CHUNK_BYTES + STAGES * BN * 128 + NWG * 4 * BN * 4 + 512 + 1024;
+  return (XT ? 0 : NCE_KC * X_CHUNK_BYTES) + STAGES * BN * 128 + NWG * 4 * BN * 4 + 512 + 1024;
 }
 
-template <int BN, int STAGES, int NWG>
+template <int BN, int STAGES, int NWG, bool XT>
 __global__ void __launch_bounds__(128 + NWG * 128, 1)
 nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
                const NceFwdParams p) {
+  static_assert(!XT || NWG * BN <= 256, "TMEM: 256 columns of X + NWG S buffers");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX = smem;
-  uint8_t* sY = sX + NCE_KC * X_CHUNK_BYTES;
+  uint8_t* sY = sX + (XT ? 0 : NCE_KC * X_CHUNK_BYTES);
   float* scratch = reinterpret_cast<float*>(sY + STAGES * BN * 128);        // [NWG][4 warps][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + NWG * 4 * BN);
   uint64_t* x_full = bars;
@@ -97,7 +106,7 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     tma_prefetch_desc(&tmap_y);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(x_full, 1);
+    mbar_init(x_full, XT ? 128 : 1);
     mbar_init(x_empty, 1);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&y_full[s], 1);
@@ -110,13 +119,37 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, NWG * BN);
+    tmem_alloc(tmem_slot, XT ? 512 : NWG * BN);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_sbuf = tmem_base + (XT ? 256 : 0);      // S buffers; XT: columns [0, 256) hold X
+
+  // XT: warps 0-3 refill the X operand in TMEM at a row-block switch (warp w owns TMEM lanes 32w .. 32w+31 = rows)
+  auto load_x_to_tmem = [&](int rb, uint32_t xph) {
+    mbar_wait_a(smem_u32(x_empty), xph ^ 1);                  // every MMA that read the previous row block has completed
+    tc_fence_after();
+    const int row = rb * 128 + warp * 32 + lane;
+    const bool row_ok = row < p.nrows;
+    const uint4* src = reinterpret_cast<const uint4*>(p.x + static_cast<long long>(row_ok ? row : 0) * NCE_D);
+    const uint32_t dst = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll 1
+    for (int kc = 0; kc < NCE_KC; ++kc) {
+      uint32_t xr[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 t = row_ok ? __ldg(src + kc * 8 + i) : make_uint4(0u, 0u, 0u, 0u);
+        xr[4 * i] = t.x; xr[4 * i + 1] = t.y; xr[4 * i + 2] = t.z; xr[4 * i + 3] = t.w;
+      }
+      tmem_st_x32(dst + kc * 32, xr);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive_a(smem_u32(x_full));
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -127,13 +160,17 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     int rb = t0 / CT, ct = t0 - rb * CT;
     for (int t = t0; t < t1; ++t) {
       if (rb != cur_rb) {
-        mbar_wait_a(xe, xph ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx_a(xf, NCE_KC * X_CHUNK_BYTES);
+        if constexpr (XT) {
+          load_x_to_tmem(rb, xph);
+        } else {
+          mbar_wait_a(xe, xph ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx_a(xf, NCE_KC * X_CHUNK_BYTES);
 #pragma unroll
-          for (int kc = 0; kc < NCE_KC; ++kc) tma_load_2d_a(sx + kc * X_CHUNK_BYTES, &tmap_x, xf, kc * 64, rb * 128);
+            for (int kc = 0; kc < NCE_KC; ++kc) tma_load_2d_a(sx + kc * X_CHUNK_BYTES, &tmap_x, xf, kc * 64, rb * 128);
+          }
+          __syncwarp();
         }
-        __syncwarp();
         xph ^= 1;
         cur_rb = rb;
       }
@@ -160,13 +197,14 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     int rb = t0 / CT, ct = t0 - rb * CT;
     for (int t = t0; t < t1; ++t) {
       if (rb != cur_rb) {
+        if constexpr (XT) load_x_to_tmem(rb, xph);
         mbar_wait_a(xf, xph);
         xph ^= 1;
         cur_rb = rb;
       }
       mbar_wait_a(se0 + 8 * buf, sph ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + buf * BN;
+      const uint32_t d_tmem = tmem_sbuf + buf * BN;
 #pragma unroll
       for (int kc = 0; kc < NCE_KC; ++kc) {
         mbar_wait_a(yf0 + 8 * s, ph);
@@ -174,7 +212,10 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         if (elect_one()) {
           const uint32_t a = x_lo + kc * (X_CHUNK_BYTES >> 4), b = y_lo + s * (Y_BYTES >> 4);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) mma_ss_lo(d_tmem, a + 2 * j, b + 2 * j, idesc, (kc | j) != 0);
+          for (int j = 0; j < 4; ++j) {
+            if constexpr (XT) mma_ts_lo(d_tmem, tmem_base + kc * 32 + j * 8, b + 2 * j, idesc, (kc | j) != 0);
+            else mma_ss_lo(d_tmem, a + 2 * j, b + 2 * j, idesc, (kc | j) != 0);
+          }
           tc_commit_a(ye0 + 8 * s);
         }
         __syncwarp();
@@ -189,14 +230,28 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       if (++buf == NWG) { buf = 0; sph ^= 1; }
       if (++ct == CT) { ct = 0; ++rb; }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    // ===================== warps 2, 3 (XT): their TMEM lane quadrants of X at every row-block switch =====================
+    if constexpr (XT) {
+      int cur_rb = -1;
+      uint32_t xph = 0;
+      for (int t = t0; t < t1; ++t) {
+        const int rb = t / CT;
+        if (rb != cur_rb) {
+          load_x_to_tmem(rb, xph);
+          xph ^= 1;
+          cur_rb = rb;
+        }
+      }
+    }
+  } else {
     // ===================== epilogue warpgroups: tile n of this CTA -> warpgroup n % NWG =====================
     const int w = (warp - 4) >> 2;                 // epilogue warpgroup
     const int q = warp & 3;                        // TMEM lane quadrant
     const int tid_wg = threadIdx.x - 128 - w * 128;
     float* my_scratch = scratch + w * 4 * BN;
     const uint32_t sf = smem_u32(s_full) + 8 * w, se = smem_u32(s_empty) + 8 * w;
-    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + w * BN;
+    const uint32_t t_addr = tmem_sbuf + (static_cast<uint32_t>(q * 32) << 16) + w * BN;
     float rsum = 0.f;
     int cur_rb = -1;
     uint32_t sph = 0;
@@ -260,7 +315,7 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, NWG * BN);
+  if (warp == 2) tmem_dealloc(tmem_base, XT ? 512 : NWG * BN);
 }
 
 // ================================================================================================
@@ -300,6 +355,8 @@ struct NceBwdParams {
   float out_scale;          // 1 / (B_glob * tau)
   const float* grad_scale;  // optional device scalar multiplied into out_scale (upstream dLoss)
   long long* prof;          // debug: per-role wait-cycle counters of one cluster (b200clip_debug_set_nce_prof) or null
+  int nsplit[2];            // version 4: column splits per direction (each split is its own cluster, writes its own partial dX)
+  long long split_stride[2];   // elements between the partial outputs of consecutive splits
 };
 
 // debug instrumentation (build with B200CLIP_NCE_PROF=1 python build.py): cycles spent inside each wait, accumulated per
@@ -628,10 +685,15 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
   const int dir = blockIdx.z;
   int h;                                            // D-half owned by this CTA == rank in the pair; read once (volatile asm:
   asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(h));   // the compiler otherwise re-reads the special register in the tile loop)
-  const int rb = blockIdx.x;
   const int nrows = dir ? p.nrows[1] : p.nrows[0];
   const int ncols = dir ? p.ncols[1] : p.ncols[0];
-  if (rb * 128 >= nrows) return;                    // uniform over the whole cluster (same rb), before any barrier
+  // blockIdx.x = split * row_blocks + row block.  With few local rows (data parallel: b_loc << b_glob) direction 0 has few,
+  // long row blocks; its columns are then cut into `nsplit` ranges handled by separate clusters (partial dX each).
+  const int rbs = (nrows + 127) >> 7;
+  const int split = static_cast<int>(blockIdx.x) / rbs;
+  const int rb = static_cast<int>(blockIdx.x) - split * rbs;
+  const int nsplit = dir ? p.nsplit[1] : p.nsplit[0];
+  if (split >= nsplit) return;                      // uniform over the whole cluster (same blockIdx.x), before any barrier
   const CUtensorMap* tmap_x = dir == 0 ? &tmap_x0 : &tmap_x1;
   const CUtensorMap* tmap_y = dir == 0 ? &tmap_y0 : &tmap_y1;
   const uint32_t peer = static_cast<uint32_t>(h ^ 1);
@@ -661,8 +723,10 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
 #ifdef B200CLIP_NCE_PROF
   const bool prof_on = p.prof != nullptr && dir == 0 && rb == 100;
 #endif
-  const int nt = (ncols + BWD_BN - 1) / BWD_BN;     // all tiles
-  const int nown = (nt - h + 1) / 2;                // tiles owned by this CTA: n = 2m + h
+  const int nt_all = (ncols + BWD_BN - 1) / BWD_BN; // all column tiles
+  const int tile0 = static_cast<int>(static_cast<long long>(nt_all) * split / nsplit);           // this split's tile range
+  const int nt = static_cast<int>(static_cast<long long>(nt_all) * (split + 1) / nsplit) - tile0;
+  const int nown = (nt - h + 1) / 2;                // tiles owned by this CTA: n = 2m + h (n local to the split)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(tmap_x);
@@ -720,7 +784,7 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
         mbar_arrive_expect_tx_a(bf0 + 8 * ib, BWD_GROUP_BYTES);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          tma_load_2d_a(sb + ib * BWD_GROUP_BYTES + c * BWD_SLOT_BYTES, tmap_y, bf0 + 8 * ib, k_in + c * 64, n * BWD_BN);
+          tma_load_2d_a(sb + ib * BWD_GROUP_BYTES + c * BWD_SLOT_BYTES, tmap_y, bf0 + 8 * ib, k_in + c * 64, (tile0 + n) * BWD_BN);
       }
       __syncwarp();
       if (++ib == BWD4_TB) { ib = 0; pb ^= 1; }
@@ -730,7 +794,7 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
           mbar_arrive_expect_tx_a(af0 + 8 * ia, BWD_GROUP_BYTES);
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            tma_load_2d_a(sa + ia * BWD_GROUP_BYTES + c * BWD_SLOT_BYTES, tmap_y, af0 + 8 * ia, k_out + c * 64, n * BWD_BN);
+            tma_load_2d_a(sa + ia * BWD_GROUP_BYTES + c * BWD_SLOT_BYTES, tmap_y, af0 + 8 * ia, k_out + c * 64, (tile0 + n) * BWD_BN);
         }
         __syncwarp();
         if (++ia == BWD4_TA) { ia = 0; pa ^= 1; }
@@ -882,7 +946,7 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
     NCE_PROF_BEGIN();
     for (int m = w; m < nown; m += 2) {
       const int n = 2 * m + h;
-      const int col0 = n * BWD_BN;
+      const int col0 = (tile0 + n) * BWD_BN;
       const bool full_tile = col0 + BWD_BN <= ncols;
       const bool diag_tile = (col0 < warp_diag_lo + 32) && (col0 + BWD_BN > warp_diag_lo);
       float cs[32];
@@ -946,7 +1010,8 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
     tc_fence_after();
     float scale = p.out_scale;
     if (p.grad_scale) scale *= *p.grad_scale;
-    float* orow = (dir ? p.out[1] : p.out[0]) + static_cast<long long>(row) * NCE_D + h * 256 + w * 128;
+    float* orow = (dir ? p.out[1] : p.out[0]) + split * (dir ? p.split_stride[1] : p.split_stride[0]) +
+                  static_cast<long long>(row) * NCE_D + h * 256 + w * 128;
 #pragma unroll 1
     for (int c = 0; c < 128; c += 32) {
       uint32_t v[32];
@@ -1055,9 +1120,16 @@ __global__ void __launch_bounds__(256) nce_loss_kernel(const __nv_bfloat16* __re
   }
 }
 
-constexpr int FWD_BN = 128;
-constexpr int FWD_STAGES = 5;
-constexpr int FWD_NWG = 4;                 // epilogue warpgroups = TMEM S buffers (4 x 128 columns)
+// Default: X in shared memory, 128 x 128 S tiles, 5-stage Y ring: 0.82 ms at B = 32768.  The pass streams all of Y from L2
+// once per row block (256 x 32 MB = 8.6 GB -> 10.5 TB/s at 0.82 ms): it sits on the L2 -> SM bandwidth, not on the MMA
+// rate.  The TMEM-resident-X variant (XT: BN = 64, 24 stages) moves the same bytes in 8 KB boxes and measured 1.42 ms.
+#ifndef B200CLIP_FWD_XT
+#define B200CLIP_FWD_XT 0
+#endif
+constexpr bool FWD_XT = B200CLIP_FWD_XT != 0;
+constexpr int FWD_BN = FWD_XT ? 64 : 128;
+constexpr int FWD_STAGES = FWD_XT ? 24 : 5;
+constexpr int FWD_NWG = 4;                 // epilogue warpgroups = TMEM S buffers
 
 struct NceFwdPlan {
   int row_blocks, col_tiles, total_tiles, tiles_per_cta, grid, r_slots, nrows_pad;
@@ -1112,9 +1184,9 @@ extern "C" int b200clip_infonce_fwd_stats(const void* i_hat, const void* t_hat, 
   NceFwdParams p{};
   p.nrows = (int)b_loc; p.ncols = (int)b_glob; p.num_col_tiles = pl.col_tiles; p.total_tiles = pl.total_tiles;
   p.tiles_per_cta = pl.tiles_per_cta; p.r_slots = pl.r_slots; p.k1 = LOG2E / temperature; p.k2 = LOG2E / temperature;
-  p.r_part = r_part; p.c_part = c_part; p.nrows_pad = pl.nrows_pad;
-  auto kern = nce_fwd_kernel<FWD_BN, FWD_STAGES, FWD_NWG>;
-  constexpr int smem = nce_fwd_smem_bytes<FWD_BN, FWD_STAGES, FWD_NWG>();
+  p.r_part = r_part; p.c_part = c_part; p.nrows_pad = pl.nrows_pad; p.x = static_cast<const __nv_bfloat16*>(i_hat);
+  auto kern = nce_fwd_kernel<FWD_BN, FWD_STAGES, FWD_NWG, FWD_XT>;
+  constexpr int smem = nce_fwd_smem_bytes<FWD_BN, FWD_STAGES, FWD_NWG, FWD_XT>();
   static bool configured = false;
   if (!configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1155,9 +1227,17 @@ static long long* g_nce_prof = nullptr;
 // debug only: device buffer of 128 int64 receiving the wait-cycle counters of one cluster of the next backward launches
 extern "C" void b200clip_debug_set_nce_prof(void* buf) { g_nce_prof = static_cast<long long*>(buf); }
 
+// Column splits of direction 0 (dI): with b_loc << b_glob its few row blocks are 1024-tile-long CTAs that outlive the rest of
+// the grid; each split writes its own partial d_i (summed by the consumer, b200clip_l2norm_bwd's dy_partials).
+extern "C" int b200clip_infonce_bwd_splits(long long b_loc, long long b_glob) {
+  if (b_loc <= 0 || b_glob <= 0) return 1;
+  const long long s = (b_glob + b_loc) / (2 * b_loc);        // round(nt0 / (2 nt1))
+  return static_cast<int>(std::max<long long>(1, std::min<long long>(8, s)));
+}
+
 extern "C" int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D, long long b_loc, long long b_glob,
                                     long long row0, float temperature, const float* rinvh, const float* cinvh,
-                                    const float* grad_scale, float* d_i, float* d_t_partial, void* stream) {
+                                    const float* grad_scale, float* d_i, int d_i_splits, float* d_t_partial, void* stream) {
   B200_REQUIRE(D == NCE_D, "infonce: D=%d unsupported (kernels are built for D=%d)", D, NCE_D);
   B200_REQUIRE(b_loc > 0 && b_glob > 0 && row0 >= 0 && row0 + b_loc <= b_glob, "infonce_bwd: bad row range");
   B200_REQUIRE(aligned16(d_i) && aligned16(d_t_partial) && aligned16(rinvh) && aligned16(cinvh), "infonce_bwd: unaligned pointer");
@@ -1176,6 +1256,9 @@ extern "C" int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D,
   p.k1 = LOG2E / temperature; p.k2 = LOG2E / temperature;
   p.out_scale = 1.0f / (static_cast<float>(b_glob) * temperature);
   p.grad_scale = grad_scale;
+  B200_REQUIRE(d_i_splits >= 1 && d_i_splits <= 8, "infonce_bwd: d_i_splits=%d out of range", d_i_splits);
+  p.nsplit[0] = d_i_splits; p.split_stride[0] = b_loc * static_cast<long long>(D);
+  p.nsplit[1] = 1; p.split_stride[1] = 0;
   p.prof = g_nce_prof;
   constexpr int smem = nce_bwd_smem_bytes();
   static bool configured = false;
@@ -1186,7 +1269,9 @@ extern "C" int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D,
     B200_CHECK_CUDA(cudaFuncSetAttribute(nce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid(static_cast<unsigned>((b_glob + 127) / 128), 2, 2);
+  const long long gx = std::max((b_glob + 127) / 128, ((b_loc + 127) / 128) * d_i_splits);
+  dim3 grid(static_cast<unsigned>(variant == 4 ? gx : (b_glob + 127) / 128), 2, 2);
+  B200_REQUIRE(variant == 4 || d_i_splits == 1, "infonce_bwd: column splits need the CTA-pair kernel");
   if (variant == 4)
     nce_bwd4_kernel<<<grid, BWD_THREADS, nce_bwd4_smem_bytes(), static_cast<cudaStream_t>(stream)>>>(tx0, ty0, tx1, ty1, p);
   else

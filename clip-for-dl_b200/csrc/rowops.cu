@@ -68,10 +68,11 @@ __global__ void __launch_bounds__(ROW_THREADS) l2norm_bwd_kernel(const float* __
                                                                  long long ldx, const float* __restrict__ inv_norm,
                                                                  float* __restrict__ dx, int accumulate, int rows, int D,
                                                                  float eps, const float* __restrict__ addend,
-                                                                 const float* __restrict__ addend_scale) {
+                                                                 const float* __restrict__ addend_scale, int dy_partials) {
   const int lane = threadIdx.x & 31;
   const int nv = D >> 7;
   const float ascale = (addend && addend_scale) ? *addend_scale : 1.0f;
+  const long long pstride = static_cast<long long>(rows) * D;     // dy = sum of dy_partials partial sums, pstride apart
   for (long long row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); row < rows;
        row += static_cast<long long>(gridDim.x) * (ROW_THREADS / 32)) {
     const float inv = inv_norm[row];
@@ -82,6 +83,10 @@ __global__ void __launch_bounds__(ROW_THREADS) l2norm_bwd_kernel(const float* __
     for (int i = 0; i < MAX_V; ++i)
       if (i < nv) {
         g[i] = ld4(dy + row * D + i * 128 + lane * 4);
+        for (int s = 1; s < dy_partials; ++s) {
+          const float4 t = ld4(dy + s * pstride + row * D + i * 128 + lane * 4);
+          g[i].x += t.x; g[i].y += t.y; g[i].z += t.z; g[i].w += t.w;
+        }
         const float4 xv = ld4(x + row * ldx + i * 128 + lane * 4);
         yh[i] = make_float4(xv.x * inv, xv.y * inv, xv.z * inv, xv.w * inv);
         dot += g[i].x * yh[i].x + g[i].y * yh[i].y + g[i].z * yh[i].z + g[i].w * yh[i].w;
@@ -356,19 +361,20 @@ extern "C" int b200clip_l2norm_fwd(const void* x, int x_is_bf16, long long ldx, 
   return B200_OK;
 }
 
-extern "C" int b200clip_l2norm_bwd(const float* dy, const void* x, int x_is_bf16, long long ldx, const float* inv_norm,
-                                   float* dx, int accumulate, long long rows, int D, float eps, const float* addend,
-                                   const float* addend_scale, void* stream) {
+extern "C" int b200clip_l2norm_bwd(const float* dy, int dy_partials, const void* x, int x_is_bf16, long long ldx,
+                                   const float* inv_norm, float* dx, int accumulate, long long rows, int D, float eps,
+                                   const float* addend, const float* addend_scale, void* stream) {
+  B200_REQUIRE(dy_partials >= 1 && dy_partials <= 8, "l2norm_bwd: dy_partials=%d out of range", dy_partials);
   B200_REQUIRE(rows >= 0 && D > 0 && D % 128 == 0 && D <= MAX_D, "l2norm_bwd: D=%d must be a multiple of 128, <= %d", D, MAX_D);
   B200_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(addend), "l2norm_bwd: pointers must be 16-byte aligned");
   if (rows == 0) return B200_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (x_is_bf16)
     B200_DISPATCH_V(D, (l2norm_bwd_kernel<__nv_bfloat16, MAX_V><<<row_grid(rows), ROW_THREADS, 0, s>>>(
-        dy, static_cast<const __nv_bfloat16*>(x), ldx, inv_norm, dx, accumulate, (int)rows, D, eps, addend, addend_scale)));
+        dy, static_cast<const __nv_bfloat16*>(x), ldx, inv_norm, dx, accumulate, (int)rows, D, eps, addend, addend_scale, dy_partials)));
   else
     B200_DISPATCH_V(D, (l2norm_bwd_kernel<float, MAX_V><<<row_grid(rows), ROW_THREADS, 0, s>>>(
-        dy, static_cast<const float*>(x), ldx, inv_norm, dx, accumulate, (int)rows, D, eps, addend, addend_scale)));
+        dy, static_cast<const float*>(x), ldx, inv_norm, dx, accumulate, (int)rows, D, eps, addend, addend_scale, dy_partials)));
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -44,10 +44,11 @@ int b200clip_gemm_bf16(const void* a, const void* b, int a_mn_major, int b_mn_ma
 /* ---- a-L2: F.normalize(x, dim=-1), eps 1e-12 -- 0426/train.py:191-192, :971; 0426/disease_analysis.py:332 ----- */
 int b200clip_l2norm_fwd(const void* x, int x_is_bf16, long long ldx, void* y_bf16, float* y_f32, float* inv_norm,
                         long long rows, int D, float eps, void* stream);
-/* dx (+)= d/dx normalize(x) . dy  [+ addend * *addend_scale]   (addend [rows,D] f32 and its device scalar are optional) */
-int b200clip_l2norm_bwd(const float* dy, const void* x, int x_is_bf16, long long ldx, const float* inv_norm, float* dx,
-                        int accumulate, long long rows, int D, float eps, const float* addend, const float* addend_scale,
-                        void* stream);
+/* dx (+)= d/dx normalize(x) . dy  [+ addend * *addend_scale]   (addend [rows,D] f32 and its device scalar are optional);
+ * dy may be given as dy_partials >= 1 partial sums, rows*D elements apart (b200clip_infonce_bwd's d_i splits) */
+int b200clip_l2norm_bwd(const float* dy, int dy_partials, const void* x, int x_is_bf16, long long ldx, const float* inv_norm,
+                        float* dx, int accumulate, long long rows, int D, float eps, const float* addend,
+                        const float* addend_scale, void* stream);
 
 /* ---- LayerNorm tail of the projection block -- nn.LayerNorm(512), 0426/train.py:82,95 ------------------------ */
 int b200clip_layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y_f32, void* yhat_bf16,
@@ -95,9 +96,12 @@ int b200clip_infonce_fwd_stats(const void* i_hat, const void* t_hat, int D, long
 int b200clip_infonce_loss(const void* i_hat, const void* t_hat, int D, long long b_loc, long long b_glob, long long row0,
                           float temperature, const float* r, const float* c, long long c_lo, long long c_hi, float* rinvh,
                           float* cinvh, double* sums, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+/* d_i is [d_i_splits][b_loc][D]: partial sums over column ranges (1 <= splits <= 8; b200clip_infonce_bwd_splits suggests
+ * a count that balances the grid when b_loc << b_glob); their sum is the gradient. */
+int b200clip_infonce_bwd_splits(long long b_loc, long long b_glob);
 int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D, long long b_loc, long long b_glob, long long row0,
                          float temperature, const float* rinvh, const float* cinvh, const float* grad_scale, float* d_i,
-                         float* d_t_partial, void* stream);
+                         int d_i_splits, float* d_t_partial, void* stream);
 
 /* ---- a-B: multilabel_contrastive_loss(image_features, text_features, labels, temperature) -- 0426/train.py:178-230
  * label_sum: device scalar = sum(labels) over the GLOBAL batch; total_elems = B_glob * C.  status gets 1 when the

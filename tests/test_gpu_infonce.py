@@ -74,7 +74,7 @@ def test_upstream_gradient_scale_and_determinism():
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])     # bit-reproducible
 
 
-@pytest.mark.parametrize("W", [2, 4])
+@pytest.mark.parametrize("W", [2, 4, 8])
 def test_rank_partitioned_equals_monolithic(W):
     """Simulated data-parallel ranks on ONE GPU: each 'rank' runs the kernels on its row block against all columns;
     column sums are SUM-combined and dT partials summed (what all_reduce / reduce_scatter do across GPUs)."""
@@ -106,8 +106,10 @@ def test_rank_partitioned_equals_monolithic(W):
                                              k * n, (k + 1) * n, _lib.ptr(rinvh), _lib.ptr(cinvh), _lib.ptr(sums), None,
                                              _lib.ptr(ws), nb, _lib.stream_ptr()), "loss")
         total += sums
-        d_i, d_t = ops.infonce_backward(blk, tb, tau, rinvh, cinvh, None, row0=k * n)
-        dI.append(d_i)
+        # allow_splits: with b_loc << b_glob the kernel cuts direction 0's columns into ranges (partial d_i sums)
+        d_i, d_t = ops.infonce_backward(blk, tb, tau, rinvh, cinvh, None, row0=k * n, allow_splits=True)
+        assert (d_i.dim() == 3) == (W >= 3), d_i.shape
+        dI.append(d_i.sum(0) if d_i.dim() == 3 else d_i)
         dT += d_t
     loss = 1.0 / tau + (total[0] + total[1]) / (2.0 * B) - total[2] / B
     assert abs(loss.item() - loss_ref.item()) <= LOSS_TOL * abs(loss_ref.item())

@@ -22,6 +22,10 @@ def test_l2norm_fwd_bwd(rows, D):
     assert rel_l2(yf, y) < 1e-6
     assert rel_l2(yb.float(), y) < 4e-3
     assert rel_l2(ops.l2norm_bwd(g, x, inv), xr.grad) < 1e-5
+    # dy given as 3 partial sums + a scaled addend (what the fused head feeds it)
+    parts = torch.stack([0.5 * g, 0.25 * g, 0.25 * g])
+    add, sc = synth.randn(3, rows, D).to(dev()), torch.full((), 1.5, device=dev())
+    assert rel_l2(ops.l2norm_bwd(parts, x, inv, addend=add, addend_scale=sc), xr.grad + 1.5 * add) < 1e-5
     # autograd wrapper + bf16 input path
     xa = x.clone().requires_grad_(True)
     ops.normalize(xa).backward(g)
