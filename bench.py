@@ -315,8 +315,12 @@ def run_head(args, cfg):
     # the recomputed logits are NOT counted), DESIGN.md "Kernels".
     bwd_avg_ms = sum(bwd_ms) / max(len(bwd_ms), 1)
     achieved = (4.0 * b_loc * B * cfg["D"]) / (bwd_avg_ms / 1e3) / 1e12 if bwd_avg_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "nce_bwd_kernel", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["src"] + ", sustained bf16",
+    # DRAM bytes of one launch from the ncu --set full capture of this kernel at this size (profiles/r1_v6_ncu_nce_B32768.txt);
+    # no capture exists for other sizes / rank counts
+    traffic = 236.41e6 if (world == 1 and B == 32768 and cfg["D"] == 512) else None
+    roofline = {"bound": "tensor", "kernel": "nce_bwd4_kernel", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tflops"], "traffic": traffic, "peak_source": pk["src"] + ", sustained bf16",
+                "executed_tflops": 2.0 * achieved,      # the kernel also recomputes the logits once per direction (8 B^2 D executed)
                 "launch_ms": bwd_avg_ms, "kernel_timing": kernel_timing, "share_of_step": bwd_avg_ms / ms_step,
                 "fwd_kernel_ms": sum(fwd_ms) / max(len(fwd_ms), 1),
                 "step_algorithmic_tflops": head_flops(B, cfg["D"], cfg["E_img"], cfg["E_txt"], cfg["C"]) / world / (ms_step / 1e3) / 1e12,

@@ -59,6 +59,37 @@ __host__ __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t ro
   return static_cast<float>(h >> 8) * (1.0f / 16777216.0f) >= p;
 }
 
+// 256-bit global loads / stores (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per thread access.  A row-per-thread
+// epilogue that stores 16 bytes at a time writes HALF sectors (32 rows x 16 B per warp instruction).  32-byte aligned.
+struct alignas(32) u32x8 { uint32_t v[8]; };
+__device__ __forceinline__ void st_global_v8(void* ptr, const u32x8& a) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]),
+               "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]) : "memory");
+}
+__device__ __forceinline__ u32x8 ld_global_v8(const void* ptr) {
+  u32x8 a;
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(a.v[0]), "=r"(a.v[1]), "=r"(a.v[2]), "=r"(a.v[3]),
+               "=r"(a.v[4]), "=r"(a.v[5]), "=r"(a.v[6]), "=r"(a.v[7]) : "l"(ptr));
+  return a;
+}
+__device__ __forceinline__ void st_global_f32x8(float* ptr, const float* f) {
+  u32x8 a;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a.v[i] = __float_as_uint(f[i]);
+  st_global_v8(ptr, a);
+}
+__device__ __forceinline__ void st_global_bf16x16(__nv_bfloat16* ptr, const float* f) {
+  u32x8 a;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a.v[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+  st_global_v8(ptr, a);
+}
+__device__ __forceinline__ void ld_global_bf16x16(const __nv_bfloat16* ptr, float* f) {
+  const u32x8 a = ld_global_v8(ptr);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { f[2 * i] = bf16_lo(a.v[i]); f[2 * i + 1] = bf16_hi(a.v[i]); }
+}
+
 // ------------------------------------------------------------------------------------------------
 // mbarrier (shared::cta) with a watchdog: a protocol bug traps instead of hanging the GPU box.
 // ------------------------------------------------------------------------------------------------

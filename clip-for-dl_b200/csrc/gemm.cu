@@ -31,8 +31,10 @@ int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, in
               cudaStream_t stream, float drop_p, unsigned int drop_seed) {
   B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   B200_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
-  B200_REQUIRE(out0 != nullptr && aligned16(out0), "gemm: out0 must be non-null and 16-byte aligned");
-  B200_REQUIRE(ld0 % 8 == 0, "gemm: ld0 must be a multiple of 8 elements");
+  // the epilogues use 256-bit global accesses: 32-byte aligned bases, leading dimensions a multiple of 16 elements
+  auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
+  B200_REQUIRE(out0 != nullptr && al32(out0) && al32(out1) && al32(resid) && al32(aux), "gemm: out0/out1/resid/aux must be 32-byte aligned");
+  B200_REQUIRE(ld0 % 16 == 0 && ld1 % 16 == 0 && ld_res % 16 == 0 && ld_aux % 16 == 0, "gemm: output/resid/aux leading dimensions must be multiples of 16 elements");
   const int BN = (N % 256 == 0) ? 256 : 128;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;

@@ -70,7 +70,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
   if constexpr (EPI == EPI_STORE_F32) {
     float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+    for (int i = 0; i < 32; i += 8) st_global_f32x8(o + i, f + i);
   } else if constexpr (EPI == EPI_ATOMIC_F32) {
     float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
 #pragma unroll
@@ -84,25 +84,21 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
       for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
     }
 #pragma unroll
-    for (int i = 0; i < 32; i += 8)
-      *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf16x2(f[i], f[i + 1]), pack_bf16x2(f[i + 2], f[i + 3]),
-                                                    pack_bf16x2(f[i + 4], f[i + 5]), pack_bf16x2(f[i + 6], f[i + 7]));
+    for (int i = 0; i < 32; i += 16) st_global_bf16x16(o + i, f + i);
   } else if constexpr (EPI == EPI_BIAS_GELU) {
     __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
     __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(p.out1) + static_cast<long long>(row) * p.ld1 + col;
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      *reinterpret_cast<uint4*>(o0 + i) = make_uint4(pack_bf16x2(f[i], f[i + 1]), pack_bf16x2(f[i + 2], f[i + 3]),
-                                                     pack_bf16x2(f[i + 4], f[i + 5]), pack_bf16x2(f[i + 6], f[i + 7]));
-      float g[8];
+    for (int i = 0; i < 32; i += 16) {
+      st_global_bf16x16(o0 + i, f + i);
+      float g[16];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
+      for (int t = 0; t < 16; ++t) {
         // GELU is applied to the bf16-rounded p so that backward (which only sees the stored p) is consistent
         const float pr = __bfloat162float(__float2bfloat16_rn(f[i + t]));
         g[t] = gelu_erf_f(pr);
       }
-      *reinterpret_cast<uint4*>(o1 + i) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
-                                                     pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+      st_global_bf16x16(o1 + i, g);
     }
   } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
     const __nv_bfloat16* rs = p.resid + static_cast<long long>(row) * p.ld_res + col;
@@ -114,30 +110,29 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
         f[i] = dropout_keep(p.drop_seed, static_cast<uint32_t>(row), static_cast<uint32_t>(col + i), static_cast<uint32_t>(p.N), p.drop_p) ? f[i] * sc : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      const uint4 r4 = *reinterpret_cast<const uint4*>(rs + i);
-      f[i] += bf16_lo(r4.x); f[i + 1] += bf16_hi(r4.x); f[i + 2] += bf16_lo(r4.y); f[i + 3] += bf16_hi(r4.y);
-      f[i + 4] += bf16_lo(r4.z); f[i + 5] += bf16_hi(r4.z); f[i + 6] += bf16_lo(r4.w); f[i + 7] += bf16_hi(r4.w);
+    for (int i = 0; i < 32; i += 16) {
+      float r[16];
+      ld_global_bf16x16(rs + i, r);
+#pragma unroll
+      for (int t = 0; t < 16; ++t) f[i + t] += r[t];
     }
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+    for (int i = 0; i < 32; i += 8) st_global_f32x8(o + i, f + i);
   } else if constexpr (EPI == EPI_GELU_BWD) {
     const __nv_bfloat16* rs = p.resid + static_cast<long long>(row) * p.ld_res + col;
     const float* ax = p.aux + static_cast<long long>(row) * p.ld_aux + col;
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      const uint4 r4 = *reinterpret_cast<const uint4*>(rs + i);
-      const float pv[8] = {bf16_lo(r4.x), bf16_hi(r4.x), bf16_lo(r4.y), bf16_hi(r4.y),
-                           bf16_lo(r4.z), bf16_hi(r4.z), bf16_lo(r4.w), bf16_hi(r4.w)};
-      const float4 a0 = *reinterpret_cast<const float4*>(ax + i);
-      const float4 a1 = *reinterpret_cast<const float4*>(ax + i + 4);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      float g[8];
+    for (int i = 0; i < 32; i += 16) {
+      float pv[16], g[16];
+      ld_global_bf16x16(rs + i, pv);
+      const u32x8 a0 = ld_global_v8(ax + i), a1 = ld_global_v8(ax + i + 8);
 #pragma unroll
-      for (int t = 0; t < 8; ++t) g[t] = f[i + t] * gelu_erf_grad_f(pv[t]) + av[t];
-      *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
-                                                    pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+      for (int t = 0; t < 8; ++t) {
+        g[t] = f[i + t] * gelu_erf_grad_f(pv[t]) + __uint_as_float(a0.v[t]);
+        g[8 + t] = f[i + 8 + t] * gelu_erf_grad_f(pv[8 + t]) + __uint_as_float(a1.v[t]);
+      }
+      st_global_bf16x16(o + i, g);
     }
   }
 }

@@ -638,10 +638,12 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constan
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(orow + c + i) =
-              make_float4(__uint_as_float(v[i]) * scale, __uint_as_float(v[i + 1]) * scale,
-                          __uint_as_float(v[i + 2]) * scale, __uint_as_float(v[i + 3]) * scale);
+        for (int i = 0; i < 32; i += 8) {           // 256-bit stores: full 32-byte sectors from a row-per-thread layout
+          float f8[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) f8[t] = __uint_as_float(v[i + t]) * scale;
+          st_global_f32x8(orow + c + i, f8);
+        }
       }
     }
   }
@@ -1019,10 +1021,12 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(orow + c + i) =
-              make_float4(__uint_as_float(v[i]) * scale, __uint_as_float(v[i + 1]) * scale,
-                          __uint_as_float(v[i + 2]) * scale, __uint_as_float(v[i + 3]) * scale);
+        for (int i = 0; i < 32; i += 8) {           // 256-bit stores: full 32-byte sectors from a row-per-thread layout
+          float f8[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) f8[t] = __uint_as_float(v[i + t]) * scale;
+          st_global_f32x8(orow + c + i, f8);
+        }
       }
     }
   }
@@ -1240,7 +1244,8 @@ extern "C" int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D,
                                     const float* grad_scale, float* d_i, int d_i_splits, float* d_t_partial, void* stream) {
   B200_REQUIRE(D == NCE_D, "infonce: D=%d unsupported (kernels are built for D=%d)", D, NCE_D);
   B200_REQUIRE(b_loc > 0 && b_glob > 0 && row0 >= 0 && row0 + b_loc <= b_glob, "infonce_bwd: bad row range");
-  B200_REQUIRE(aligned16(d_i) && aligned16(d_t_partial) && aligned16(rinvh) && aligned16(cinvh), "infonce_bwd: unaligned pointer");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(d_i) & 31u) == 0 && (reinterpret_cast<uintptr_t>(d_t_partial) & 31u) == 0 &&
+               aligned16(rinvh) && aligned16(cinvh), "infonce_bwd: d_i / d_t_partial must be 32-byte aligned, statistics 16-byte");
   CUtensorMap tx0, ty0, tx1, ty1;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tx0, i_hat, b_loc, D, D, 64, 128))) return rc;      // dir 0: X = I rows
