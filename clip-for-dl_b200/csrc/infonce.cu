@@ -1039,20 +1039,33 @@ nce_bwd4_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_consta
 // ================================================================================================
 // small reductions around the two passes
 // ================================================================================================
-// r[i] = sum_slots r_part ; c[j] = sum_rb c_part
-__global__ void nce_reduce_stats_kernel(const float* __restrict__ r_part, int r_slots, int nrows_pad, int nrows,
-                                        const float* __restrict__ c_part, int row_blocks, int ncols,
-                                        float* __restrict__ r, float* __restrict__ c) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nrows) {
-    float acc = 0.f;
-    for (int s = 0; s < r_slots; ++s) acc += r_part[static_cast<long long>(s) * nrows_pad + i];
-    r[i] = acc;
-  }
+// r[i] = sum_slots r_part ; c[j] = sum_rb c_part.  Block = 64 columns x 4 row-block groups (c_part is 33 MB at B = 32768:
+// one thread per column walking all 256 row blocks left the memory system idle); the 4 group sums are added in fixed order.
+__global__ void __launch_bounds__(256) nce_reduce_stats_kernel(const float* __restrict__ r_part, int r_slots, int nrows_pad, int nrows,
+                                                               const float* __restrict__ c_part, int row_blocks, int ncols,
+                                                               float* __restrict__ r, float* __restrict__ c) {
+  __shared__ float red[2][4][64];
+  const int x = threadIdx.x & 63, y = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + x;
+  float ra = 0.f, ca = 0.f;
+  if (i < nrows)
+    for (int s = y; s < r_slots; s += 4) ra += r_part[static_cast<long long>(s) * nrows_pad + i];
   if (i < ncols) {
-    float acc = 0.f;
-    for (int b = 0; b < row_blocks; ++b) acc += c_part[static_cast<long long>(b) * ncols + i];
-    c[i] = acc;
+    float c0 = 0.f, c1 = 0.f;                           // two independent chains (more loads in flight)
+    int b = y;
+    for (; b + 4 < row_blocks; b += 8) {
+      c0 += c_part[static_cast<long long>(b) * ncols + i];
+      c1 += c_part[static_cast<long long>(b + 4) * ncols + i];
+    }
+    if (b < row_blocks) c0 += c_part[static_cast<long long>(b) * ncols + i];
+    ca = c0 + c1;
+  }
+  red[0][y][x] = ra;
+  red[1][y][x] = ca;
+  __syncthreads();
+  if (y == 0) {
+    if (i < nrows) r[i] = (red[0][0][x] + red[0][1][x]) + (red[0][2][x] + red[0][3][x]);
+    if (i < ncols) c[i] = (red[1][0][x] + red[1][1][x]) + (red[1][2][x] + red[1][3][x]);
   }
 }
 
@@ -1199,7 +1212,7 @@ extern "C" int b200clip_infonce_fwd_stats(const void* i_hat, const void* t_hat, 
   kern<<<pl.grid, 128 + FWD_NWG * 128, smem, s>>>(tx, ty, p);
   B200_LAUNCH_CHECK();
   const int n = (int)std::max(b_loc, b_glob);
-  nce_reduce_stats_kernel<<<(n + 255) / 256, 256, 0, s>>>(r_part, pl.r_slots, pl.nrows_pad, (int)b_loc, c_part, pl.row_blocks,
+  nce_reduce_stats_kernel<<<(n + 63) / 64, 256, 0, s>>>(r_part, pl.r_slots, pl.nrows_pad, (int)b_loc, c_part, pl.row_blocks,
                                                         (int)b_glob, r, c_partial);
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -1219,7 +1232,7 @@ extern "C" int b200clip_infonce_loss(const void* i_hat, const void* t_hat, int D
   unsigned int* counter = reinterpret_cast<unsigned int*>(tail + 4096 * 3 * sizeof(double));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   B200_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
-  int grid = (int)std::min<long long>((b_glob + 255) / 256, 1024);
+  int grid = (int)std::min<long long>((b_glob + 63) / 64, 1024);      // 8 rows of the diagonal per warp at B = 32768
   nce_loss_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(i_hat), static_cast<const __nv_bfloat16*>(t_hat),
                                        (int)b_loc, (int)b_glob, (int)row0, 1.0f / temperature, r, c, (int)c_lo, (int)c_hi,
                                        rinvh, cinvh, partial, counter, sums, loss, 1.0f / temperature);

@@ -14,7 +14,7 @@ namespace b200 {
 int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, int K, long long lda, long long ldb,
               int epi, float alpha, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
               const void* resid, long long ld_res, const float* aux, long long ld_aux, int split_k, cudaStream_t stream,
-              float drop_p = 0.f, unsigned int drop_seed = 0u);
+              float drop_p = 0.f, unsigned int drop_seed = 0u, int aux_is_bf16 = 0);
 }
 using namespace b200;
 
@@ -73,8 +73,11 @@ extern "C" int b200clip_proj_bwd(const float* dy, const void* x_bf16, long long 
   const size_t cs_ws = b200clip_colsum_workspace_bytes(B, D);
   void* cs_work = carve(cs_ws);
 
-  int rc = b200clip_layernorm_bwd(dy, z_f32, mean, rstd, gamma, dz, dz_bf, dgamma, dbeta, db2, 0, B, D, drop_p, drop_seed, ln_work,
-                                  ln_ws, stream);
+  // Without dropout the fc branch and the residual branch see the same dz: the f32 copy (67 MB written + read at B = 32768)
+  // is skipped and the residual add in the GELU-backward epilogue reads the bf16 copy the GEMMs use anyway.
+  const bool need_f32_dz = drop_p > 0.f;
+  int rc = b200clip_layernorm_bwd(dy, z_f32, mean, rstd, gamma, need_f32_dz ? dz : nullptr, dz_bf, dgamma, dbeta, db2, 0, B, D, drop_p,
+                                  drop_seed, ln_work, ln_ws, stream);
   if (rc) return rc;
   // dW2[o][j] = sum_b dz[b][o] h[b][j]
   B200_CHECK_CUDA(cudaMemsetAsync(dw2, 0, static_cast<size_t>(D) * D * 4, s));
@@ -83,7 +86,7 @@ extern "C" int b200clip_proj_bwd(const float* dy, const void* x_bf16, long long 
     return rc;
   // dp = (dz W2) * gelu'(p) + dz
   if ((rc = gemm_bf16(dz_bf, w2_bf16, 0, 1, (int)B, D, D, D, D, EPI_GELU_BWD, 1.0f, dp_bf, D, nullptr, 0, nullptr, p_bf16, D,
-                      dz, D, 1, s)))
+                      need_f32_dz ? dz : reinterpret_cast<const float*>(dz_bf), D, 1, s, 0.f, 0u, need_f32_dz ? 0 : 1)))
     return rc;
   if ((rc = b200clip_colsum(dp_bf, 1, D, B, D, db1, 0, cs_work, cs_ws, stream))) return rc;
   // dW1[o][e] = sum_b dp[b][o] x[b][e]
