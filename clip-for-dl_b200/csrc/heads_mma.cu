@@ -247,10 +247,19 @@ __global__ void __launch_bounds__(HM_THREADS, 2) bce_heads_mma_kernel(const Head
   if (threadIdx.x == 0) is_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
   __syncthreads();
   if (is_last) {
+    // fold with 8 threads per value (blocks j, j+8, ... each), then add the 8 in fixed order: deterministic
     __threadfence();
+    __shared__ double fold[3 + HM_C][8];
+    if (threadIdx.x < (3 + HM_C) * 8) {
+      const int k = threadIdx.x >> 3, j = threadIdx.x & 7;
+      double t = 0.0;
+      for (unsigned b = j; b < gridDim.x; b += 8) t += p.partial[b * (3 + HM_C) + k];
+      fold[k][j] = t;
+    }
+    __syncthreads();
     if (threadIdx.x < 3 + HM_C) {
       double t = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) t += p.partial[b * (3 + HM_C) + threadIdx.x];
+      for (int j = 0; j < 8; ++j) t += fold[threadIdx.x][j];
       if (threadIdx.x < 3) p.sums[threadIdx.x] = t;
       else if (p.db) p.db[threadIdx.x - 3] = static_cast<float>(t);
     }

@@ -1126,14 +1126,26 @@ __global__ void __launch_bounds__(256) nce_loss_kernel(const __nv_bfloat16* __re
   __syncthreads();
   if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
+  if (is_last) {
+    // the last block folds the per-block partials with all 256 threads (one thread walking ~1000 dependent L2 loads cost
+    // more than the rest of the kernel); thread t takes blocks t, t+256, ..., then a fixed-order tree: deterministic
     __threadfence();
+    __shared__ double fold[3][256];
     double s[3] = {0.0, 0.0, 0.0};
-    for (unsigned b = 0; b < gridDim.x; ++b)
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += 256)
       for (int k = 0; k < 3; ++k) s[k] += partial[b * 3 + k];
-    sums[0] = s[0]; sums[1] = s[1]; sums[2] = s[2];
-    if (loss) *loss = static_cast<float>(static_cast<double>(shift_m) + (s[0] + s[1]) / (2.0 * b_glob) - s[2] / b_glob);
-    *counter = 0;
+    for (int k = 0; k < 3; ++k) fold[k][threadIdx.x] = s[k];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o)
+        for (int k = 0; k < 3; ++k) fold[k][threadIdx.x] += fold[k][threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      sums[0] = fold[0][0]; sums[1] = fold[1][0]; sums[2] = fold[2][0];
+      if (loss) *loss = static_cast<float>(static_cast<double>(shift_m) + (fold[0][0] + fold[1][0]) / (2.0 * b_glob) - fold[2][0] / b_glob);
+      *counter = 0;
+    }
   }
 }
 
