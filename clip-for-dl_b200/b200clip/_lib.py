@@ -37,7 +37,8 @@ SIGNATURES = {
     "b200clip_sum_f32": (i32, [vp, ll, vp, vp]),
     "b200clip_proj_fwd": (i32, [vp, ll, i32, i32, vp, vp, vp, vp, vp, vp, f32, f32, C.c_uint, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "b200clip_proj_bwd_workspace_bytes": (sz, [ll, i32, i32]),
-    "b200clip_proj_bwd": (i32, [vp, vp, ll, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, C.c_uint, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "b200clip_proj_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, ll, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, C.c_uint, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "b200clip_layernorm_l2_bwd": (i32, [vp, i32, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, ll, i32, f32, C.c_uint, vp, sz, vp]),
     "b200clip_infonce_workspace_bytes": (sz, [ll, ll]),
     "b200clip_infonce_fwd_stats": (i32, [vp, vp, i32, ll, ll, f32, vp, vp, vp, sz, vp]),
     "b200clip_infonce_loss": (i32, [vp, vp, i32, ll, ll, ll, f32, vp, vp, ll, ll, vp, vp, vp, vp, vp, sz, vp]),

@@ -109,19 +109,21 @@ def head_backward(tensors, meta, g):
     g = ops._f32c(g).reshape(())
     d_ihat, d_that = ops.infonce_backward(ihat, that_all, meta["tau_nce"], rinvh, cinvh, g, row0=row0, allow_splits=True)
     d_that_loc, work = dp.scatter_sum_rows(d_that, group, async_op=True)
-    # image side: through the L2 normalisation, plus g * (the two BCE heads' input gradient from the forward pass)
-    dy_img = ops.l2norm_bwd(d_ihat, y_img, inv_img, addend=d_bce, addend_scale=g)
+    # image side: the L2-normalisation backward (+ g * the two BCE heads' input gradient from the forward pass) runs inside
+    # the projection block's LayerNorm-backward kernel
     if db_raw is not None:
         dfw, dfb = ops.skinny_outer_mma(coef, ihat, db_raw, out_scale=g)
     else:
         dfw, dfb = ops.skinny_outer(coef, y_img, want_bias=True, out_scale=g)
-    gi = ops.proj_bwd(dy_img, xi, iw1b, iw2b, ig, saved_i, need_dxi, meta["in_dtypes"][0], drop_p=drop_p, drop_seed=drop_seed)
+    gi = ops.proj_bwd(None, xi, iw1b, iw2b, ig, saved_i, need_dxi, meta["in_dtypes"][0], drop_p=drop_p, drop_seed=drop_seed,
+                      l2=(d_ihat, ihat, inv_img, d_bce, g))
     # image-side parameter gradients travel while the text side is still computing (SUM, not mean: every loss term is
     # normalised by the GLOBAL batch)
     img_grads, img_work = dp.allreduce_flat([gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], dfw, dfb], group, async_op=True)
     dp.wait(work)
-    dy_txt = ops.l2norm_bwd(d_that_loc, y_txt, inv_txt)
-    gt = ops.proj_bwd(dy_txt, xt, tw1b, tw2b, tg, saved_t, need_dxt, meta["in_dtypes"][1], drop_p=drop_p, drop_seed=drop_seed + 1)
+    that_loc = that_all[row0:row0 + y_txt.shape[0]]                  # this rank's normalised text rows (bf16)
+    gt = ops.proj_bwd(None, xt, tw1b, tw2b, tg, saved_t, need_dxt, meta["in_dtypes"][1], drop_p=drop_p, drop_seed=drop_seed + 1,
+                      l2=(d_that_loc, that_loc, inv_txt, None, None))
     txt_grads = dp.allreduce_flat([gt[1], gt[2], gt[3], gt[4], gt[5], gt[6]], group)
     dp.wait(img_work)
     grads = [*img_grads[:6], *txt_grads, img_grads[6], img_grads[7]]

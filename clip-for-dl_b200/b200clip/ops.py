@@ -165,12 +165,22 @@ def proj_fwd(x_bf16, w1_bf16, b1, w2_bf16, b2, gamma, beta, want_yhat: bool, dro
 
 
 def proj_bwd(dy, x_bf16, w1_bf16, w2_bf16, gamma, saved, need_dx: bool, dx_dtype=torch.float32, drop_p: float = 0.0,
-             drop_seed: int = 0):
+             drop_seed: int = 0, l2=None):
+    """dy: gradient w.r.t. the block's output y.  Fused form: dy=None and l2=(dyhat, yhat_bf16, inv_norm, addend,
+    addend_scale) -- the gradient w.r.t. the L2-normalised output ([S,]B,D partial sums allowed), the normalised bf16
+    output, 1/||y|| and an optional f32 addend times a device scalar; the L2-norm backward runs inside LayerNorm's."""
     p, h, z, mean, rstd = saved
     B, E = x_bf16.shape
     D = w1_bf16.shape[0]
     dev = x_bf16.device
-    dy = _f32c(dy)
+    dyhat = yhat = inv = addend = ascale = None
+    parts = 1
+    if dy is not None:
+        dy = _f32c(dy)
+    else:
+        dyhat, yhat, inv, addend, ascale = l2
+        dyhat = _f32c(dyhat)
+        parts = dyhat.shape[0] if dyhat.dim() == 3 else 1
     dx_bf = need_dx and dx_dtype == torch.bfloat16
     dx = torch.empty((B, E), dtype=torch.bfloat16 if dx_bf else torch.float32, device=dev) if need_dx else None
     dw1 = torch.empty((D, E), dtype=torch.float32, device=dev)
@@ -178,7 +188,7 @@ def proj_bwd(dy, x_bf16, w1_bf16, w2_bf16, gamma, saved, need_dx: bool, dx_dtype
     db1, db2, dg, dbeta = (torch.empty((D,), dtype=torch.float32, device=dev) for _ in range(4))
     nb = load().b200clip_proj_bwd_workspace_bytes(B, E, D)
     ws = _ws(nb, dev)
-    check(load().b200clip_proj_bwd(ptr(dy), ptr(x_bf16), B, E, D, ptr(w1_bf16), ptr(w2_bf16), ptr(gamma), ptr(p), ptr(h), ptr(z),
+    check(load().b200clip_proj_bwd(ptr(dy), ptr(dyhat), parts, ptr(yhat), ptr(inv), ptr(addend), ptr(ascale), ptr(x_bf16), B, E, D, ptr(w1_bf16), ptr(w2_bf16), ptr(gamma), ptr(p), ptr(h), ptr(z),
                                    ptr(mean), ptr(rstd), float(drop_p), int(drop_seed) & 0xFFFFFFFF, ptr(None if dx_bf else dx), ptr(dx if dx_bf else None), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dg), ptr(dbeta),
                                    ptr(ws), ws.numel(), stream_ptr()), "proj_bwd")
     return dx, dw1, db1, dw2, db2, dg, dbeta

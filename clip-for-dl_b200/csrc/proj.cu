@@ -54,7 +54,11 @@ extern "C" size_t b200clip_proj_bwd_workspace_bytes(long long B, int E, int D) {
   return n + 1024;
 }
 
-extern "C" int b200clip_proj_bwd(const float* dy, const void* x_bf16, long long B, int E, int D, const void* w1_bf16,
+// dy == nullptr selects the fused entry: the gradient arrives w.r.t. the L2-normalised output (dyhat, possibly as partial
+// sums) and the L2-norm backward runs inside the LayerNorm-backward kernel (b200clip_layernorm_l2_bwd).
+extern "C" int b200clip_proj_bwd(const float* dy, const float* dyhat, int dyhat_partials, const void* yhat_bf16,
+                                 const float* inv_norm, const float* addend, const float* addend_scale,
+                                 const void* x_bf16, long long B, int E, int D, const void* w1_bf16,
                                  const void* w2_bf16, const float* gamma, const void* p_bf16, const void* h_bf16,
                                  const float* z_f32, const float* mean, const float* rstd, float drop_p,
                                  unsigned int drop_seed, float* dx_f32, void* dx_bf16,
@@ -76,8 +80,12 @@ extern "C" int b200clip_proj_bwd(const float* dy, const void* x_bf16, long long 
   // Without dropout the fc branch and the residual branch see the same dz: the f32 copy (67 MB written + read at B = 32768)
   // is skipped and the residual add in the GELU-backward epilogue reads the bf16 copy the GEMMs use anyway.
   const bool need_f32_dz = drop_p > 0.f;
-  int rc = b200clip_layernorm_bwd(dy, z_f32, mean, rstd, gamma, need_f32_dz ? dz : nullptr, dz_bf, dgamma, dbeta, db2, 0, B, D, drop_p,
-                                  drop_seed, ln_work, ln_ws, stream);
+  B200_REQUIRE(dy != nullptr || (dyhat != nullptr && yhat_bf16 != nullptr && inv_norm != nullptr), "proj_bwd: need dy, or dyhat + yhat + inv_norm");
+  int rc = dy ? b200clip_layernorm_bwd(dy, z_f32, mean, rstd, gamma, need_f32_dz ? dz : nullptr, dz_bf, dgamma, dbeta, db2, 0, B, D,
+                                       drop_p, drop_seed, ln_work, ln_ws, stream)
+              : b200clip_layernorm_l2_bwd(dyhat, dyhat_partials, yhat_bf16, inv_norm, 1e-12f, addend, addend_scale, z_f32, mean,
+                                          rstd, gamma, need_f32_dz ? dz : nullptr, dz_bf, dgamma, dbeta, db2, 0, B, D, drop_p,
+                                          drop_seed, ln_work, ln_ws, stream);
   if (rc) return rc;
   // dW2[o][j] = sum_b dz[b][o] h[b][j]
   B200_CHECK_CUDA(cudaMemsetAsync(dw2, 0, static_cast<size_t>(D) * D * 4, s));

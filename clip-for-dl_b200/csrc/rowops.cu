@@ -176,36 +176,91 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_fwd_kernel(const float*
 // LayerNorm backward: dz = rstd * (g*dy - mean(g*dy) - zhat * mean(g*dy*zhat)); per-block partial dgamma/dbeta and
 // column sums of dz (the bias gradient of the Linear feeding the residual sum), reduced by reduce_partials_kernel.
 // Outputs dz both as f32 (residual branch + bias grads) and bf16 (operand of the dW2 / dh GEMMs).
-template <int MAX_V>
-__global__ void __launch_bounds__(ROW_THREADS) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+// L2F = true fuses the backward of the L2 normalisation in front: dy is not read but formed per row from the gradient
+// w.r.t. the normalised features (given as `l2.parts` partial sums), the bf16 normalised features and 1/||y||:
+//   dy = inv (g - yhat (yhat . g)) [+ addend * *addend_scale]         (saves writing and re-reading dy: 134 MB at B = 32768)
+struct L2BwdArgs {
+  const float* dyhat; int parts;      // [parts][rows][D] partial sums of d loss / d yhat
+  const __nv_bfloat16* yhat;          // [rows][D]
+  const float* inv_norm;              // [rows]
+  float eps;                          // F.normalize eps: a clamped norm has zero gradient through the norm
+  const float* addend;                // [rows][D] f32 gradient that reaches y directly, or null
+  const float* addend_scale;          // device scalar or null
+};
+
+template <int MAX_V, bool L2F>
+__global__ void __launch_bounds__(ROW_THREADS, MAX_V <= 4 ? 3 : 2) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                                     const float* __restrict__ mean,
                                                                     const float* __restrict__ rstd,
                                                                     const float* __restrict__ gamma,
                                                                     float* __restrict__ dz_f32,
                                                                     __nv_bfloat16* __restrict__ dz_bf16,
                                                                     float* __restrict__ partial /*[grid][3][D]*/, int rows,
-                                                                    int D, float drop_p, unsigned int drop_seed) {
-  __shared__ float red[ROW_THREADS / 32][128];
+                                                                    int D, float drop_p, unsigned int drop_seed, const L2BwdArgs l2) {
+  // per-warp column accumulators (dgamma, dbeta, column sum of dz) live in shared memory, [warp][3][D]: each lane owns its
+  // columns, so the read-modify-write needs no synchronisation, and 48 registers per thread are free for loads in flight
+  extern __shared__ __align__(16) float ln_acc[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nv = D >> 7;
-  float4 dg[MAX_V], db[MAX_V], dzs[MAX_V];
-#pragma unroll
-  for (int i = 0; i < MAX_V; ++i) dg[i] = db[i] = dzs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float* my_acc = ln_acc + static_cast<size_t>(warp) * 3 * D;
+  for (int i = lane * 4; i < 3 * D; i += 128) *reinterpret_cast<float4*>(my_acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  auto acc_add = [&](int which, int i, float4 v) {
+    float4* q = reinterpret_cast<float4*>(my_acc + which * D + i * 128 + lane * 4);
+    float4 t = *q;
+    t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    *q = t;
+  };
   for (long long row = blockIdx.x * (ROW_THREADS / 32) + warp; row < rows;
        row += static_cast<long long>(gridDim.x) * (ROW_THREADS / 32)) {
     const float mu = mean[row], rs = rstd[row];
     float4 g[MAX_V], zh[MAX_V];
     float s1 = 0.f, s2 = 0.f;
+    float4 dyv[MAX_V];
+    if constexpr (L2F) {
+      const float inv = l2.inv_norm[row];
+      const bool clamped = inv >= 1.0f / l2.eps;
+      const long long pstride = static_cast<long long>(rows) * D;
+      const float ascale = (l2.addend && l2.addend_scale) ? *l2.addend_scale : 1.0f;
+      float4 yh[MAX_V];
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAX_V; ++i)
+        if (i < nv) {
+          float4 t = ld4(l2.dyhat + row * D + i * 128 + lane * 4);
+#pragma unroll 1
+          for (int sp = 1; sp < l2.parts; ++sp) {
+            const float4 u = ld4(l2.dyhat + sp * pstride + row * D + i * 128 + lane * 4);
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+          }
+          dyv[i] = t;
+          yh[i] = ld4(l2.yhat + row * D + i * 128 + lane * 4);
+          dot += t.x * yh[i].x + t.y * yh[i].y + t.z * yh[i].z + t.w * yh[i].w;
+        }
+      dot = clamped ? 0.f : warp_sum(dot);
+#pragma unroll
+      for (int i = 0; i < MAX_V; ++i)
+        if (i < nv) {
+          float4 o = make_float4(inv * (dyv[i].x - yh[i].x * dot), inv * (dyv[i].y - yh[i].y * dot),
+                                 inv * (dyv[i].z - yh[i].z * dot), inv * (dyv[i].w - yh[i].w * dot));
+          if (l2.addend) {
+            const float4 a = ld4(l2.addend + row * D + i * 128 + lane * 4);
+            o.x += a.x * ascale; o.y += a.y * ascale; o.z += a.z * ascale; o.w += a.w * ascale;
+          }
+          dyv[i] = o;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < MAX_V; ++i)
       if (i < nv) {
-        const float4 d = ld4(dy + row * D + i * 128 + lane * 4);
+        float4 d;
+        if constexpr (L2F) d = dyv[i]; else d = ld4(dy + row * D + i * 128 + lane * 4);
         const float4 zz = ld4(z + row * D + i * 128 + lane * 4);
         const float4 gm = ld4(gamma + i * 128 + lane * 4);
         zh[i] = make_float4((zz.x - mu) * rs, (zz.y - mu) * rs, (zz.z - mu) * rs, (zz.w - mu) * rs);
-        dg[i].x += d.x * zh[i].x; dg[i].y += d.y * zh[i].y; dg[i].z += d.z * zh[i].z; dg[i].w += d.w * zh[i].w;
-        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+        acc_add(0, i, make_float4(d.x * zh[i].x, d.y * zh[i].y, d.z * zh[i].z, d.w * zh[i].w));
+        acc_add(1, i, d);
         g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
         s1 += g[i].x + g[i].y + g[i].z + g[i].w;
         s2 += g[i].x * zh[i].x + g[i].y * zh[i].y + g[i].z * zh[i].z + g[i].w * zh[i].w;
@@ -227,28 +282,18 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_bwd_kernel(const float*
           m.z = dropout_keep(drop_seed, (uint32_t)row, c0 + 2, (uint32_t)D, drop_p) ? o.z * sc : 0.f;
           m.w = dropout_keep(drop_seed, (uint32_t)row, c0 + 3, (uint32_t)D, drop_p) ? o.w * sc : 0.f;
         }
-        dzs[i].x += m.x; dzs[i].y += m.y; dzs[i].z += m.z; dzs[i].w += m.w;
+        acc_add(2, i, m);
         if (dz_bf16) st4(dz_bf16 + row * D + i * 128 + lane * 4, m);
       }
   }
-  // block reduction of the per-warp dgamma/dbeta partials, one 128-column slab at a time
+  // block reduction of the per-warp partials (fixed warp order: deterministic)
+  __syncthreads();
   float* pg = partial + static_cast<long long>(blockIdx.x) * 3 * D;
-  for (int which = 0; which < 3; ++which) {
-    for (int i = 0; i < nv; ++i) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = threadIdx.x; c < 3 * D; c += ROW_THREADS) {
+    float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < MAX_V; ++k)
-        if (k == i) v = which == 0 ? dg[k] : (which == 1 ? db[k] : dzs[k]);
-      __syncthreads();
-      *reinterpret_cast<float4*>(&red[warp][lane * 4]) = v;
-      __syncthreads();
-      if (threadIdx.x < 128) {
-        float acc = 0.f;
-#pragma unroll
-        for (int w = 0; w < ROW_THREADS / 32; ++w) acc += red[w][threadIdx.x];
-        pg[which * D + i * 128 + threadIdx.x] = acc;
-      }
-    }
+    for (int w = 0; w < ROW_THREADS / 32; ++w) acc += ln_acc[static_cast<size_t>(w) * 3 * D + c];
+    pg[c] = acc;
   }
 }
 
@@ -330,7 +375,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16
 
 static inline int part_grid(long long rows) {      // kernels that emit per-block partials: keep the partial count small
   const long long want = (rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
-  const long long cap = static_cast<long long>(num_sms()) * 2;
+  const long long cap = static_cast<long long>(num_sms()) * 3;
   return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
 }
 static inline int row_grid(long long rows) {
@@ -405,8 +450,37 @@ extern "C" int b200clip_layernorm_bwd(const float* dy, const float* z, const flo
     return fail(B200_ERR_WORKSPACE, "layernorm_bwd: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
-  B200_DISPATCH_V(D, (layernorm_bwd_kernel<MAX_V><<<grid, ROW_THREADS, 0, s>>>(
-      dy, z, mean, rstd, gamma, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), partial, (int)rows, D, drop_p, drop_seed)));
+  const size_t ln_smem = static_cast<size_t>(ROW_THREADS / 32) * 3 * D * sizeof(float);
+  B200_DISPATCH_V(D, (cudaFuncSetAttribute(layernorm_bwd_kernel<MAX_V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ln_smem)));
+  B200_DISPATCH_V(D, (layernorm_bwd_kernel<MAX_V, false><<<grid, ROW_THREADS, ln_smem, s>>>(
+      dy, z, mean, rstd, gamma, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), partial, (int)rows, D, drop_p, drop_seed, L2BwdArgs{})));
+  B200_LAUNCH_CHECK();
+  reduce_partials_kernel<<<(3 * D + 31) / 32, 256, 0, s>>>(partial, 3LL * D, grid, 3 * D, D, dgamma, dbeta, dz_colsum,
+                                                         accumulate_params);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// LayerNorm backward with the backward of the L2 normalisation (F.normalize of the LayerNorm output) fused in front.
+extern "C" int b200clip_layernorm_l2_bwd(const float* dyhat, int dyhat_partials, const void* yhat_bf16, const float* inv_norm,
+                                         float l2_eps, const float* addend, const float* addend_scale, const float* z,
+                                         const float* mean, const float* rstd, const float* gamma, float* dz_f32,
+                                         void* dz_bf16, float* dgamma, float* dbeta, float* dz_colsum, int accumulate_params,
+                                         long long rows, int D, float drop_p, unsigned int drop_seed, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  B200_REQUIRE(rows > 0 && D > 0 && D % 128 == 0 && D <= MAX_D, "layernorm_l2_bwd: D=%d must be a multiple of 128, <= %d", D, MAX_D);
+  B200_REQUIRE(dyhat && yhat_bf16 && inv_norm && dyhat_partials >= 1 && dyhat_partials <= 8, "layernorm_l2_bwd: missing arguments");
+  B200_REQUIRE(aligned16(dyhat) && aligned16(yhat_bf16) && aligned16(addend) && aligned16(z), "layernorm_l2_bwd: pointers must be 16-byte aligned");
+  const int grid = part_grid(rows);
+  if (workspace_bytes < static_cast<size_t>(grid) * 3 * D * sizeof(float))
+    return fail(B200_ERR_WORKSPACE, "layernorm_l2_bwd: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  L2BwdArgs l2{dyhat, dyhat_partials, static_cast<const __nv_bfloat16*>(yhat_bf16), inv_norm, l2_eps, addend, addend_scale};
+  const size_t ln_smem = static_cast<size_t>(ROW_THREADS / 32) * 3 * D * sizeof(float);
+  B200_DISPATCH_V(D, (cudaFuncSetAttribute(layernorm_bwd_kernel<MAX_V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ln_smem)));
+  B200_DISPATCH_V(D, (layernorm_bwd_kernel<MAX_V, true><<<grid, ROW_THREADS, ln_smem, s>>>(
+      nullptr, z, mean, rstd, gamma, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), partial, (int)rows, D, drop_p, drop_seed, l2)));
   B200_LAUNCH_CHECK();
   reduce_partials_kernel<<<(3 * D + 31) / 32, 256, 0, s>>>(partial, 3LL * D, grid, 3 * D, D, dgamma, dbeta, dz_colsum,
                                                          accumulate_params);

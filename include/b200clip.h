@@ -59,6 +59,13 @@ int b200clip_layernorm_bwd(const float* dy, const float* z, const float* mean, c
                            float* dz_f32, void* dz_bf16, float* dgamma, float* dbeta, float* dz_colsum,
                            int accumulate_params, long long rows, int D, float drop_p, unsigned int drop_seed,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* LayerNorm backward with the backward of F.normalize(LayerNorm output) fused in front: dy = inv (g - yhat (yhat . g))
+ * [+ addend * *addend_scale], g = sum of dyhat_partials partial sums (rows*D elements apart), yhat bf16 [rows,D]. */
+int b200clip_layernorm_l2_bwd(const float* dyhat, int dyhat_partials, const void* yhat_bf16, const float* inv_norm,
+                              float l2_eps, const float* addend, const float* addend_scale, const float* z, const float* mean,
+                              const float* rstd, const float* gamma, float* dz_f32, void* dz_bf16, float* dgamma, float* dbeta,
+                              float* dz_colsum, int accumulate_params, long long rows, int D, float drop_p,
+                              unsigned int drop_seed, void* workspace, size_t workspace_bytes, void* stream);
 size_t b200clip_colsum_workspace_bytes(long long rows, int N);
 int b200clip_colsum(const void* a, int a_is_bf16, long long lda, long long rows, int N, float* out, int accumulate,
                     void* workspace, size_t workspace_bytes, void* stream);
@@ -76,7 +83,11 @@ int b200clip_proj_fwd(const void* x_bf16, long long B, int E, int D, const void*
                       float drop_p, unsigned int drop_seed, void* p_bf16, void* h_bf16, float* z_f32, float* y_f32, void* yhat_bf16, float* mean, float* rstd,
                       float* inv_norm, void* stream);
 size_t b200clip_proj_bwd_workspace_bytes(long long B, int E, int D);
-int b200clip_proj_bwd(const float* dy, const void* x_bf16, long long B, int E, int D, const void* w1_bf16,
+/* dy = gradient w.r.t. the LayerNorm output y.  Fused entry (dy == NULL): dyhat = gradient w.r.t. yhat = y/||y|| as
+ * dyhat_partials partial sums, plus yhat, 1/||y|| and an optional addend (gradient that reaches y directly, times a device
+ * scalar): the L2-norm backward then runs inside the LayerNorm-backward kernel. */
+int b200clip_proj_bwd(const float* dy, const float* dyhat, int dyhat_partials, const void* yhat_bf16, const float* inv_norm,
+                      const float* addend, const float* addend_scale, const void* x_bf16, long long B, int E, int D, const void* w1_bf16,
                       const void* w2_bf16, const float* gamma, const void* p_bf16, const void* h_bf16, const float* z_f32,
                       const float* mean, const float* rstd, float drop_p, unsigned int drop_seed, float* dx_f32, void* dx_bf16,
                       float* dw1, float* db1, float* dw2,
