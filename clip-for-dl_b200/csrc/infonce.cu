@@ -79,7 +79,12 @@ template <int BN, int STAGES, int NWG, bool XT>
 __global__ void __launch_bounds__(128 + NWG * 128, 1)
 nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
                const NceFwdParams p) {
-  static_assert(!XT || NWG * BN <= 256, "TMEM: 256 columns of X + NWG S buffers");
+  // S buffers in TMEM: one per epilogue warpgroup, or (XT) two buffers shared by pairs of warpgroups that split the columns
+  constexpr int NBUF = XT ? 2 : NWG;
+  constexpr int WPB = NWG / NBUF;                 // warpgroups per buffer
+  constexpr int CW = BN / WPB;                    // columns per warpgroup
+  static_assert(!XT || NBUF * BN <= 256, "TMEM: 256 columns of X + the S buffers");
+  static_assert(NWG % NBUF == 0 && CW % 32 == 0, "column split");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX = smem;
@@ -112,9 +117,9 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       mbar_init(&y_full[s], 1);
       mbar_init(&y_empty[s], 1);
     }
-    for (int b = 0; b < NWG; ++b) {
+    for (int b = 0; b < NBUF; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], 128);
+      mbar_init(&s_empty[b], 128 * WPB);
     }
     fence_mbar_init();
   }
@@ -227,7 +232,7 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         if (last_of_rb) tc_commit_a(xe);
       }
       __syncwarp();
-      if (++buf == NWG) { buf = 0; sph ^= 1; }
+      if (++buf == NBUF) { buf = 0; sph ^= 1; }
       if (++ct == CT) { ct = 0; ++rb; }
     }
   } else if (warp < 4) {
@@ -245,13 +250,15 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue warpgroups: tile n of this CTA -> warpgroup n % NWG =====================
+    // ===================== epilogue warpgroups: tile n of this CTA -> buffer n % NBUF; warpgroup w reads buffer w % NBUF,
+    // columns [(w / NBUF) * CW, +CW) =====================
     const int w = (warp - 4) >> 2;                 // epilogue warpgroup
     const int q = warp & 3;                        // TMEM lane quadrant
     const int tid_wg = threadIdx.x - 128 - w * 128;
+    const int bufw = w % NBUF, cpart = (w / NBUF) * CW;
     float* my_scratch = scratch + w * 4 * BN;
-    const uint32_t sf = smem_u32(s_full) + 8 * w, se = smem_u32(s_empty) + 8 * w;
-    const uint32_t t_addr = tmem_sbuf + (static_cast<uint32_t>(q * 32) << 16) + w * BN;
+    const uint32_t sf = smem_u32(s_full) + 8 * bufw, se = smem_u32(s_empty) + 8 * bufw;
+    const uint32_t t_addr = tmem_sbuf + (static_cast<uint32_t>(q * 32) << 16) + bufw * BN + cpart;
     float rsum = 0.f;
     int cur_rb = -1;
     uint32_t sph = 0;
@@ -262,7 +269,7 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       if (row < p.nrows) p.r_part[static_cast<long long>(slot) * p.nrows_pad + row] = rsum;
       rsum = 0.f;
     };
-    for (int t = t0 + w; t < t1; t += NWG) {
+    for (int t = t0 + bufw; t < t1; t += NBUF) {
       const int rb = t / CT, ct = t - rb * CT;
       if (rb != cur_rb) {
         if (cur_rb >= 0) flush_rsum(cur_rb);
@@ -274,11 +281,11 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       sph ^= 1;
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = 0; c < CW; c += 32) {
         uint32_t v[32];
         tmem_ld_x32(t_addr + c, v);
         tmem_ld_wait();
-        if (c + 32 == BN) {                         // last TMEM read of this tile: hand the buffer back
+        if (c + 32 == CW) {                         // last TMEM read of this tile: hand the buffer back
           tc_fence_before();
           mbar_arrive_a(se);
         }
@@ -291,7 +298,7 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           }
         } else {
           const bool row_ok = row < p.nrows;
-          const int col0 = ct * BN + c;
+          const int col0 = ct * BN + cpart + c;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float x = fast_exp2(fmaf(__uint_as_float(v[i]), p.k1, -p.k2));
@@ -299,14 +306,14 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             rsum += e[i];
           }
         }
-        my_scratch[q * BN + c + lane] = warp_colsum32(e, lane);
+        my_scratch[q * CW + c + lane] = warp_colsum32(e, lane);
       }
       named_bar_sync(1 + w, 128);
       {
-        const int col = ct * BN + tid_wg;
-        if (tid_wg < BN && col < p.ncols)
+        const int col = ct * BN + cpart + tid_wg;
+        if (tid_wg < CW && col < p.ncols)
           p.c_part[static_cast<long long>(rb) * p.ncols + col] =
-              (my_scratch[tid_wg] + my_scratch[BN + tid_wg]) + (my_scratch[2 * BN + tid_wg] + my_scratch[3 * BN + tid_wg]);
+              (my_scratch[tid_wg] + my_scratch[CW + tid_wg]) + (my_scratch[2 * CW + tid_wg] + my_scratch[3 * CW + tid_wg]);
       }
       named_bar_sync(1 + w, 128);
     }
@@ -1149,15 +1156,17 @@ __global__ void __launch_bounds__(256) nce_loss_kernel(const __nv_bfloat16* __re
   }
 }
 
-// Default: X in shared memory, 128 x 128 S tiles, 5-stage Y ring: 0.82 ms at B = 32768.  The pass streams all of Y from L2
-// once per row block (256 x 32 MB = 8.6 GB -> 10.5 TB/s at 0.82 ms): it sits on the L2 -> SM bandwidth, not on the MMA
-// rate.  The TMEM-resident-X variant (XT: BN = 64, 24 stages) moves the same bytes in 8 KB boxes and measured 1.42 ms.
+// Default: X in shared memory, 128 x 128 S tiles, 5-stage Y ring, 4 TMEM S buffers: 0.83 ms at B = 32768 (ncu: tensor pipe
+// 67 % active; the 8 KB of SS operands per 64-clk MMA plus the TMA writes of Y oversubscribe the 128 B/clk smem port).
+// The TMEM-resident-X variant (XT: TS MMAs, 12-stage ring, 2 S buffers shared by warpgroup pairs that split the columns)
+// measured 0.80 ms -- the port is no longer the limit, but with two S buffers the epilogue is -- so it stays optional
+// (-DB200CLIP_FWD_XT=1; same results, tests pass).  A 64-column XT variant measured 1.42 ms.
 #ifndef B200CLIP_FWD_XT
 #define B200CLIP_FWD_XT 0
 #endif
 constexpr bool FWD_XT = B200CLIP_FWD_XT != 0;
-constexpr int FWD_BN = FWD_XT ? 64 : 128;
-constexpr int FWD_STAGES = FWD_XT ? 24 : 5;
+constexpr int FWD_BN = 128;
+constexpr int FWD_STAGES = FWD_XT ? 12 : 5;   // 16 KB Y chunks
 constexpr int FWD_NWG = 4;                 // epilogue warpgroups = TMEM S buffers
 
 struct NceFwdPlan {

@@ -24,6 +24,13 @@ for _ in range(5):
 e1.record()
 torch.cuda.synchronize()
 print(f"bwd kernel: {e0.elapsed_time(e1) / 5:.3f} ms at B={B}")
+ops.KERNEL_EVENTS["infonce_fwd"] = []
+for _ in range(6):
+    loss = ops.infonce_forward(I, T, 0.07)[0]
+torch.cuda.synchronize()
+ts = [a.elapsed_time(b) for a, b in ops.KERNEL_EVENTS["infonce_fwd"]][1:]
+ops.KERNEL_EVENTS["infonce_fwd"] = None
+print(f"fwd stats kernels: {sum(ts) / len(ts):.3f} ms at B={B}  (loss {float(loss):.6f})")
 buf = torch.zeros(1024, dtype=torch.int64, device=dev)
 _lib.load().b200clip_debug_set_nce_prof(_lib.ptr(buf))
 ops.infonce_backward(I, T, 0.07, rinvh, cinvh, None)
