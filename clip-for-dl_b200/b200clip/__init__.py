@@ -4,7 +4,8 @@ Public names mirror cjycarrie/CLIP-FOR-DL (0426/train.py, disease_analysis.py): 
 contrastive_loss, multilabel_contrastive_loss, predict_multilabel, predict_zero_shot; plus ClassificationAdapter
 (the notebook's "C-Adapter"), the fused ClipHead and install() which patches a reference module in place.
 """
-from .modules import MODEL_CONFIG, ClassificationAdapter, ImageProjection, TextProjection  # noqa: F401
+from .modules import (MODEL_CONFIG, ClassificationAdapter, ImageProjection, MultiViewFusion,  # noqa: F401
+                      TextProjection)
 from .losses import contrastive_loss, fc_adapter_bce, multilabel_contrastive_loss, predict_multilabel  # noqa: F401
 from .zero_shot import (predict_zero_shot, unpack_mask, zero_shot_posneg, zero_shot_threshold,  # noqa: F401
                         zero_shot_topk)

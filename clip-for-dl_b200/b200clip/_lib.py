@@ -22,6 +22,10 @@ SIGNATURES = {
     "b200clip_bce_heads_mma_workspace_bytes": (sz, [ll]),
     "b200clip_bce_heads_mma_fwd": (i32, [vp, vp, ll, i32, vp, i32, vp, vp, i32, vp, i32, ll, f32, vp, f64, f64, vp, vp, vp, vp, vp, sz, vp]),
     "b200clip_skinny_outer_mma": (i32, [vp, vp, ll, i32, i32, vp, vp, vp, vp, vp, sz, vp]),
+    "b200clip_cast_f32_bf16_2d": (i32, [vp, ll, vp, ll, ll, i32, vp]),
+    "b200clip_fusion_fwd": (i32, [vp, ll, i32, vp, vp, vp, vp, f32, C.c_uint, vp, vp, vp]),
+    "b200clip_fusion_bwd_workspace_bytes": (sz, [ll, i32]),
+    "b200clip_fusion_bwd": (i32, [vp, vp, ll, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "b200clip_head_loss_finalize": (i32, [vp, vp, f32, f64, f64, f64, vp, vp, vp, vp]),
     "b200clip_debug_set_nce_prof": (None, [vp]),
     "b200clip_gemm_bf16": (i32, [vp, vp, i32, i32, i32, i32, i32, ll, ll, i32, f32, vp, ll, vp, ll, vp, vp, ll, vp, ll, i32, vp]),

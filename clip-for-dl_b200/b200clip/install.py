@@ -11,6 +11,7 @@ def install(*modules: types.ModuleType) -> None:
     table = {
         "ImageProjection": mods.ImageProjection,
         "TextProjection": mods.TextProjection,
+        "MultiViewFusion": mods.MultiViewFusion,
         "contrastive_loss": losses.contrastive_loss,
         "multilabel_contrastive_loss": losses.multilabel_contrastive_loss,
         "predict_multilabel": losses.predict_multilabel,

@@ -62,6 +62,24 @@ class TextProjection(_ProjectionBase):
         super().__init__(text_embedding_size, shared_embedding_size, dropout_rate)
 
 
+class MultiViewFusion(nn.Module):
+    """Drop-in for 0426/train.py:988-1000: cat[frontal, lateral] -> Linear(1024,512) -> ReLU -> Dropout(0.2) -> Linear(512,512).
+    Same no-argument constructor and state_dict keys (fusion.0.*, fusion.3.*); the extra keyword arguments only exist for
+    other widths.  Dropout follows nn.Dropout semantics (train mode only), fused into the first GEMM's epilogue."""
+
+    def __init__(self, shared_embedding_size: int = MODEL_CONFIG["shared_embedding_size"], dropout_rate: float = 0.2):
+        super().__init__()
+        d = shared_embedding_size
+        self.fusion = nn.Sequential(nn.Linear(2 * d, d), nn.ReLU(), nn.Dropout(dropout_rate), nn.Linear(d, d))
+
+    def forward(self, frontal_view: torch.Tensor, lateral_view: torch.Tensor) -> torch.Tensor:
+        p = float(self.fusion[2].p) if self.training else 0.0
+        seed = ops.new_dropout_seed() if p > 0 else 0
+        self.last_dropout_seed = seed
+        return ops.FusionFn.apply(frontal_view, lateral_view, self.fusion[0].weight, self.fusion[0].bias, self.fusion[3].weight,
+                                  self.fusion[3].bias, p, seed)
+
+
 class ClassificationAdapter(nn.Module):
     """The "C-Adapter": nn.Linear(512,16) + BCEWithLogitsLoss (NB02 c28:50-52).  `forward` = logits (as nn.Linear),
     `loss` = fused Linear+BCE, `predict` = sigmoid(logits) > threshold (NB02 c30:42-43).  state_dict keys weight/bias."""

@@ -223,6 +223,57 @@ class ProjectionFn(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------------------------
+# MultiViewFusion (0426/train.py:988-1000)
+# --------------------------------------------------------------------------------------------------------------
+class FusionFn(torch.autograd.Function):
+    """cat[frontal, lateral] -> Linear(2D, D) -> ReLU -> Dropout -> Linear(D, D); dropout (p, seed) is fused into the first
+    GEMM's epilogue, the saved activations carry the mask into the backward pass."""
+
+    @staticmethod
+    def forward(ctx, frontal, lateral, w0, b0, w3, b3, drop_p=0.0, drop_seed=0):
+        require_cuda(frontal, lateral, w0, w3)
+        lib = load()
+        f, l = _f32c(frontal), _f32c(lateral)
+        B, D = f.shape
+        if l.shape != f.shape or w0.shape != (D, 2 * D) or w3.shape != (D, D):
+            raise RuntimeError(f"b200clip.MultiViewFusion: expected two [B,{D}] views and weights [{D},{2 * D}], [{D},{D}]")
+        dev = f.device
+        x = torch.empty((B, 2 * D), dtype=torch.bfloat16, device=dev)            # the concatenation, written by two strided casts
+        check(lib.b200clip_cast_f32_bf16_2d(ptr(f), D, ptr(x), 2 * D, B, D, stream_ptr()), "cast_2d")
+        check(lib.b200clip_cast_f32_bf16_2d(ptr(l), D, C.c_void_p(x.data_ptr() + 2 * D), 2 * D, B, D, stream_ptr()), "cast_2d")
+        w0b, w3b = cast_bf16(w0), cast_bf16(w3)
+        h = torch.empty((B, D), dtype=torch.bfloat16, device=dev)
+        y = torch.empty((B, D), dtype=torch.float32, device=dev)
+        check(lib.b200clip_fusion_fwd(ptr(x), B, D, ptr(w0b), ptr(_f32c(b0)), ptr(w3b), ptr(_f32c(b3)), float(drop_p),
+                                      int(drop_seed) & 0xFFFFFFFF, ptr(h), ptr(y), stream_ptr()), "fusion_fwd")
+        ctx.save_for_backward(x, w0b, w3b, h)
+        ctx.drop_p = float(drop_p)
+        ctx.need_dx = frontal.requires_grad or lateral.requires_grad
+        ctx.dtypes = (frontal.dtype, lateral.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = load()
+        x, w0b, w3b, h = ctx.saved_tensors
+        B, D2 = x.shape
+        D = D2 // 2
+        dev = x.device
+        dy = _f32c(dy)
+        dx = torch.empty((B, D2), dtype=torch.float32, device=dev) if ctx.need_dx else None
+        dw0 = torch.empty((D, D2), dtype=torch.float32, device=dev)
+        dw3 = torch.empty((D, D), dtype=torch.float32, device=dev)
+        db0, db3 = torch.empty((D,), dtype=torch.float32, device=dev), torch.empty((D,), dtype=torch.float32, device=dev)
+        ws = _ws(lib.b200clip_fusion_bwd_workspace_bytes(B, D), dev)
+        check(lib.b200clip_fusion_bwd(ptr(dy), ptr(x), B, D, ptr(w0b), ptr(w3b), ptr(h), ctx.drop_p, ptr(dx), ptr(dw0), ptr(db0),
+                                      ptr(dw3), ptr(db3), ptr(ws), ws.numel(), stream_ptr()), "fusion_bwd")
+        df = dl = None
+        if dx is not None:
+            df, dl = dx[:, :D].to(ctx.dtypes[0]), dx[:, D:].to(ctx.dtypes[1])
+        return df, dl, dw0, db0, dw3, db3, None, None
+
+
+# --------------------------------------------------------------------------------------------------------------
 # a-N symmetric InfoNCE
 # --------------------------------------------------------------------------------------------------------------
 def infonce_forward(i_hat: torch.Tensor, t_hat: torch.Tensor, temperature: float, row0: int = 0, group=None,

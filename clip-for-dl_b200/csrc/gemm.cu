@@ -71,6 +71,7 @@ int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, in
   B200_GEMM_CASE(0, 1, EPI_STORE_F32)
   B200_GEMM_CASE(0, 1, EPI_STORE_BF16)
   B200_GEMM_CASE(0, 1, EPI_GELU_BWD)
+  B200_GEMM_CASE(0, 1, EPI_RELU_BWD)
   B200_GEMM_CASE(1, 1, EPI_STORE_F32)
   B200_GEMM_CASE(1, 1, EPI_ATOMIC_F32)
   B200_GEMM_CASE(1, 0, EPI_STORE_F32)

@@ -18,7 +18,8 @@ enum GemmEpilogue : int {
   EPI_BIAS_RESID_F32 = 3,   // out0 f32  = acc + bias + resid(bf16)
   EPI_ATOMIC_F32 = 4,       // atomicAdd(out0 f32, alpha * acc)       (split-K reduction)
   EPI_GELU_BWD = 5,         // out0 bf16 = acc * gelu'(resid=p bf16) + aux(f32 [M,N])   (dp = dh*gelu'(p) + dz)
-  EPI_RELU_BF16 = 6,        // out0 bf16 = relu(acc + bias)
+  EPI_RELU_BF16 = 6,        // out0 bf16 = dropout(relu(acc + bias))      (drop_p = 0: plain ReLU)
+  EPI_RELU_BWD = 7,         // out0 bf16 = alpha * acc where resid(bf16) > 0, else 0      (d relu / d dropout of EPI_RELU_BF16)
 };
 
 struct GemmParams {
@@ -102,6 +103,12 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
     if constexpr (EPI == EPI_RELU_BF16) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+      if (p.drop_p > 0.f) {                       // nn.Dropout after the ReLU (MultiViewFusion, 0426/train.py:994)
+        const float sc = 1.0f / (1.0f - p.drop_p);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          f[i] = dropout_keep(p.drop_seed, static_cast<uint32_t>(row), static_cast<uint32_t>(col + i), static_cast<uint32_t>(p.N), p.drop_p) ? f[i] * sc : 0.f;
+      }
     }
 #pragma unroll
     for (int i = 0; i < 32; i += 16) st_global_bf16x16(o + i, f + i);
@@ -138,6 +145,17 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
     }
 #pragma unroll
     for (int i = 0; i < 32; i += 8) st_global_f32x8(o + i, f + i);
+  } else if constexpr (EPI == EPI_RELU_BWD) {
+    const __nv_bfloat16* rs = p.resid + static_cast<long long>(row) * p.ld_res + col;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
+#pragma unroll
+    for (int i = 0; i < 32; i += 16) {
+      float hv[16], g[16];
+      ld_global_bf16x16(rs + i, hv);
+#pragma unroll
+      for (int t = 0; t < 16; ++t) g[t] = hv[t] > 0.f ? f[i + t] : 0.f;
+      st_global_bf16x16(o + i, g);
+    }
   } else if constexpr (EPI == EPI_GELU_BWD) {
     const __nv_bfloat16* rs = p.resid + static_cast<long long>(row) * p.ld_res + col;
     const float* ax = p.aux + static_cast<long long>(row) * p.ld_aux + col;

@@ -111,6 +111,69 @@ extern "C" int b200clip_proj_bwd(const float* dy, const float* dyhat, int dyhat_
   return B200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// MultiViewFusion (0426/train.py:988-1000): cat[frontal, lateral] -> Linear(2D, D) -> ReLU -> Dropout(0.2)
+// -> Linear(D, D).  x_bf16 = the concatenated views [B, 2D]; h = dropout(relu(x W0^T + b0)) is saved for backward (the masked,
+// rescaled activations: h > 0 <=> the unit was positive AND kept).
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int b200clip_fusion_fwd(const void* x_bf16, long long B, int D, const void* w0_bf16, const float* b0,
+                                   const void* w3_bf16, const float* b3, float drop_p, unsigned int drop_seed, void* h_bf16,
+                                   float* y_f32, void* stream) {
+  B200_REQUIRE(B > 0 && D > 0 && D % 128 == 0 && D <= 1024, "fusion_fwd: bad shape B=%lld D=%d", B, D);
+  B200_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "fusion_fwd: dropout probability must be in [0,1)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = gemm_bf16(x_bf16, w0_bf16, 0, 0, (int)B, D, 2 * D, 2 * D, 2 * D, EPI_RELU_BF16, 1.0f, h_bf16, D, nullptr, 0, b0, nullptr, 0,
+                     nullptr, 0, 1, s, drop_p, drop_seed);
+  if (rc) return rc;
+  return gemm_bf16(h_bf16, w3_bf16, 0, 0, (int)B, D, D, D, D, EPI_STORE_F32, 1.0f, y_f32, D, nullptr, 0, b3, nullptr, 0, nullptr, 0, 1, s);
+}
+
+extern "C" size_t b200clip_fusion_bwd_workspace_bytes(long long B, int D) {
+  size_t n = 0;
+  n += 2 * (((static_cast<size_t>(B) * D * 2) + 255) & ~size_t(255));      // dy bf16, dh bf16
+  n += 2 * ((b200clip_colsum_workspace_bytes(B, D) + 255) & ~size_t(255));
+  return n + 1024;
+}
+
+extern "C" int b200clip_fusion_bwd(const float* dy, const void* x_bf16, long long B, int D, const void* w0_bf16,
+                                   const void* w3_bf16, const void* h_bf16, float drop_p, float* dx_f32, float* dw0, float* db0,
+                                   float* dw3, float* db3, void* workspace, size_t workspace_bytes, void* stream) {
+  B200_REQUIRE(B > 0 && D > 0 && D % 128 == 0 && D <= 1024, "fusion_bwd: bad shape B=%lld D=%d", B, D);
+  if (workspace_bytes < b200clip_fusion_bwd_workspace_bytes(B, D)) return fail(B200_ERR_WORKSPACE, "fusion_bwd: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  auto carve = [&](size_t bytes) { uint8_t* p = ws; ws += (bytes + 255) & ~size_t(255); return p; };
+  void* dy_bf = carve(static_cast<size_t>(B) * D * 2);
+  void* dh_bf = carve(static_cast<size_t>(B) * D * 2);
+  const size_t cs_ws = b200clip_colsum_workspace_bytes(B, D);
+  void* cs0 = carve(cs_ws);
+  void* cs1 = carve(cs_ws);
+  int rc;
+  if ((rc = b200clip_cast_f32_bf16(dy, dy_bf, B * D, stream))) return rc;
+  if ((rc = b200clip_colsum(dy, 0, D, B, D, db3, 0, cs0, cs_ws, stream))) return rc;           // db3 = column sums of dy
+  // dW3[o][j] = sum_b dy[b][o] h[b][j]
+  B200_CHECK_CUDA(cudaMemsetAsync(dw3, 0, static_cast<size_t>(D) * D * 4, s));
+  if ((rc = gemm_bf16(dy_bf, h_bf16, 1, 1, D, D, (int)B, D, D, EPI_ATOMIC_F32, 1.0f, dw3, D, nullptr, 0, nullptr, nullptr, 0,
+                      nullptr, 0, split_for(D, D, (int)B), s)))
+    return rc;
+  // dh = (dy W3) / (1 - p) where the unit was positive and kept
+  if ((rc = gemm_bf16(dy_bf, w3_bf16, 0, 1, (int)B, D, D, D, D, EPI_RELU_BWD, 1.0f / (1.0f - drop_p), dh_bf, D, nullptr, 0, nullptr,
+                      h_bf16, D, nullptr, 0, 1, s)))
+    return rc;
+  if ((rc = b200clip_colsum(dh_bf, 1, D, B, D, db0, 0, cs1, cs_ws, stream))) return rc;
+  // dW0[o][e] = sum_b dh[b][o] x[b][e]
+  B200_CHECK_CUDA(cudaMemsetAsync(dw0, 0, static_cast<size_t>(D) * 2 * D * 4, s));
+  if ((rc = gemm_bf16(dh_bf, x_bf16, 1, 1, D, 2 * D, (int)B, D, 2 * D, EPI_ATOMIC_F32, 1.0f, dw0, 2 * D, nullptr, 0, nullptr, nullptr, 0,
+                      nullptr, 0, split_for(D, 2 * D, (int)B), s)))
+    return rc;
+  if (dx_f32) {
+    if ((rc = gemm_bf16(dh_bf, w0_bf16, 0, 1, (int)B, 2 * D, D, D, 2 * D, EPI_STORE_F32, 1.0f, dx_f32, 2 * D, nullptr, 0, nullptr,
+                        nullptr, 0, nullptr, 0, 1, s)))
+      return rc;
+  }
+  return B200_OK;
+}
+
 extern "C" int b200clip_version(void) { return 100; }
 extern "C" unsigned long long b200clip_launch_count(void) { return b200::launch_counter().load(); }
 extern "C" const char* b200clip_last_error_string(void) { return b200::last_error().c_str(); }

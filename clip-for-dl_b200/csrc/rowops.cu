@@ -523,6 +523,30 @@ extern "C" int b200clip_dropout_mask(float* out, long long rows, int cols, float
   return B200_OK;
 }
 
+// strided 2-D cast (concatenating two [rows, cols] f32 views side by side into one bf16 matrix = two calls)
+__global__ void __launch_bounds__(256) cast2d_f32_bf16_kernel(const float* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out,
+                                                              long long ld_out, long long rows, int cols4) {
+  const long long n = rows * cols4;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+    const long long r = i / cols4;
+    const int c = static_cast<int>(i - r * cols4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(in + r * ld_in + c);
+    *reinterpret_cast<uint2*>(out + r * ld_out + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+extern "C" int b200clip_cast_f32_bf16_2d(const float* in, long long ld_in, void* out, long long ld_out, long long rows, int cols,
+                                         void* stream) {
+  B200_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && aligned16(in) &&
+               (reinterpret_cast<uintptr_t>(out) & 7u) == 0, "cast_2d: cols / leading dimensions must be multiples of 4, pointers aligned");
+  if (rows == 0) return B200_OK;
+  const long long n = rows * (cols / 4);
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, static_cast<long long>(num_sms()) * 16));
+  cast2d_f32_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, ld_in, static_cast<__nv_bfloat16*>(out), ld_out, rows, cols / 4);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 extern "C" int b200clip_cast_f32_bf16(const float* in, void* out, long long n, void* stream) {
   B200_REQUIRE(n >= 0 && n % 4 == 0 && aligned16(in) && (reinterpret_cast<uintptr_t>(out) & 7u) == 0,
                "cast: n must be a multiple of 4 and pointers aligned");

@@ -93,6 +93,19 @@ int b200clip_proj_bwd(const float* dy, const float* dyhat, int dyhat_partials, c
                       float* dw1, float* db1, float* dw2,
                       float* db2, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- MultiViewFusion.forward(frontal_view, lateral_view) -- 0426/train.py:988-1000 --------------
+ * x_bf16 = cat[frontal, lateral] as one [B, 2D] bf16 matrix (b200clip_cast_f32_bf16_2d writes the two halves);
+ * h = dropout(relu(x W0^T + b0)) (bf16, saved for backward), y = h W3^T + b3.  Backward regenerates nothing: the saved h
+ * carries the mask (h > 0 <=> positive and kept). */
+int b200clip_cast_f32_bf16_2d(const float* in, long long ld_in, void* out_bf16, long long ld_out, long long rows, int cols,
+                              void* stream);
+int b200clip_fusion_fwd(const void* x_bf16, long long B, int D, const void* w0_bf16, const float* b0, const void* w3_bf16,
+                        const float* b3, float drop_p, unsigned int drop_seed, void* h_bf16, float* y_f32, void* stream);
+size_t b200clip_fusion_bwd_workspace_bytes(long long B, int D);
+int b200clip_fusion_bwd(const float* dy, const void* x_bf16, long long B, int D, const void* w0_bf16, const void* w3_bf16,
+                        const void* h_bf16, float drop_p, float* dx_f32, float* dw0, float* db0, float* dw3, float* db3,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a-N: contrastive_loss(image_features, text_features, temperature) -- 0426/train.py:154-176 ----------------
  * Inputs are L2-normalised bf16 rows.  Data-parallel form: i_hat = this rank's rows [b_loc, D] (global rows
  * row0 .. row0+b_loc), t_hat = all b_glob rows.  fwd_stats -> r (row sums, complete) and c_partial (this rank's

@@ -77,6 +77,49 @@ def test_layernorm_fwd_bwd(rows, D):
     assert rel_l2(dzs, zr.grad.sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("rows,D,parts,with_addend", [(1000, 512, 1, False), (777, 512, 3, True), (130, 1024, 2, True)])
+def test_layernorm_backward_with_fused_l2norm_backward(rows, D, parts, with_addend):
+    """b200clip_layernorm_l2_bwd == autograd through  normalize(LayerNorm(z))  (+ a gradient that reaches y directly),
+    with the normalised features given in bf16 and d/dyhat given as partial sums."""
+    from b200clip import _lib
+    lib = _lib.load()
+    d = dev()
+    z = (synth.randn(3, rows, D) * 2 + 0.5).to(d)
+    gamma = (1 + 0.1 * synth.randn(4, D)).to(d)
+    beta = (0.1 * synth.randn(5, D)).to(d)
+    zr, gr, br = z.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.layer_norm(zr, (D,), gr, br, 1e-5)
+    nrm = y.norm(dim=-1, keepdim=True)
+    yhat_b = (y / nrm).detach().to(torch.bfloat16)
+    # reference: the kernel sees yhat only in bf16, so differentiate  y -> y / ||y||  at the bf16-rounded direction
+    g = synth.randn(6, rows, D).to(d)
+    add = synth.randn(7, rows, D).to(d) if with_addend else None
+    sc = torch.full((), 0.75, device=d)
+    yh = yhat_b.float()
+    dy = (g - yh * (yh * g).sum(-1, keepdim=True)) / nrm.detach()
+    if add is not None:
+        dy = dy + 0.75 * add
+    y.backward(dy)
+    gp = torch.stack([g / parts] * parts).contiguous()
+    mean, rstd = z.mean(-1), 1.0 / torch.sqrt(z.var(-1, unbiased=False) + 1e-5)
+    inv = (1.0 / nrm.detach().squeeze(-1)).contiguous()
+    dz = torch.empty_like(z)
+    dzb = torch.empty(rows, D, dtype=torch.bfloat16, device=d)
+    dg, db, dzs = torch.empty(D, device=d), torch.empty(D, device=d), torch.empty(D, device=d)
+    nb = lib.b200clip_layernorm_bwd_workspace_bytes(rows, D)
+    ws = torch.empty(nb, dtype=torch.uint8, device=d)
+    _lib.check(lib.b200clip_layernorm_l2_bwd(_lib.ptr(gp), parts, _lib.ptr(yhat_b), _lib.ptr(inv), 1e-12, _lib.ptr(add),
+                                             _lib.ptr(sc if add is not None else None), _lib.ptr(z), _lib.ptr(mean.contiguous()),
+                                             _lib.ptr(rstd.contiguous()), _lib.ptr(gamma), _lib.ptr(dz), _lib.ptr(dzb), _lib.ptr(dg),
+                                             _lib.ptr(db), _lib.ptr(dzs), 0, rows, D, 0.0, 0, _lib.ptr(ws), nb, _lib.stream_ptr()),
+               "ln_l2_bwd")
+    assert rel_l2(dz, zr.grad) < 2e-5
+    assert rel_l2(dzb.float(), zr.grad) < 4e-3
+    assert rel_l2(dg, gr.grad) < 2e-5
+    assert rel_l2(db, br.grad) < 2e-5
+    assert rel_l2(dzs, zr.grad.sum(0)) < 1e-4
+
+
 @pytest.mark.parametrize("rows,N,bf16", [(1000, 512, False), (257, 768, True), (5, 128, False), (40000, 512, True), (300, 2048, False)])
 def test_colsum(rows, N, bf16):
     from b200clip import _lib

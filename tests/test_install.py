@@ -13,12 +13,13 @@ import b200clip
 
 def test_install_patches_module_globals():
     fake = types.ModuleType("train")
-    for n in ("ImageProjection", "TextProjection", "contrastive_loss", "multilabel_contrastive_loss", "predict_multilabel"):
+    for n in ("ImageProjection", "TextProjection", "MultiViewFusion", "contrastive_loss", "multilabel_contrastive_loss",
+              "predict_multilabel"):
         setattr(fake, n, object())
     fake.unrelated = 1
     b200clip.install(fake)
     assert fake.ImageProjection is b200clip.ImageProjection and fake.TextProjection is b200clip.TextProjection
-    assert fake.contrastive_loss is b200clip.contrastive_loss
+    assert fake.contrastive_loss is b200clip.contrastive_loss and fake.MultiViewFusion is b200clip.MultiViewFusion
     assert fake.multilabel_contrastive_loss is b200clip.multilabel_contrastive_loss
     assert fake.predict_multilabel is b200clip.predict_multilabel
     assert fake.unrelated == 1 and not hasattr(fake, "predict_zero_shot")
@@ -49,3 +50,8 @@ def test_reference_checkpoint_keys_load(tmp_path):
     mine_img.load_state_dict(ref_img.state_dict())                                          # strict load of a reference checkpoint
     mine_txt.load_state_dict(ref_txt.state_dict())
     assert torch.equal(mine_img.fc.weight, ref_img.fc.weight)
+    # MultiViewFusion: same no-argument constructor, same keys, strict load (0426/train.py:988-1000)
+    assert ref.MultiViewFusion is b200clip.MultiViewFusion
+    mine_fus = ref.MultiViewFusion()
+    assert set(mine_fus.state_dict()) == {"fusion.0.weight", "fusion.0.bias", "fusion.3.weight", "fusion.3.bias"}
+    assert tuple(mine_fus.state_dict()["fusion.0.weight"].shape) == (512, 1024)
