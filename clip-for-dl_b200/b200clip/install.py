@@ -14,6 +14,7 @@ def install(*modules: types.ModuleType) -> None:
         "MultiViewFusion": mods.MultiViewFusion,
         "contrastive_loss": losses.contrastive_loss,
         "multilabel_contrastive_loss": losses.multilabel_contrastive_loss,
+        "multilabel_asymmetric_loss": losses.multilabel_asymmetric_loss,
         "predict_multilabel": losses.predict_multilabel,
         "predict_zero_shot": zero_shot.predict_zero_shot,
     }

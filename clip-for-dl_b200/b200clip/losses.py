@@ -37,6 +37,13 @@ def multilabel_contrastive_loss(image_features, text_features, labels, temperatu
 multilabel_contrastive_loss.last_status = None
 
 
+def multilabel_asymmetric_loss(logits, targets, gamma_pos=0, gamma_neg=4, clip=0.05, eps=1e-8, reduction='mean'):
+    """multimodal_attention/train.py:233-268 (ASL): logits [B, C] (before the sigmoid), targets [B, C] in {0, 1}.
+    reduction 'mean' | 'sum' | anything else returns the elementwise loss, like the reference."""
+    red = reduction if reduction in ("mean", "sum") else "none"
+    return ops.AslFn.apply(logits, targets, float(gamma_pos), float(gamma_neg), float(clip) if clip else 0.0, float(eps), red)
+
+
 def fc_adapter_bce(x, weight, bias, labels):
     """BCEWithLogitsLoss()(F.linear(x, weight, bias), labels) -- NB02 c29:23-25."""
     return ops.FcBceFn.apply(x, weight, bias, labels)

@@ -589,6 +589,50 @@ def skinny_outer_mma(coefn, yhat_bf16, db_raw, out_scale=None):
     return out_w, out_b
 
 
+# --------------------------------------------------------------------------------------------------------------
+# multilabel_asymmetric_loss (ASL), multimodal_attention/train.py:233-268
+# --------------------------------------------------------------------------------------------------------------
+_ASL_RED = {"none": 0, "mean": 1, "sum": 2}
+
+
+def _asl_call(logits, targets, gamma_pos, gamma_neg, clip, eps, red, grad_scale=None, grad_elem=None, want_elem=False, want_grad=False):
+    lib = load()
+    z, t = _f32c(logits), _f32c(targets)
+    dev = z.device
+    n = z.numel()
+    loss_elem = torch.empty_like(z) if want_elem else None
+    d_logits = torch.empty_like(z) if want_grad else None
+    s = torch.empty((1,), dtype=torch.float64, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    ws = _ws(lib.b200clip_asl_workspace_bytes(), dev)
+    check(lib.b200clip_asl_fwd_bwd(ptr(z), ptr(t), n, float(gamma_pos), float(gamma_neg), float(clip or 0.0), float(eps), red,
+                                   ptr(grad_scale), ptr(grad_elem), ptr(loss_elem), ptr(d_logits), ptr(s), ptr(loss), ptr(ws),
+                                   ws.numel(), stream_ptr()), "asl_fwd_bwd")
+    return loss, loss_elem, d_logits
+
+
+class AslFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, gamma_pos, gamma_neg, clip, eps, reduction):
+        require_cuda(logits, targets)
+        if logits.shape != targets.shape:
+            raise RuntimeError("multilabel_asymmetric_loss: logits and targets must have the same shape")
+        red = _ASL_RED[reduction]
+        loss, loss_elem, _ = _asl_call(logits, targets, gamma_pos, gamma_neg, clip, eps, red, want_elem=(red == 0))
+        ctx.save_for_backward(logits, targets)
+        ctx.cfg = (gamma_pos, gamma_neg, clip, eps, red)
+        return loss_elem.reshape(logits.shape) if red == 0 else loss
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, targets = ctx.saved_tensors
+        gamma_pos, gamma_neg, clip, eps, red = ctx.cfg
+        g = _f32c(g)
+        _, _, d = _asl_call(logits, targets, gamma_pos, gamma_neg, clip, eps, red, grad_scale=None if red == 0 else g.reshape(()),
+                            grad_elem=g if red == 0 else None, want_grad=True)
+        return d.reshape(logits.shape).to(logits.dtype), None, None, None, None, None, None
+
+
 def head_loss_finalize(sums6, label_sum, tau_nce, b_glob, total_text, total_fc):
     """loss, parts[3] (InfoNCE, text BCE, FC BCE), status from the six numerators (already summed over ranks)."""
     dev = sums6.device

@@ -458,6 +458,75 @@ __global__ void head_loss_finalize_kernel(const double* __restrict__ sums6, cons
   *loss = static_cast<float>(l_nce) + l_text + l_fc;
 }
 
+// multilabel_asymmetric_loss (ASL), multimodal_attention/train.py:233-268 -- elementwise on the [B, C] logits, fused with its
+// derivative.  Line references are to that file.  torch.clamp passes the gradient where the input is inside the closed range.
+struct AslParams {
+  const float* logits; const float* targets; long long n;
+  float gamma_pos, gamma_neg, clip, eps;
+  float inv_count;                    // 1/n for 'mean', 1 otherwise (scales the gradient)
+  const float* grad_scale;            // upstream scalar gradient (mean / sum) or null
+  const float* grad_elem;             // upstream elementwise gradient (reduction 'none') or null
+  float* loss_elem;                   // [n] or null
+  float* d_logits;                    // [n] or null
+  double* partial; unsigned int* counter; double* sum; float* loss;
+};
+
+__global__ void __launch_bounds__(256) asl_kernel(const AslParams p) {
+  __shared__ double red[8];
+  __shared__ bool is_last;
+  const float gs = p.grad_scale ? *p.grad_scale : 1.0f;
+  double acc = 0.0;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < p.n; i += static_cast<long long>(gridDim.x) * 256) {
+    const float z = p.logits[i], t = p.targets[i];
+    const float pr = 1.0f / (1.0f + expf(-z));                        // :247
+    const float dpr = pr * (1.0f - pr);
+    float qc = 1.0f - pr;                                             // :249
+    float dqc = -dpr;
+    if (p.clip > 0.f) {                                               // :251-252
+      qc += p.clip;
+      if (qc > 1.0f) { qc = 1.0f; dqc = 0.f; }
+    }
+    const float a = fmaxf(pr, p.eps), b = fmaxf(qc, p.eps);           // :254-255 clamp(min=eps)
+    const float da = pr >= p.eps ? dpr : 0.f, db = qc >= p.eps ? dqc : 0.f;
+    float pos = t * logf(a), dpos = t * da / a;
+    float neg = (1.0f - t) * logf(b), dneg = (1.0f - t) * db / b;
+    if (p.gamma_pos > 0.f) {                                          // :257-258
+      const float w = powf(1.0f - pr, p.gamma_pos), dw = -p.gamma_pos * powf(1.0f - pr, p.gamma_pos - 1.0f) * dpr;
+      dpos = dpos * w + pos * dw;
+      pos *= w;
+    }
+    if (p.gamma_neg > 0.f) {                                          // :259-260 (focusing term uses the UNCLIPPED probability)
+      const float w = powf(pr, p.gamma_neg), dw = p.gamma_neg * powf(pr, p.gamma_neg - 1.0f) * dpr;
+      dneg = dneg * w + neg * dw;
+      neg *= w;
+    }
+    const float l = -(pos + neg);                                     // :262
+    acc += static_cast<double>(l);
+    if (p.loss_elem) p.loss_elem[i] = l;
+    if (p.d_logits) p.d_logits[i] = -(dpos + dneg) * p.inv_count * gs * (p.grad_elem ? p.grad_elem[i] : 1.0f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    p.partial[blockIdx.x] = s;
+    __threadfence();
+    is_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    double s = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += p.partial[b];      // fixed order: deterministic
+    *p.sum = s;
+    if (p.loss) *p.loss = static_cast<float>(s * static_cast<double>(p.inv_count));
+    *p.counter = 0;
+  }
+}
+
 static int sc_grid(long long rows) {
   const long long per_block = (SC_THREADS / 32) * 4;
   const long long want = (rows + per_block - 1) / per_block;
@@ -499,6 +568,34 @@ extern "C" size_t b200clip_smallc_workspace_bytes(long long rows, int C, int D) 
   const int rpb = SO_ROWS;
   const size_t outer = static_cast<size_t>((rows + rpb - 1) / rpb) * (static_cast<size_t>(C) * D + C) * sizeof(float);
   return loss_part + outer + 256;
+}
+
+constexpr int ASL_MAX_GRID = 256;
+extern "C" size_t b200clip_asl_workspace_bytes(void) { return ASL_MAX_GRID * sizeof(double) + 256; }
+
+// reduction: 0 'none' (loss_elem required), 1 'mean', 2 'sum'.  loss[0] = mean or sum; d_logits (optional) = d loss / d logits
+// times the upstream gradient (grad_scale scalar for mean/sum, grad_elem [n] for 'none').
+extern "C" int b200clip_asl_fwd_bwd(const float* logits, const float* targets, long long n, float gamma_pos, float gamma_neg,
+                                    float clip, float eps, int reduction, const float* grad_scale, const float* grad_elem,
+                                    float* loss_elem, float* d_logits, double* sum, float* loss, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  B200_REQUIRE(n > 0 && logits && targets && sum, "asl: missing arguments");
+  B200_REQUIRE(reduction >= 0 && reduction <= 2 && (reduction != 0 || loss_elem || d_logits), "asl: bad reduction mode");
+  B200_REQUIRE(gamma_pos >= 0.f && gamma_neg >= 0.f && eps > 0.f, "asl: gamma_pos, gamma_neg >= 0 and eps > 0 expected");
+  if (workspace_bytes < b200clip_asl_workspace_bytes()) return fail(B200_ERR_WORKSPACE, "asl: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  AslParams p{};
+  p.logits = logits; p.targets = targets; p.n = n; p.gamma_pos = gamma_pos; p.gamma_neg = gamma_neg; p.clip = clip; p.eps = eps;
+  p.inv_count = reduction == 1 ? 1.0f / static_cast<float>(n) : 1.0f;
+  p.grad_scale = grad_scale; p.grad_elem = grad_elem; p.loss_elem = loss_elem; p.d_logits = d_logits;
+  p.partial = static_cast<double*>(workspace);
+  p.counter = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(workspace) + ASL_MAX_GRID * sizeof(double));
+  p.sum = sum; p.loss = loss;
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, ASL_MAX_GRID));
+  B200_CHECK_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), s));
+  asl_kernel<<<grid, 256, 0, s>>>(p);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
 }
 
 extern "C" int b200clip_head_loss_finalize(const double* sums6, const float* label_sum, float temperature_nce, double b_glob,

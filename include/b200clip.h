@@ -164,6 +164,13 @@ int b200clip_skinny_outer_mma(const void* coefn_bf16, const void* yhat_bf16, lon
                               const float* out_scale, float* out_w, const float* db_raw, float* db_out, void* workspace,
                               size_t workspace_bytes, void* stream);
 
+/* ---- multilabel_asymmetric_loss(logits, targets, gamma_pos=0, gamma_neg=4, clip=0.05, eps=1e-8, reduction='mean')
+ * -- multimodal_attention/train.py:233-268.  reduction: 0 none, 1 mean, 2 sum. */
+size_t b200clip_asl_workspace_bytes(void);
+int b200clip_asl_fwd_bwd(const float* logits, const float* targets, long long n, float gamma_pos, float gamma_neg, float clip,
+                         float eps, int reduction, const float* grad_scale, const float* grad_elem, float* loss_elem,
+                         float* d_logits, double* sum, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+
 /* loss of the fused head step from its six numerators (summed over ranks): sums6 = {sum_i log r_i, sum_j log c_j,
  * sum_i S_ii, text-BCE pos numerator, text-BCE neg numerator, FC-BCE sum}; parts3 = {InfoNCE, text BCE, FC BCE}. */
 int b200clip_head_loss_finalize(const double* sums6, const float* label_sum, float temperature_nce, double b_glob,

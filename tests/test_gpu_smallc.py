@@ -125,3 +125,35 @@ def test_bce_heads_tensor_core_path_vs_oracle(B, tau):
     assert rel_l2(d_y, y_eff.grad) < 2e-2
     assert rel_l2(dW, 2.0 * Wr.grad) < 2e-2
     assert rel_l2(dB, 2.0 * br.grad) < 2e-2
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(gamma_pos=1, gamma_neg=2, clip=0.1, reduction="sum"), dict(clip=0.0, gamma_neg=0),
+                                dict(reduction="none", gamma_pos=2)])
+def test_multilabel_asymmetric_loss(kw, golden):
+    """ASL (multimodal_attention/train.py:233-268) vs the oracle's autograd and the golden values minted from the reference."""
+    import b200clip
+    lg = synth.randn(71, 40, 16) * 3
+    y = synth.labels(72, 40, 16, density=0.2)
+    lr = lg.clone().requires_grad_(True)
+    ref = R.multilabel_asymmetric_loss(lr, y, **kw)
+    w = synth.randn(73, 40, 16)
+    (ref * w).sum().backward() if ref.dim() else (3.0 * ref).backward()
+    lgpu = lg.to(dev()).requires_grad_(True)
+    out = b200clip.multilabel_asymmetric_loss(lgpu, y.to(dev()), **kw)
+    (out * w.to(dev())).sum().backward() if out.dim() else (3.0 * out).backward()
+    assert rel_l2(out, ref) < 1e-5
+    assert rel_l2(lgpu.grad, lr.grad) < 1e-4
+    if not kw:
+        np.testing.assert_allclose(out.item(), golden["asl_mean"], rtol=1e-5)
+    if kw.get("reduction") == "sum":
+        np.testing.assert_allclose(out.item(), golden["asl_sum_g1"], rtol=1e-5)
+    # large batch, extreme logits: clamps active on both sides
+    big = (synth.randn(74, 5000, 16) * 12).to(dev()).requires_grad_(True)
+    yb = synth.labels(75, 5000, 16, density=0.3)
+    br = big.detach().cpu().requires_grad_(True)
+    rb = R.multilabel_asymmetric_loss(br, yb, **{k: v for k, v in kw.items() if k != "reduction"})
+    rb.backward()
+    ob = b200clip.multilabel_asymmetric_loss(big, yb.to(dev()), **{k: v for k, v in kw.items() if k != "reduction"})
+    ob.backward()
+    assert abs(ob.item() - rb.item()) <= 1e-5 * abs(rb.item())
+    assert rel_l2(big.grad, br.grad) < 1e-4
