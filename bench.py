@@ -281,13 +281,13 @@ def run_head(args, cfg):
 
     def e2e_step(i):
         slot = i & 1
-        prefetch(slot ^ 1)                                  # next step's batch, overlapped with this step's compute
         cur = torch.cuda.current_stream()
         cur.wait_event(copied[slot])
         d_img, d_txt, d_lab = bufs[slot]
         l = step(d_img, d_txt, d_lab)                      # graph mode: D2D into the static inputs, then one replay
         consumed[slot].record(cur)
         host_loss.copy_(l.detach(), non_blocking=True)
+        prefetch(slot ^ 1)                                  # next step's batch: enqueued while this step computes
         cur.synchronize()                                   # the user reads the loss every step
         return float(host_loss)
 
