@@ -4,8 +4,8 @@ Public names mirror cjycarrie/CLIP-FOR-DL (0426/train.py, disease_analysis.py): 
 contrastive_loss, multilabel_contrastive_loss, predict_multilabel, predict_zero_shot; plus ClassificationAdapter
 (the notebook's "C-Adapter"), the fused ClipHead and install() which patches a reference module in place.
 """
-from .modules import (MODEL_CONFIG, ClassificationAdapter, ImageProjection, MultiViewFusion,  # noqa: F401
-                      TextProjection)
+from .modules import (MODEL_CONFIG, ClassificationAdapter, ImageProjection, MultiModalAttention,  # noqa: F401
+                      MultiViewFusion, TextProjection)
 from .losses import (contrastive_loss, fc_adapter_bce, multilabel_asymmetric_loss,  # noqa: F401
                      multilabel_contrastive_loss, predict_multilabel)
 from .zero_shot import (predict_zero_shot, unpack_mask, zero_shot_posneg, zero_shot_threshold,  # noqa: F401

@@ -12,6 +12,7 @@ def install(*modules: types.ModuleType) -> None:
         "ImageProjection": mods.ImageProjection,
         "TextProjection": mods.TextProjection,
         "MultiViewFusion": mods.MultiViewFusion,
+        "MultiModalAttention": mods.MultiModalAttention,
         "contrastive_loss": losses.contrastive_loss,
         "multilabel_contrastive_loss": losses.multilabel_contrastive_loss,
         "multilabel_asymmetric_loss": losses.multilabel_asymmetric_loss,

@@ -80,6 +80,25 @@ class MultiViewFusion(nn.Module):
                                   self.fusion[3].bias, p, seed)
 
 
+class MultiModalAttention(nn.Module):
+    """Drop-in for multimodal_attention/train.py:1069-1110: additive attention of each image over the class texts.
+    Same no-argument constructor, sub-module names and state_dict keys (image_proj.*, text_proj.*, attention.*,
+    output_proj.*); forward(image_features [B,D], text_features [C,D]) -> (enhanced_features [B,D], attn_weights [B,C])."""
+
+    def __init__(self, shared_embedding_size: int = MODEL_CONFIG["shared_embedding_size"]):
+        super().__init__()
+        d = shared_embedding_size
+        self.image_proj = nn.Linear(d, d)
+        self.text_proj = nn.Linear(d, d)
+        self.attention = nn.Linear(d, 1)
+        self.output_proj = nn.Linear(d, d)
+
+    def forward(self, image_features: torch.Tensor, text_features: torch.Tensor):
+        return ops.AttentionFn.apply(image_features, text_features, self.image_proj.weight, self.image_proj.bias,
+                                     self.text_proj.weight, self.text_proj.bias, self.attention.weight, self.attention.bias,
+                                     self.output_proj.weight, self.output_proj.bias)
+
+
 class ClassificationAdapter(nn.Module):
     """The "C-Adapter": nn.Linear(512,16) + BCEWithLogitsLoss (NB02 c28:50-52).  `forward` = logits (as nn.Linear),
     `loss` = fused Linear+BCE, `predict` = sigmoid(logits) > threshold (NB02 c30:42-43).  state_dict keys weight/bias."""

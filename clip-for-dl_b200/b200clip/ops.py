@@ -274,6 +274,63 @@ class FusionFn(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------------------------
+# MultiModalAttention (multimodal_attention/train.py:1069-1110)
+# --------------------------------------------------------------------------------------------------------------
+class AttentionFn(torch.autograd.Function):
+    """(enhanced_features [B,D], attn_weights [B,C]) = MultiModalAttention(image_features [B,D], text_features [C,D])."""
+
+    @staticmethod
+    def forward(ctx, image_features, text_features, wi, bi, wt, bt, wa, ba, wo, bo):
+        require_cuda(image_features, text_features, wi, wo)
+        lib = load()
+        B, D = image_features.shape
+        Cn = text_features.shape[0]
+        dev = image_features.device
+        x = cast_bf16(image_features)
+        t = _f32c(text_features)
+        wib, wob = cast_bf16(wi), cast_bf16(wo)
+        wtf, waf = _f32c(wt), _f32c(wa).reshape(-1)
+        ip = torch.empty((B, D), dtype=torch.float32, device=dev)
+        tp = torch.empty((Cn, D), dtype=torch.float32, device=dev)
+        w = torch.empty((B, Cn), dtype=torch.float32, device=dev)
+        e = torch.empty((B, D), dtype=torch.bfloat16, device=dev)
+        out = torch.empty((B, D), dtype=torch.float32, device=dev)
+        check(lib.b200clip_attention_fwd(ptr(x), ptr(t), B, Cn, D, ptr(wib), ptr(_f32c(bi)), ptr(wtf), ptr(_f32c(bt)), ptr(waf),
+                                         ptr(_f32c(ba)), ptr(wob), ptr(_f32c(bo)), ptr(ip), ptr(tp), ptr(w), ptr(e), ptr(out),
+                                         stream_ptr()), "attention_fwd")
+        ctx.save_for_backward(x, t, wib, wtf, waf, _f32c(ba), wob, ip, tp, w, e)
+        ctx.need = (image_features.requires_grad, text_features.requires_grad)
+        ctx.dtypes = (image_features.dtype, text_features.dtype)
+        ctx.wa_shape = wa.shape
+        return out, w
+
+    @staticmethod
+    def backward(ctx, d_out, d_w):
+        lib = load()
+        x, t, wib, wtf, waf, ba, wob, ip, tp, w, e = ctx.saved_tensors
+        B, D = ip.shape
+        Cn = tp.shape[0]
+        dev = ip.device
+        d_out = _f32c(d_out) if d_out is not None else torch.zeros((B, D), dtype=torch.float32, device=dev)
+        d_w = _f32c(d_w) if d_w is not None else None
+        f32 = dict(dtype=torch.float32, device=dev)
+        dx = torch.empty((B, D), **f32) if ctx.need[0] else None
+        dt = torch.empty((Cn, D), **f32) if ctx.need[1] else None
+        dwi, dwt, dwo = torch.empty((D, D), **f32), torch.empty((D, D), **f32), torch.empty((D, D), **f32)
+        dbi, dbt, dbo, dwa = (torch.empty((D,), **f32) for _ in range(4))
+        dba = torch.empty((1,), **f32)
+        ws = _ws(lib.b200clip_attention_bwd_workspace_bytes(B, Cn, D), dev)
+        check(lib.b200clip_attention_bwd(ptr(d_out), ptr(d_w), ptr(x), ptr(t), B, Cn, D, ptr(wib), ptr(wtf), ptr(waf), ptr(ba), ptr(wob),
+                                         ptr(ip), ptr(tp), ptr(w), ptr(e), ptr(dx), ptr(dt), ptr(dwi), ptr(dbi), ptr(dwt), ptr(dbt),
+                                         ptr(dwa), ptr(dba), ptr(dwo), ptr(dbo), ptr(ws), ws.numel(), stream_ptr()), "attention_bwd")
+        if dx is not None:
+            dx = dx.to(ctx.dtypes[0])
+        if dt is not None:
+            dt = dt.to(ctx.dtypes[1])
+        return dx, dt, dwi, dbi, dwt, dbt, dwa.reshape(ctx.wa_shape), dba, dwo, dbo
+
+
+# --------------------------------------------------------------------------------------------------------------
 # a-N symmetric InfoNCE
 # --------------------------------------------------------------------------------------------------------------
 def infonce_forward(i_hat: torch.Tensor, t_hat: torch.Tensor, temperature: float, row0: int = 0, group=None,

@@ -106,6 +106,20 @@ int b200clip_fusion_bwd(const float* dy, const void* x_bf16, long long B, int D,
                         const void* h_bf16, float drop_p, float* dx_f32, float* dw0, float* db0, float* dw3, float* db3,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- MultiModalAttention.forward(image_features, text_features) -- multimodal_attention/train.py:1069-1110
+ * x_bf16 [B,D] image features, t [C,D] class text features (fp32, C <= 16, D <= 512); returns out [B,D] (enhanced features)
+ * and w [B,C] (attention weights).  ip [B,D], tp [C,D], w, e_bf16 [B,D] are caller tensors saved for the backward pass;
+ * the [B,C,D] tensor the reference expands is never formed. */
+int b200clip_attention_fwd(const void* x_bf16, const float* t, long long B, int C, int D, const void* wi_bf16, const float* bi,
+                           const float* wt, const float* bt, const float* wa, const float* ba, const void* wo_bf16,
+                           const float* bo, float* ip, float* tp, float* w, void* e_bf16, float* out, void* stream);
+size_t b200clip_attention_bwd_workspace_bytes(long long B, int C, int D);
+int b200clip_attention_bwd(const float* d_out, const float* d_w, const void* x_bf16, const float* t, long long B, int C, int D,
+                           const void* wi_bf16, const float* wt, const float* wa, const float* ba, const void* wo_bf16,
+                           const float* ip, const float* tp, const float* w, const void* e_bf16, float* dx, float* dt,
+                           float* dwi, float* dbi, float* dwt, float* dbt, float* dwa, float* dba, float* dwo, float* dbo,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a-N: contrastive_loss(image_features, text_features, temperature) -- 0426/train.py:154-176 ----------------
  * Inputs are L2-normalised bf16 rows.  Data-parallel form: i_hat = this rank's rows [b_loc, D] (global rows
  * row0 .. row0+b_loc), t_hat = all b_glob rows.  fwd_stats -> r (row sums, complete) and c_partial (this rank's

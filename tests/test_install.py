@@ -58,3 +58,12 @@ def test_reference_checkpoint_keys_load(tmp_path):
     mine_fus = ref.MultiViewFusion()
     assert set(mine_fus.state_dict()) == {"fusion.0.weight", "fusion.0.bias", "fusion.3.weight", "fusion.3.bias"}
     assert tuple(mine_fus.state_dict()["fusion.0.weight"].shape) == (512, 1024)
+
+
+def test_multimodal_attention_state_dict_keys():
+    """multimodal_attention/train.py:1069-1080: four nn.Linear sub-modules under these names."""
+    m = b200clip.MultiModalAttention()
+    sd = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert sd == {"image_proj.weight": (512, 512), "image_proj.bias": (512,), "text_proj.weight": (512, 512),
+                  "text_proj.bias": (512,), "attention.weight": (1, 512), "attention.bias": (1,),
+                  "output_proj.weight": (512, 512), "output_proj.bias": (512,)}
