@@ -4,8 +4,8 @@
 // Forward : GEMM1 (+b1, GELU -> p,h bf16)  GEMM2 (+b2 +p -> z f32)  LayerNorm(+L2-norm)
 // Backward: LN-bwd -> dz ; dW2 = dz^T h (split-K) ; dp = (dz W2) * gelu'(p) + dz (fused epilogue) ;
 //           dW1 = dp^T x (split-K) ; dx = dp W1 ; bias grads = column sums.
-// Dropout (p=0.1 in train mode, 0426/train.py:93) is the identity here: parity is defined with dropout off
-// (SURVEY.md 7.3-4); the Python module refuses train-mode dropout > 0 rather than silently skipping it.
+// Dropout (p=0.1 in train mode, 0426/train.py:93): a counter-based keep-mask hash(seed, row, col) applied in the second GEMM's
+// epilogue and regenerated in the LayerNorm-backward kernel (no mask is stored); drop_p = 0 in eval mode.
 #include "gemm.cuh"
 #include "host.cuh"
 #include "../../include/b200clip.h"
