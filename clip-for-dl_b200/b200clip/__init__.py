@@ -6,7 +6,8 @@ contrastive_loss, multilabel_contrastive_loss, predict_multilabel, predict_zero_
 """
 from .modules import (MODEL_CONFIG, ClassificationAdapter, ImageProjection, MultiModalAttention,  # noqa: F401
                       MultiViewFusion, TextProjection)
-from .losses import (contrastive_loss, fc_adapter_bce, multilabel_asymmetric_loss,  # noqa: F401
+from .losses import (contrastive_clip_loss_function, contrastive_loss, fc_adapter_bce,  # noqa: F401
+                     multilabel_asymmetric_loss,
                      multilabel_contrastive_loss, predict_multilabel)
 from .zero_shot import (predict_zero_shot, unpack_mask, zero_shot_posneg, zero_shot_threshold,  # noqa: F401
                         zero_shot_topk)

@@ -14,6 +14,7 @@ def install(*modules: types.ModuleType) -> None:
         "MultiViewFusion": mods.MultiViewFusion,
         "MultiModalAttention": mods.MultiModalAttention,
         "contrastive_loss": losses.contrastive_loss,
+        "contrastive_clip_loss_function": losses.contrastive_clip_loss_function,
         "multilabel_contrastive_loss": losses.multilabel_contrastive_loss,
         "multilabel_asymmetric_loss": losses.multilabel_asymmetric_loss,
         "predict_multilabel": losses.predict_multilabel,

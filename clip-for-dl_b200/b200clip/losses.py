@@ -18,6 +18,17 @@ def contrastive_loss(image_features, text_features, temperature=1.0):
     return ops.InfoNCEFn.apply(image_features, text_features, float(temperature))
 
 
+def contrastive_clip_loss_function(text_projection, image_projection, temperature=MODEL_CONFIG["temperature"], mode="eval"):
+    """0426/train.py:127-152 (the notebooks' stage-1 loss, NB02 c22): soft targets from both self-similarities, gradients
+    flow through the targets.  mode "train" -> scalar loss, "eval" -> logits [B, B], anything else -> None (as the reference)."""
+    if mode == "eval":
+        return ops.softclip_logits(text_projection, image_projection, float(temperature))
+    if mode != "train":
+        logging.error("Invalid mode for contrastive loss")
+        return None
+    return ops.SoftClipFn.apply(text_projection, image_projection, float(temperature))
+
+
 def multilabel_contrastive_loss(image_features, text_features, labels, temperature=1.0, strict_guard=False):
     """0426/train.py:178-230.  The NaN/Inf/>1000 guard (:224) is evaluated on the device; with strict_guard=True the
     flag is read back (one host sync, like the reference's two) and the reference's fallback is taken."""

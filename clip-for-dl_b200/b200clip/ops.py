@@ -690,6 +690,53 @@ class AslFn(torch.autograd.Function):
         return d.reshape(logits.shape).to(logits.dtype), None, None, None, None, None, None
 
 
+# --------------------------------------------------------------------------------------------------------------
+# a-S soft-target CLIP loss (0426/train.py:127-152)
+# --------------------------------------------------------------------------------------------------------------
+def softclip_logits(text, image, temperature):
+    require_cuda(text, image)
+    t, i = _f32c(text), _f32c(image)
+    n, D = t.shape
+    out = torch.empty((n, i.shape[0]), dtype=torch.float32, device=t.device)
+    if i.shape != t.shape:
+        raise RuntimeError("contrastive_clip_loss_function: text and image projections must have the same shape")
+    check(load().b200clip_softclip_logits(ptr(t), ptr(i), n, D, float(temperature), ptr(out), stream_ptr()), "softclip_logits")
+    return out
+
+
+def _softclip_call(t, i, temperature, grad_scale, want_grad):
+    lib = load()
+    n, D = t.shape
+    dev = t.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    dt = torch.empty((n, D), dtype=torch.float32, device=dev) if want_grad else None
+    di = torch.empty((n, D), dtype=torch.float32, device=dev) if want_grad else None
+    ws = _ws(lib.b200clip_softclip_workspace_bytes(n), dev)
+    check(lib.b200clip_softclip_fwd_bwd(ptr(t), ptr(i), n, D, float(temperature), ptr(grad_scale), ptr(loss), ptr(dt), ptr(di),
+                                        ptr(ws), ws.numel(), stream_ptr()), "softclip_fwd_bwd")
+    return loss, dt, di
+
+
+class SoftClipFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, text, image, temperature):
+        require_cuda(text, image)
+        if text.shape != image.shape or text.dim() != 2:
+            raise RuntimeError("contrastive_clip_loss_function: text and image projections must both be [B, D]")
+        t, i = _f32c(text), _f32c(image)
+        loss, _, _ = _softclip_call(t, i, temperature, None, False)
+        ctx.save_for_backward(t, i)
+        ctx.temperature = float(temperature)
+        ctx.dtypes = (text.dtype, image.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        t, i = ctx.saved_tensors
+        _, dt, di = _softclip_call(t, i, ctx.temperature, _f32c(g).reshape(()), True)     # recomputes the n x n matrices
+        return dt.to(ctx.dtypes[0]), di.to(ctx.dtypes[1]), None
+
+
 def head_loss_finalize(sums6, label_sum, tau_nce, b_glob, total_text, total_fc):
     """loss, parts[3] (InfoNCE, text BCE, FC BCE), status from the six numerators (already summed over ranks)."""
     dev = sums6.device

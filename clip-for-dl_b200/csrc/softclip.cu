@@ -1,0 +1,254 @@
+// b200clip: the soft-target CLIP loss of the notebooks (a-S; contrastive_clip_loss_function, 0426/train.py:127-152 with
+// cross_entropy :118-125; NB02 c22:3-27) in fp32.
+//   L = T I^T / tau          P = softmax_row((I I^T + T T^T) / 2 * tau)        (targets, NOT detached)
+//   loss = mean_i 1/2 [ -sum_j P_ij logsoftmax_row(L)_ij  -  sum_j P_ji logsoftmax_col(L)_ji ]
+// The inputs are LayerNorm outputs (norm ~ sqrt(D)), not unit vectors: at tau = 0.07 the logits reach +-10^3..10^4, so the Gram
+// products must be fp32-accurate (bf16 operands would put O(1) errors on the logits) and every softmax needs its true row
+// maximum.  This first version therefore runs on fp32 CUDA cores and keeps the n x n matrices in a caller workspace
+// (4 n^2 floats): it covers the batch sizes the reference trains this loss with (16..64, NB02 c25) up to n = 8192; it is
+// NOT the flash-style tensor-core path of infonce.cu.  Backward, for upstream gradient g:
+//   dL_ij = g [ (softmax_row(L)_ij - P_ij) + (softmax_col(L)_ij colsum(P)_j - P_ij) ] / (2n)
+//   dP_ij = -g (logsoftmax_row(L)_ij + logsoftmax_col(L)_ij) / (2n)      dQ_ij = P_ij (dP_ij - sum_k P_ik dP_ik)
+//   dT = dL I / tau + S T      dI = dL^T T / tau + S I      S = (dQ + dQ^T) tau / 2
+#include <algorithm>
+
+#include "common.cuh"
+#include "host.cuh"
+#include "../../include/b200clip.h"
+
+namespace b200 {
+
+constexpr int SG_TILE = 64, SG_K = 16;
+
+// C[m][n] (+)= alpha * sum_k A(m,k) B(k,n) with element strides (any transposition without copies); 64x64 tile, 4x4 per thread
+__global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ A, long long sa_m, long long sa_k,
+                                                            const float* __restrict__ B, long long sb_k, long long sb_n,
+                                                            float* __restrict__ C, long long ldc, int M, int N, int K, float alpha,
+                                                            int accumulate) {
+  __shared__ float As[SG_K][SG_TILE + 4];
+  __shared__ float Bs[SG_K][SG_TILE + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * SG_TILE, n0 = blockIdx.x * SG_TILE;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += SG_K) {
+    for (int e = threadIdx.x; e < SG_K * SG_TILE; e += 256) {
+      // pick the faster-varying index along the unit-stride direction of each operand
+      int ka, ma, kb, nb;
+      if (sa_k == 1) { ka = e % SG_K; ma = e / SG_K; } else { ma = e % SG_TILE; ka = e / SG_TILE; }
+      if (sb_k == 1) { kb = e % SG_K; nb = e / SG_K; } else { nb = e % SG_TILE; kb = e / SG_TILE; }
+      const int gm = m0 + ma, gka = k0 + ka, gn = n0 + nb, gkb = k0 + kb;
+      As[ka][ma] = (gm < M && gka < K) ? A[gm * sa_m + gka * sa_k] : 0.f;
+      Bs[kb][nb] = (gn < N && gkb < K) ? B[gkb * sb_k + gn * sb_n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SG_K; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+      if (gm < M && gn < N) {
+        float* c = C + gm * ldc + gn;
+        *c = accumulate ? *c + alpha * acc[i][j] : alpha * acc[i][j];
+      }
+    }
+}
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) r = fmaxf(r, red[w]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) r += red[w];
+  __syncthreads();
+  return r;
+}
+
+// lse[i] = log sum_j exp(M[i][j])      (one block per row)
+__global__ void __launch_bounds__(256) row_lse_kernel(const float* __restrict__ M, int n, float* __restrict__ lse) {
+  __shared__ float red[8];
+  const float* row = M + static_cast<long long>(blockIdx.x) * n;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < n; j += 256) mx = fmaxf(mx, row[j]);
+  mx = block_max(mx, red);
+  float s = 0.f;
+  for (int j = threadIdx.x; j < n; j += 256) s += expf(row[j] - mx);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) lse[blockIdx.x] = mx + logf(s);
+}
+
+// Q[i][:] <- softmax(Q[i][:] * scale)      (in place; one block per row)
+__global__ void __launch_bounds__(256) row_softmax_kernel(float* __restrict__ Q, int n, float scale) {
+  __shared__ float red[8];
+  float* row = Q + static_cast<long long>(blockIdx.x) * n;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < n; j += 256) mx = fmaxf(mx, row[j] * scale);
+  mx = block_max(mx, red);
+  float s = 0.f;
+  for (int j = threadIdx.x; j < n; j += 256) s += expf(row[j] * scale - mx);
+  s = block_sum(s, red);
+  const float inv = 1.0f / s;
+  for (int j = threadIdx.x; j < n; j += 256) row[j] = expf(row[j] * scale - mx) * inv;
+}
+
+// out[j] = sum_i P[i][j]
+__global__ void __launch_bounds__(256) col_sum_kernel(const float* __restrict__ P, int n, float* __restrict__ out) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= n) return;
+  float a = 0.f;
+  for (int i = 0; i < n; ++i) a += P[static_cast<long long>(i) * n + j];
+  out[j] = a;
+}
+
+// rowloss[i] = sum_j P_ij ((L_ij - lse_r[i]) + (L_ij - lse_c[j]))      (one block per row)
+__global__ void __launch_bounds__(256) soft_rowloss_kernel(const float* __restrict__ L, const float* __restrict__ P, const float* __restrict__ lse_r,
+                                                           const float* __restrict__ lse_c, int n, float* __restrict__ rowloss) {
+  __shared__ float red[8];
+  const long long base = static_cast<long long>(blockIdx.x) * n;
+  const float lr = lse_r[blockIdx.x];
+  float a = 0.f;
+  for (int j = threadIdx.x; j < n; j += 256) {
+    const float l = L[base + j];
+    a += P[base + j] * ((l - lr) + (l - lse_c[j]));
+  }
+  a = block_sum(a, red);
+  if (threadIdx.x == 0) rowloss[blockIdx.x] = a;
+}
+
+// loss = -(1 / 2n) sum_i rowloss[i]       (single block, fixed order)
+__global__ void __launch_bounds__(256) soft_loss_final_kernel(const float* __restrict__ rowloss, int n, float* __restrict__ loss) {
+  __shared__ double red[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) a += static_cast<double>(rowloss[i]);
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = static_cast<float>(-red[0] / (2.0 * n));
+}
+
+// in place: L <- dL, P <- dQ   (formulas in the file header)
+__global__ void __launch_bounds__(256) soft_grad_kernel(float* __restrict__ L, float* __restrict__ P, const float* __restrict__ lse_r,
+                                                        const float* __restrict__ lse_c, const float* __restrict__ colsum_p,
+                                                        const float* __restrict__ rowloss, const float* __restrict__ grad_scale, int n) {
+  const long long idx = blockIdx.x * 256ll + threadIdx.x;
+  if (idx >= static_cast<long long>(n) * n) return;
+  const int i = static_cast<int>(idx / n), j = static_cast<int>(idx - static_cast<long long>(i) * n);
+  const float g = (grad_scale ? *grad_scale : 1.0f) / (2.0f * n);
+  const float l = L[idx], pij = P[idx];
+  const float a = l - lse_r[i], c = l - lse_c[j];
+  L[idx] = g * ((expf(a) - pij) + (expf(c) * colsum_p[j] - pij));
+  const float dp = -g * (a + c);
+  const float rowdot = -g * rowloss[i];                    // sum_k P_ik dP_ik
+  P[idx] = pij * (dp - rowdot);
+}
+
+// S[i][j] = (dQ[i][j] + dQ[j][i]) * scale
+__global__ void __launch_bounds__(256) soft_sym_kernel(const float* __restrict__ dQ, int n, float scale, float* __restrict__ S) {
+  const long long idx = blockIdx.x * 256ll + threadIdx.x;
+  if (idx >= static_cast<long long>(n) * n) return;
+  const int i = static_cast<int>(idx / n), j = static_cast<int>(idx - static_cast<long long>(i) * n);
+  S[idx] = (dQ[idx] + dQ[static_cast<long long>(j) * n + i]) * scale;
+}
+
+static int sgemm(const float* A, long long sa_m, long long sa_k, const float* B, long long sb_k, long long sb_n, float* C, long long ldc,
+                 int M, int N, int K, float alpha, int accumulate, cudaStream_t s) {
+  dim3 grid((N + SG_TILE - 1) / SG_TILE, (M + SG_TILE - 1) / SG_TILE);
+  sgemm_strided_kernel<<<grid, 256, 0, s>>>(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, M, N, K, alpha, accumulate);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+constexpr long long SOFT_MAX_N = 8192;
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" size_t b200clip_softclip_workspace_bytes(long long n) {
+  if (n <= 0) return 0;
+  return static_cast<size_t>(4 * n * n + 4 * n) * sizeof(float) + 1024;
+}
+
+// mode == "eval" (0426/train.py:149-150): logits[n, n] = text image^T / tau
+extern "C" int b200clip_softclip_logits(const float* text, const float* image, long long n, int D, float temperature, float* logits,
+                                        void* stream) {
+  B200_REQUIRE(n > 0 && D > 0 && temperature > 0.f && text && image && logits, "softclip_logits: bad arguments");
+  B200_REQUIRE(n <= SOFT_MAX_N, "softclip: n=%lld exceeds the %lld this fp32 version covers", n, SOFT_MAX_N);
+  return sgemm(text, D, 1, image, 1, D, logits, n, (int)n, (int)n, D, 1.0f / temperature, 0, static_cast<cudaStream_t>(stream));
+}
+
+// mode == "train": loss (device scalar); with d_text / d_image (both [n, D]) also the gradients for upstream *grad_scale
+extern "C" int b200clip_softclip_fwd_bwd(const float* text, const float* image, long long n, int D, float temperature,
+                                         const float* grad_scale, float* loss, float* d_text, float* d_image, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  B200_REQUIRE(n > 0 && D > 0 && temperature > 0.f && text && image && loss, "softclip: bad arguments");
+  if (n > SOFT_MAX_N) return fail(B200_ERR_UNSUPPORTED, "softclip: n=%lld exceeds the %lld this fp32 version covers", n, SOFT_MAX_N);
+  B200_REQUIRE((d_text == nullptr) == (d_image == nullptr), "softclip: pass both gradients or neither");
+  if (workspace_bytes < b200clip_softclip_workspace_bytes(n)) return fail(B200_ERR_WORKSPACE, "softclip: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int N = static_cast<int>(n);
+  const long long nn = n * n;
+  float* L = static_cast<float*>(workspace);       // logits, later dL
+  float* Lt = L + nn;                              // logits^T, later S
+  float* P = Lt + nn;                              // (I I^T + T T^T) -> targets -> dQ
+  float* vec = P + nn + nn;                        // (one n^2 block spare for alignment slack) lse_r | lse_c | colsum_p | rowloss
+  float* lse_r = vec; float* lse_c = vec + n; float* colsum_p = vec + 2 * n; float* rowloss = vec + 3 * n;
+  const float inv_tau = 1.0f / temperature;
+  int rc;
+  if ((rc = sgemm(text, D, 1, image, 1, D, L, n, N, N, D, inv_tau, 0, s))) return rc;            // :139  L = T I^T / tau
+  if ((rc = sgemm(image, D, 1, text, 1, D, Lt, n, N, N, D, inv_tau, 0, s))) return rc;           //       L^T (column statistics as rows)
+  if ((rc = sgemm(image, D, 1, image, 1, D, P, n, N, N, D, 1.0f, 0, s))) return rc;              // :141
+  if ((rc = sgemm(text, D, 1, text, 1, D, P, n, N, N, D, 1.0f, 1, s))) return rc;                // :142 (+=)
+  row_softmax_kernel<<<N, 256, 0, s>>>(P, N, 0.5f * temperature);                                // :143
+  B200_LAUNCH_CHECK();
+  row_lse_kernel<<<N, 256, 0, s>>>(L, N, lse_r);
+  B200_LAUNCH_CHECK();
+  row_lse_kernel<<<N, 256, 0, s>>>(Lt, N, lse_c);
+  B200_LAUNCH_CHECK();
+  soft_rowloss_kernel<<<N, 256, 0, s>>>(L, P, lse_r, lse_c, N, rowloss);                         // :144-146
+  B200_LAUNCH_CHECK();
+  soft_loss_final_kernel<<<1, 256, 0, s>>>(rowloss, N, loss);                                    // :147
+  B200_LAUNCH_CHECK();
+  if (!d_text) return B200_OK;
+  col_sum_kernel<<<(N + 255) / 256, 256, 0, s>>>(P, N, colsum_p);
+  B200_LAUNCH_CHECK();
+  const int eg = static_cast<int>((nn + 255) / 256);
+  soft_grad_kernel<<<eg, 256, 0, s>>>(L, P, lse_r, lse_c, colsum_p, rowloss, grad_scale, N);     // L <- dL, P <- dQ
+  B200_LAUNCH_CHECK();
+  soft_sym_kernel<<<eg, 256, 0, s>>>(P, N, 0.5f * temperature, Lt);                              // Lt <- S
+  B200_LAUNCH_CHECK();
+  if ((rc = sgemm(L, n, 1, image, D, 1, d_text, D, N, D, N, inv_tau, 0, s))) return rc;          // dT  = dL I / tau
+  if ((rc = sgemm(Lt, n, 1, text, D, 1, d_text, D, N, D, N, 1.0f, 1, s))) return rc;             //     += S T
+  if ((rc = sgemm(L, 1, n, text, D, 1, d_image, D, N, D, N, inv_tau, 0, s))) return rc;          // dI  = dL^T T / tau
+  if ((rc = sgemm(Lt, n, 1, image, D, 1, d_image, D, N, D, N, 1.0f, 1, s))) return rc;           //     += S I
+  return B200_OK;
+}

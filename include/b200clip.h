@@ -141,6 +141,17 @@ int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D, long long 
                          float temperature, const float* rinvh, const float* cinvh, const float* grad_scale, float* d_i,
                          int d_i_splits, float* d_t_partial, void* stream);
 
+/* ---- a-S: contrastive_clip_loss_function(text_projection, image_projection, temperature, mode) -- 0426/train.py:127-152
+ * (soft targets softmax((I I^T + T T^T)/2 * tau), NOT detached; cross_entropy :118-125).  fp32 throughout (un-normalised inputs:
+ * logits of +-10^3..10^4); the n x n matrices live in the caller's workspace, n <= 8192.  text, image: [n, D] f32.
+ * _logits = mode "eval"; _fwd_bwd = mode "train": loss, and with d_text/d_image the gradients for upstream *grad_scale. */
+size_t b200clip_softclip_workspace_bytes(long long n);
+int b200clip_softclip_logits(const float* text, const float* image, long long n, int D, float temperature, float* logits,
+                             void* stream);
+int b200clip_softclip_fwd_bwd(const float* text, const float* image, long long n, int D, float temperature,
+                              const float* grad_scale, float* loss, float* d_text, float* d_image, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* ---- a-B: multilabel_contrastive_loss(image_features, text_features, labels, temperature) -- 0426/train.py:178-230
  * label_sum: device scalar = sum(labels) over the GLOBAL batch; total_elems = B_glob * C.  status gets 1 when the
  * loss is NaN/Inf/>1000 (the reference's fallback condition, :224).  coef [B,C] = d loss / d (cos/tau) feeds

@@ -31,6 +31,9 @@ def test_signatures_match_reference_defaults():
     assert list(sig.parameters) == ["image_features", "text_features", "temperature"] and sig.parameters["temperature"].default == 1.0
     sig = inspect.signature(b200clip.multilabel_contrastive_loss)
     assert list(sig.parameters)[:4] == ["image_features", "text_features", "labels", "temperature"]
+    sig = inspect.signature(b200clip.contrastive_clip_loss_function)
+    assert list(sig.parameters) == ["text_projection", "image_projection", "temperature", "mode"]
+    assert sig.parameters["temperature"].default == 0.07 and sig.parameters["mode"].default == "eval"
     sig = inspect.signature(b200clip.multilabel_asymmetric_loss)
     assert list(sig.parameters) == ["logits", "targets", "gamma_pos", "gamma_neg", "clip", "eps", "reduction"]
     assert [sig.parameters[k].default for k in ("gamma_pos", "gamma_neg", "clip", "eps", "reduction")] == [0, 4, 0.05, 1e-8, "mean"]
