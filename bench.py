@@ -149,7 +149,7 @@ def run_reference(args, cfg):
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -346,7 +346,7 @@ def run_head(args, cfg):
             line["cpu_baseline"] = {
                 "value": Bs / best, "unit": "pairs/s", "cores": cores, "kind": "port",
                 "sample": f"oracle port of the reference head, torch fp32 CPU, best of 3 at B={Bs} (of B={B}); time grows ~B^2"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if not args.eager:
         gstep.close()                                    # a live graph holding NCCL kernels would block communicator teardown
     if world > 1:
@@ -421,10 +421,25 @@ def run_zeroshot(args):
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "zeroshot_kernel", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s",
                          "frac": achieved / pk["hbm"], "traffic": None, "peak_source": pk["src"]}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's real stdout; fd 1 itself is pointed at stderr for the rest of the run so that
+    banners printed by libraries (NCCL prints its version to stdout) cannot end up next to it."""
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
