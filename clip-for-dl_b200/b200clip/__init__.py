@@ -14,5 +14,6 @@ from .zero_shot import (predict_zero_shot, unpack_mask, zero_shot_posneg, zero_s
 from .head import ClipHead, ClipHeadFn, GraphedHeadStep  # noqa: F401
 from .ops import normalize  # noqa: F401
 from .install import install  # noqa: F401
+from .optim import FusedAdamW  # noqa: F401
 
 __version__ = "0.1.0"

@@ -523,6 +523,56 @@ extern "C" int b200clip_dropout_mask(float* out, long long rows, int cols, float
   return B200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// AdamW for the head parameters (the reference trains with torch.optim.AdamW(lr=1e-4, weight_decay=0.01)).
+// torch.optim.AdamW semantics (decoupled decay, bias-corrected moments, amsgrad off).  The step count lives on the device
+// (adamw_tick increments it once per optimizer step), so the update can sit inside a captured CUDA graph.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void adamw_tick_kernel(float* __restrict__ step) { *step += 1.0f; }
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
+                                                    float weight_decay, const float* __restrict__ step) {
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {                                    // bias corrections in double (1 - 0.999^t cancels badly in fp32)
+    const double t = static_cast<double>(*step);
+    s_bc[0] = static_cast<float>(1.0 - pow(static_cast<double>(beta1), t));
+    s_bc[1] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)));
+  }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
+  const float step_size = lr / bc1;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+    const float gi = g[i];
+    float pi = p[i] * (1.0f - lr * weight_decay);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    pi -= step_size * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    p[i] = pi;
+  }
+}
+
+extern "C" int b200clip_adamw_tick(float* step, void* stream) {
+  B200_REQUIRE(step != nullptr, "adamw_tick: missing step counter");
+  adamw_tick_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200clip_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                                   float beta1, float beta2, float eps, float weight_decay, const float* step, void* stream) {
+  B200_REQUIRE(n >= 0 && param && grad && exp_avg && exp_avg_sq && step, "adamw_step: missing arguments");
+  B200_REQUIRE(lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "adamw_step: bad hyper-parameters");
+  if (n == 0) return B200_OK;
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, static_cast<long long>(num_sms()) * 8));
+  adamw_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                    weight_decay, step);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 // strided 2-D cast (concatenating two [rows, cols] f32 views side by side into one bf16 matrix = two calls)
 __global__ void __launch_bounds__(256) cast2d_f32_bf16_kernel(const float* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out,
                                                               long long ld_out, long long rows, int cols4) {

@@ -196,6 +196,12 @@ int b200clip_asl_fwd_bwd(const float* logits, const float* targets, long long n,
                          float eps, int reduction, const float* grad_scale, const float* grad_elem, float* loss_elem,
                          float* d_logits, double* sum, float* loss, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- torch.optim.AdamW for the head parameters: decoupled weight decay, bias-corrected moments.  `step`
+ * is a device float counter: call b200clip_adamw_tick once per optimizer step, then b200clip_adamw_step per parameter tensor. */
+int b200clip_adamw_tick(float* step, void* stream);
+int b200clip_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, const float* step, void* stream);
+
 /* loss of the fused head step from its six numerators (summed over ranks): sums6 = {sum_i log r_i, sum_j log c_j,
  * sum_i S_ii, text-BCE pos numerator, text-BCE neg numerator, FC-BCE sum}; parts3 = {InfoNCE, text BCE, FC BCE}. */
 int b200clip_head_loss_finalize(const double* sums6, const float* label_sum, float temperature_nce, double b_glob,
