@@ -32,16 +32,28 @@ def _worker(rank, world, port, B, tau, out_dir):
     work.wait()
     assert torch.equal(T_all, T)
     r, c_part, diag, m = R.contrastive_loss_flash(I_loc, T_all, tau, row0=rank * n)
-    c = dp.sum_across(c_part.clone())
-    sums = torch.stack([torch.log(r).sum(), torch.log(c[rank * n:(rank + 1) * n]).sum(), diag])
-    loss = dp.infonce_loss_from_sums(dp.sum_across(sums), tau, B)
-    # backward: dI local, dT partial -> reduce-scatter
+    # global label count: asynchronous, waited on only before the BCE heads (head.py)
+    lsum = torch.tensor(float(rank + 1))
+    lsum_work = dp.sum_across_async(lsum)
+    c = dp.sum_across(c_part.clone())                       # the one collective on the forward critical path
+    # six loss numerators (3 InfoNCE | 3 BCE) in ONE all-reduce that nothing in the backward pass waits for
+    sums6 = torch.zeros(6, dtype=torch.float64)
+    sums6[:3] = torch.stack([torch.log(r).sum(), torch.log(c[rank * n:(rank + 1) * n]).sum(), diag])
+    sums6[3:] = torch.tensor([1.0, 2.0, 3.0]) * (rank + 1)
+    sums_work = dp.sum_across_async(sums6)
+    # backward: dI local, dT partial -> reduce-scatter; two gradient buckets, the first one asynchronous
     dI, dT_part = R.contrastive_grads_flash(I_loc, T_all, tau, r, c, row0=rank * n)
     dT_loc, _ = dp.scatter_sum_rows(dT_part.clone())
-    # parameter-gradient bucket
-    g = dp.allreduce_flat([torch.full((3,), float(rank + 1)), torch.full((2, 2), 10.0 * (rank + 1))])
-    # BCE head scalars
-    lsum = dp.sum_across(torch.tensor(float(rank + 1)))
+    g_img, g_work = dp.allreduce_flat([torch.full((3,), float(rank + 1)), torch.full((2, 2), 10.0 * (rank + 1))], async_op=True)
+    g_txt = dp.allreduce_flat([torch.full((5,), 100.0 * (rank + 1))])
+    dp.wait(g_work)
+    g = [g_img[0], g_img[1]]
+    dp.wait(sums_work)
+    dp.wait(lsum_work)
+    loss = dp.infonce_loss_from_sums(sums6[:3], tau, B)
+    tri = world * (world + 1) / 2
+    assert torch.allclose(sums6[3:], torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64) * tri)
+    assert torch.allclose(g_txt[0], torch.full((5,), 100.0 * tri))
     torch.save({"loss": loss, "dI": dI, "dT": dT_loc, "g0": g[0], "g1": g[1], "lsum": lsum}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
