@@ -48,35 +48,43 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock + throttle reasons with NVML while the timed region runs."""
+    """Samples SM clock + throttle reasons with NVML while the timed region runs (NVML is initialised in the constructor, so the
+    first sample lands at the start of the region; one sample every 5 ms)."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
-
-    def run(self):
+        self._nv = self._h = self._get = None
+        self._names = {}
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
+            self._nv, self._h = nv, nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+            self._names = {
                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
                 getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
                 getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
                 getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
             }
-            get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
-            while not self._stop_evt.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                mask = get(h)
-                for bit, nm in names.items():
-                    if mask & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.02)
+            self._get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
         except Exception as e:  # NVML missing: report that instead of failing the bench
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def run(self):
+        if self._nv is None:
+            return
+        try:
+            while not self._stop_evt.is_set():
+                self.samples.append(self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM))
+                mask = self._get(self._h)
+                for bit, nm in self._names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.005)
+        except Exception as e:
+            self.reasons.add(f"nvml_error:{type(e).__name__}")
 
     def stop(self):
         self._stop_evt.set()
