@@ -250,10 +250,16 @@ class GraphedHeadStep:
             self.graph = None
 
     def __call__(self, image_embeddings=None, text_embeddings=None, class_text_features=None, labels=None):
+        if self.graph is None:
+            raise RuntimeError("GraphedHeadStep: the graph was released by close()")
         with torch.no_grad():
-            for dst, src in ((self.x_img, image_embeddings), (self.x_txt, text_embeddings),
-                             (self.class_text, class_text_features), (self.labels, labels)):
-                if src is not None and src.data_ptr() != dst.data_ptr():
-                    dst.copy_(src, non_blocking=True)
+            for name, dst, src in (("image_embeddings", self.x_img, image_embeddings), ("text_embeddings", self.x_txt, text_embeddings),
+                                   ("class_text_features", self.class_text, class_text_features), ("labels", self.labels, labels)):
+                if src is None or src.data_ptr() == dst.data_ptr():
+                    continue
+                if tuple(src.shape) != tuple(dst.shape):
+                    raise RuntimeError(f"GraphedHeadStep: {name} has shape {tuple(src.shape)}, the graph was captured for "
+                                       f"{tuple(dst.shape)} (capture a new GraphedHeadStep for a different batch size)")
+                dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.loss

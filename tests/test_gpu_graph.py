@@ -48,6 +48,20 @@ def test_graphed_step_equals_eager_step():
         step.bind_grads()                                  # the eager step re-bound .grad: point it at the graph's tensors again
 
 
+def test_graphed_step_rejects_other_shapes_and_use_after_close():
+    import b200clip
+    import pytest
+    d = dev()
+    head = b200clip.ClipHead(768, 768, 512, 16).to(d)
+    xi, xt, ct, lab = _inputs(1, 256, 768, 512, 16, d)
+    step = b200clip.GraphedHeadStep(head, xi, xt, ct, lab)
+    with pytest.raises(RuntimeError):
+        step(xi[:128], xt[:128], ct, lab[:128])
+    step.close()
+    with pytest.raises(RuntimeError):
+        step()
+
+
 def test_graphed_step_refuses_dropout():
     import b200clip
     import pytest
