@@ -1159,8 +1159,9 @@ __global__ void __launch_bounds__(256) nce_loss_kernel(const __nv_bfloat16* __re
 // Default: X in shared memory, 128 x 128 S tiles, 5-stage Y ring, 4 TMEM S buffers: 0.83 ms at B = 32768 (ncu: tensor pipe
 // 67 % active; the 8 KB of SS operands per 64-clk MMA plus the TMA writes of Y oversubscribe the 128 B/clk smem port).
 // The TMEM-resident-X variant (XT: TS MMAs, 12-stage ring, 2 S buffers shared by warpgroup pairs that split the columns)
-// measured 0.80 ms -- the port is no longer the limit, but with two S buffers the epilogue is -- so it stays optional
-// (-DB200CLIP_FWD_XT=1; same results, tests pass).  A 64-column XT variant measured 1.42 ms.
+// measured 0.80 ms stand-alone and 0.894 vs 0.938 ms inside the step (step 5.39 vs 5.42 ms; all 109 GPU tests pass with it) --
+// B operand reads + TMA writes still fill the port (64 + 64 B/clk); a 2-CTA pair (cta_group::2) halving both is the real fix --
+// so it stays optional (-DB200CLIP_FWD_XT=1).  A 64-column XT variant measured 1.42 ms.
 #ifndef B200CLIP_FWD_XT
 #define B200CLIP_FWD_XT 0
 #endif
