@@ -98,7 +98,7 @@ def test_projection_train_mode_dropout_matches_reference_with_same_mask():
     assert torch.equal(mod.eval()(xg), mod(xg))           # eval: dropout off, deterministic
 
 
-@pytest.mark.parametrize("B,E_img", [(256, 2048), (1024, 768)])
+@pytest.mark.parametrize("B,E_img", [(256, 2048), (1024, 768), (200, 768)])      # 200: ragged (not a multiple of 16 / 128)
 def test_fused_head_step(B, E_img):
     import b200clip
     D, E_txt, C = 512, 768, 16
