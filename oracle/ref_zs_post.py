@@ -30,12 +30,15 @@ def view_predictions(prob: np.ndarray, threshold: Union[float, Dict[int, float]]
                      ) -> Tuple[List[int], List[float]]:
     """One view's (label indices, scores) as predict_zero_shot builds them (disease_analysis.py:361-413).
     threshold: scalar (:381-390) or {label index: threshold} (:372-379, labels absent from the dict never pass)."""
-    prob = np.asarray(prob, dtype=np.float64)
+    p32 = np.asarray(prob, dtype=np.float32)          # the reference holds the probabilities in a float32 tensor ...
+    prob = p32.astype(np.float64)                     # ... and turns the kept ones into python floats (:379, :386)
     L = prob.shape[0]
+    # `probabilities[j] >= threshold[disease]` compares a float32 tensor element with a python / numpy scalar: torch keeps the
+    # tensor dtype, i.e. the threshold is rounded to float32 before the comparison (:377, :382)
     if isinstance(threshold, dict):
-        preds = [j for j in range(L) if j in threshold and prob[j] >= threshold[j]]
+        preds = [j for j in range(L) if j in threshold and p32[j] >= np.float32(threshold[j])]
     else:
-        preds = [j for j in range(L) if prob[j] >= threshold]
+        preds = [j for j in range(L) if p32[j] >= np.float32(threshold)]
     scores = [float(prob[j]) for j in preds]
     if len(preds) == 0 or (top_k is not None and len(preds) < top_k):          # :393-410
         k = top_k if top_k is not None else 1

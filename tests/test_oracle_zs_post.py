@@ -57,12 +57,15 @@ def test_dynamic_thresholds_match_sklearn_transcription():
 
 
 def test_view_predictions_and_merge_cases():
-    prob = np.array([0.9, 0.2, 0.55, 0.1])
-    assert Z.view_predictions(prob, 0.5) == ([0, 2], [0.9, 0.55])
-    assert Z.view_predictions(prob, 0.95) == ([0], [0.9])                       # nothing passes -> top-1
-    assert Z.view_predictions(prob, {0: 0.95, 2: 0.5}) == ([2], [0.55])         # labels missing from the dict never pass
-    assert Z.view_predictions(prob, 0.5, top_k=3) == ([0, 2, 1], [0.9, 0.55, 0.2])   # padded from the top-k list
-    assert Z.view_predictions(prob, 0.05, top_k=2) == ([0, 2], [0.9, 0.55])     # cut to the best k
+    prob = np.array([0.875, 0.25, 0.5625, 0.125])                                # exactly representable in float32
+    assert Z.view_predictions(prob, 0.5) == ([0, 2], [0.875, 0.5625])
+    assert Z.view_predictions(prob, 0.95) == ([0], [0.875])                     # nothing passes -> top-1
+    assert Z.view_predictions(prob, {0: 0.95, 2: 0.5}) == ([2], [0.5625])       # labels missing from the dict never pass
+    assert Z.view_predictions(prob, 0.5, top_k=3) == ([0, 2, 1], [0.875, 0.5625, 0.25])   # padded from the top-k list
+    assert Z.view_predictions(prob, 0.05, top_k=2) == ([0, 2], [0.875, 0.5625])  # cut to the best k
+    # the per-view test happens in float32 (torch keeps the tensor dtype): a threshold a hair above the float32 value still passes
+    p32 = float(np.float32(0.3))
+    assert Z.view_predictions(np.array([p32]), p32 + 1e-10) == ([0], [p32])
     thr = np.array([0.6, 0.6, 0.6, 0.6])
     # lateral view counts 0.8: 0.7 * 0.8 = 0.56 < 0.6 is dropped, the frontal 0.65 stays
     assert Z.merge_two_views([[0], [1]], [[0.65], [0.7]], thr) == ([0], [0.65])
