@@ -36,6 +36,9 @@ SIGNATURES = {
     "b200clip_softclip_fwd_bwd": (i32, [vp, vp, ll, i32, f32, vp, vp, vp, vp, vp, sz, vp]),
     "b200clip_adamw_tick": (i32, [vp, vp]),
     "b200clip_adamw_step": (i32, [vp, vp, vp, vp, ll, f32, f32, f32, f32, f32, vp, vp]),
+    "b200clip_zs_thresholds_workspace_bytes": (sz, [ll, i32]),
+    "b200clip_zs_dynamic_thresholds": (i32, [vp, vp, ll, i32, vp, vp, vp, sz, vp]),
+    "b200clip_zs_merge_views": (i32, [vp, vp, ll, i32, f64, f64, vp, vp, vp]),
     "b200clip_head_loss_finalize": (i32, [vp, vp, f32, f64, f64, f64, vp, vp, vp, vp]),
     "b200clip_debug_set_nce_prof": (None, [vp]),
     "b200clip_gemm_bf16": (i32, [vp, vp, i32, i32, i32, i32, i32, ll, ll, i32, f32, vp, ll, vp, ll, vp, vp, ll, vp, ll, i32, vp]),

@@ -76,3 +76,45 @@ def predict_zero_shot(images, models: Dict, disease_list: List[str], top_k: int 
     if is_batch:
         return [[disease_list[j] for j in row] for row in idx_c], [row for row in val_c]
     return [{"disease": disease_list[j], "confidence": float(s)} for j, s in zip(idx_c[0], val_c[0])]
+
+
+# --------------------------------------------------------------------------------------------------------------
+# zero-shot post-processing on the device (multimodal_attention/zero_shot_predict.py:66-213)
+# --------------------------------------------------------------------------------------------------------------
+def dynamic_thresholds(max_scores: torch.Tensor, labels: torch.Tensor, return_f1: bool = False):
+    """Per-label thresholds from a validation slice (zero_shot_predict.py:112-159): max_scores [N, L] = per-sample maximum over
+    the two views of the sigmoid scores (:96-103), labels [N, L] in {0, 1}.  Returns a float64 CUDA tensor [L] (and the best F1
+    per label).  The reference does this with numpy + sklearn in a python loop over labels and 20 grid points."""
+    from . import ops as _ops
+    from ._lib import check, load, ptr, require_cuda, stream_ptr
+    require_cuda(max_scores, labels)
+    s, y = _ops._f32c(max_scores), _ops._f32c(labels)
+    if s.dim() != 2 or s.shape != y.shape or s.shape[1] > 32:
+        raise RuntimeError("dynamic_thresholds: scores and labels must both be [N, L] with L <= 32")
+    N, L = s.shape
+    lib = load()
+    thr = torch.empty((L,), dtype=torch.float64, device=s.device)
+    f1 = torch.empty((L,), dtype=torch.float64, device=s.device)
+    ws = torch.empty(max(int(lib.b200clip_zs_thresholds_workspace_bytes(N, L)), 256), dtype=torch.uint8, device=s.device)
+    check(lib.b200clip_zs_dynamic_thresholds(ptr(s), ptr(y), N, L, ptr(thr), ptr(f1), ptr(ws), ws.numel(), stream_ptr()),
+          "zs_dynamic_thresholds")
+    return (thr, f1) if return_f1 else thr
+
+
+def merge_two_views(prob_views: torch.Tensor, thresholds: torch.Tensor, weights=(1.0, 0.8), return_scores: bool = False):
+    """Weighted two-view merge (zero_shot_predict.py:183-221): prob_views [N, 2, L] sigmoid scores (frontal, lateral), thresholds
+    [L]; per view the labels that pass their threshold (or the single best one), weighted maximum over the views (1.0 / 0.8),
+    per-label filter, fallback to the best label.  Returns the {0,1} prediction matrix [N, L] (uint8) on the device."""
+    from . import ops as _ops
+    from ._lib import check, load, ptr, require_cuda, stream_ptr
+    require_cuda(prob_views, thresholds)
+    p = _ops._f32c(prob_views)
+    if p.dim() != 3 or p.shape[1] != 2 or p.shape[2] > 32 or thresholds.numel() != p.shape[2]:
+        raise RuntimeError("merge_two_views: prob_views must be [N, 2, L] with L <= 32 and one threshold per label")
+    N, _, L = p.shape
+    thr = thresholds.to(torch.float64).contiguous()
+    pred = torch.empty((N, L), dtype=torch.uint8, device=p.device)
+    merged = torch.empty((N, L), dtype=torch.float32, device=p.device) if return_scores else None
+    check(load().b200clip_zs_merge_views(ptr(p), ptr(thr), N, L, float(weights[0]), float(weights[1]), ptr(pred), ptr(merged),
+                                         stream_ptr()), "zs_merge_views")
+    return (pred, merged) if return_scores else pred

@@ -202,6 +202,16 @@ int b200clip_adamw_tick(float* step, void* stream);
 int b200clip_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                         float beta2, float eps, float weight_decay, const float* step, void* stream);
 
+/* ---- zero-shot post-processing -- multimodal_attention/zero_shot_predict.py:66-213, L <= 32 labels.
+ * dynamic_thresholds (:112-159): scores [N,L] = per-sample max over the two views of the sigmoid scores, labels [N,L] in {0,1}
+ * (both f32) -> thresholds [L] (f64, device), optional best F1 per label.  merge_views (:183-213 on the per-view lists of
+ * disease_analysis.py:361-413, top_k = None): prob_views [N,2,L] f32, view weights w0 = 1.0, w1 = 0.8 -> pred [N,L] u8. */
+size_t b200clip_zs_thresholds_workspace_bytes(long long N, int L);
+int b200clip_zs_dynamic_thresholds(const float* scores, const float* labels, long long N, int L, double* thresholds,
+                                   double* best_f1, void* workspace, size_t workspace_bytes, void* stream);
+int b200clip_zs_merge_views(const float* prob_views, const double* thresholds, long long N, int L, double w0, double w1,
+                            uint8_t* pred, float* merged, void* stream);
+
 /* loss of the fused head step from its six numerators (summed over ranks): sums6 = {sum_i log r_i, sum_j log c_j,
  * sum_i S_ii, text-BCE pos numerator, text-BCE neg numerator, FC-BCE sum}; parts3 = {InfoNCE, text BCE, FC BCE}. */
 int b200clip_head_loss_finalize(const double* sums6, const float* label_sum, float temperature_nce, double b_glob,

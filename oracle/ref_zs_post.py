@@ -6,7 +6,8 @@ strings (the reference maps names back through disease_list.index, :218-221).
 
 Parity status: the reference code lives inside `main()` between data loaders and a checkpoint load, so it cannot be imported
 and run here -> "parity unpinned" by reference outputs; the F1 it calls (sklearn.metrics.f1_score, zero_division=0) is pinned
-against scikit-learn itself in tests/test_oracle_zs_post.py.  No CUDA path exists yet for these functions (round 2).
+against scikit-learn itself in tests/test_oracle_zs_post.py.  The CUDA path (csrc/zs_post.cu) is checked against this file in
+tests/test_gpu_zs_post.py.
 """
 from __future__ import annotations
 
