@@ -53,12 +53,22 @@ def unpack_mask(mask: torch.Tensor, num_labels: int) -> torch.Tensor:
     return ((mask.to(torch.int32).unsqueeze(-1) >> bits) & 1).bool()
 
 
-@torch.no_grad()
-def predict_zero_shot(images, models: Dict, disease_list: List[str], top_k: int = 3, prompts=None,
-                      use_enhanced_prompts: bool = False, text_features: torch.Tensor = None):
-    """Drop-in for 0426/disease_analysis.py:291-364.  Encoders stay stock PyTorch (models['resnet']); the projector and
-    everything after it run on the B200 kernels.  `text_features` [C,D] (normalised) replaces the reference's
-    per-call BERT pass (get_prediction_text_features, :335-340) when given; otherwise models['text_features'] is used."""
+def _class_text_features(models: Dict, disease_list, text_features, text_fn):
+    """The [C, D] normalised class-text matrix of one predict_zero_shot call.  Order of precedence: an explicit tensor,
+    the patched reference module's own get_prediction_text_features (stock-PyTorch BERT + the text projector, exactly what
+    the reference does per call, 0426/disease_analysis.py:335-340), a cached models['text_features']."""
+    if text_features is not None:
+        return text_features
+    if text_fn is not None and all(k in models for k in ("tokenizer", "text_model", "text_projector")):
+        return text_fn(disease_list, models["tokenizer"], models["text_model"], models["text_projector"])
+    if "text_features" in models:
+        return models["text_features"]
+    raise RuntimeError("predict_zero_shot: need models['tokenizer'/'text_model'/'text_projector'] (reference calling "
+                       "convention, with b200clip.install() on the module) or a text_features tensor")
+
+
+def _image_features(images, models: Dict, device):
+    """images -> encoder (stock PyTorch) -> projector (B200 kernels); returns ([N, D] features, is_batch)."""
     for m in models.values():
         if hasattr(m, "eval"):
             m.eval()
@@ -67,15 +77,97 @@ def predict_zero_shot(images, models: Dict, disease_list: List[str], top_k: int 
         if isinstance(images, list):
             images = images[0]
         images = images.unsqueeze(0)
-    dev = next(models["image_projector"].parameters()).device
+    dev = device if device is not None else next(models["image_projector"].parameters()).device
     emb = models["resnet"](images.to(dev))
-    feats = models["image_projector"](emb.reshape(emb.size(0), -1))
-    tf = text_features if text_features is not None else models["text_features"]
-    idx, val = zero_shot_topk(feats, tf, top_k)
-    idx_c, val_c = idx.cpu().numpy(), val.cpu().numpy()            # one D2H for the batch (reference: one per row)
+    return models["image_projector"](emb.reshape(emb.size(0), -1)), is_batch
+
+
+@torch.no_grad()
+def predict_zero_shot(images, models: Dict, disease_list: List[str], top_k: int = 3, prompts=None,
+                      use_enhanced_prompts: bool = False, text_features: torch.Tensor = None, _text_fn=None, _device=None):
+    """Drop-in for 0426/disease_analysis.py:291-364 (same positional order, same return types).  Encoders stay stock
+    PyTorch (models['resnet'], models['text_model']); the projector and everything after it run on the B200 kernels:
+    F.normalize -> similarities / tau -> softmax -> topk is ONE kernel and ONE D2H copy for the batch (the reference
+    does a topk + two .cpu() per row).  `text_features` [C, D] (normalised) skips the per-call BERT pass."""
+    feats, is_batch = _image_features(images, models, _device)
+    tf = _class_text_features(models, disease_list, text_features, _text_fn)
+    idx, val = zero_shot_topk(feats, tf, min(top_k, len(disease_list)))
+    idx_c, val_c = idx.cpu().numpy(), val.cpu().numpy()
     if is_batch:
         return [[disease_list[j] for j in row] for row in idx_c], [row for row in val_c]
     return [{"disease": disease_list[j], "confidence": float(s)} for j, s in zip(idx_c[0], val_c[0])]
+
+
+@torch.no_grad()
+def predict_zero_shot_multimodal(images, models: Dict, disease_list: List[str], threshold=0.5, top_k=None, prompts=None,
+                                 use_enhanced_prompts: bool = False, text_features: torch.Tensor = None, _text_fn=None,
+                                 _device=None):
+    """Drop-in for multimodal_attention/disease_analysis.py:291-421: optional MultiModalAttention, sigmoid(cos / 0.5),
+    `threshold` a float or a per-disease dict (diseases missing from the dict never pass, :370-373), `top_k=None` ->
+    argmax fallback for empty sets, top-k fill / truncation otherwise (:385-408).  The device produces the scores, the
+    pass mask (>= logit(thr), exact) and the arg-max in one kernel; the per-row python lists are assembled from ONE D2H
+    copy instead of `.item()` per element."""
+    import numpy as np
+    feats, is_batch = _image_features(images, models, _device)
+    tf = _class_text_features(models, disease_list, text_features, _text_fn)
+    if "multimodal_attention" in models:                                  # :344-347
+        feats, _ = models["multimodal_attention"](ops.normalize(feats), tf)
+    L = len(disease_list)
+    if isinstance(threshold, dict):
+        thr = [float(threshold[d]) if d in threshold else 2.0 for d in disease_list]     # 2.0 -> logit = +inf: never passes
+    else:
+        thr = [float(threshold)] * L
+    x, p = _prep(feats, tf)
+    out = ops.zeroshot_score(x, p, pair_mode=False, temperature=0.5, thresholds=thr, thr_inclusive=True, want_scores=True)
+    scores = out["scores"].cpu().numpy()
+    mask = out["mask"].cpu().numpy().astype(np.int64) & ((1 << L) - 1)
+    prob = (1.0 / (1.0 + np.exp(-scores.astype(np.float32)))).astype(np.float32)
+    batch_predictions, batch_scores = [], []
+    for i in range(prob.shape[0]):
+        pi = prob[i]
+        passed = [j for j in range(L) if (mask[i] >> j) & 1]
+        predictions = [disease_list[j] for j in passed]
+        sc = [float(pi[j]) for j in passed]
+        if len(predictions) == 0 or (top_k is not None and len(predictions) < top_k):
+            k = top_k if top_k is not None else 1
+            order = sorted(range(L), key=lambda j: (-scores[i, j], j))[:k]     # torch.topk: descending, first index on ties
+            if predictions:
+                have = set(predictions)
+                for j in order:
+                    if disease_list[j] not in have:
+                        predictions.append(disease_list[j])
+                        sc.append(float(pi[j]))
+                        if len(predictions) >= k:
+                            break
+            else:
+                predictions = [disease_list[j] for j in order]
+                sc = [float(pi[j]) for j in order]
+        elif top_k is not None and len(predictions) > top_k:
+            pairs = sorted(zip(predictions, sc), key=lambda t: t[1], reverse=True)[:top_k]
+            predictions, sc = [a for a, _ in pairs], [b for _, b in pairs]
+        batch_predictions.append(list(predictions))
+        batch_scores.append(list(sc))
+    if is_batch:
+        return batch_predictions, batch_scores
+    return [{"disease": d, "confidence": float(s)} for d, s in zip(batch_predictions[0], batch_scores[0])]
+
+
+def bind_predict_zero_shot(module):
+    """The predict_zero_shot that replaces `module.predict_zero_shot`: picks the variant from the reference function's own
+    signature (`threshold` parameter = multimodal_attention) and binds the module's get_prediction_text_features and DEVICE,
+    so unmodified callers (0426/zero_shot_predict.py:71-78, multimodal_attention/zero_shot_predict.py:73-157) work."""
+    import functools
+    import inspect
+    ref = getattr(module, "predict_zero_shot", None)
+    multimodal = ref is not None and "threshold" in inspect.signature(ref).parameters
+    text_fn = getattr(module, "get_prediction_text_features", None)
+    device = getattr(module, "DEVICE", None)
+    if device is not None and not (isinstance(device, str) and device.startswith("cuda") or getattr(device, "type", "") == "cuda"):
+        device = None                                                     # reference configured for CPU: use the projector's device
+    impl = predict_zero_shot_multimodal if multimodal else predict_zero_shot
+    fn = functools.partial(impl, _text_fn=text_fn, _device=device)
+    functools.update_wrapper(fn, impl)
+    return fn
 
 
 # --------------------------------------------------------------------------------------------------------------

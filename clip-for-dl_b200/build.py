@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "b200clip", "_lib")
 LIB = os.path.join(OUT_DIR, "libb200clip.so")
-SOURCES = ["gemm.cu", "rowops.cu", "smallc.cu", "heads_mma.cu", "attention.cu", "softclip.cu", "zs_post.cu", "zeroshot.cu", "infonce.cu", "proj.cu"]
+SOURCES = ["gemm.cu", "rowops.cu", "smallc.cu", "heads_mma.cu", "attention.cu", "softclip.cu", "zs_post.cu", "metrics.cu", "zeroshot.cu", "infonce.cu", "proj.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-DNDEBUG"]

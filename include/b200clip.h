@@ -241,6 +241,20 @@ int b200clip_zeroshot_score(const void* x_bf16, long long ldx, long long n, cons
                             int mask_is_u32, uint8_t* topk_idx, float* topk_val, float* scores,
                             unsigned long long* guard_count, void* stream);
 
+/* ---- step edges --------------------------------------------------------------------------
+ * calculate_multilabel_metrics(predictions, labels) -- 0426/train.py:251-302 -- and the in-loop accuracy counters of
+ * train_epoch / validate (0426/train.py:437-447).  predictions [B,C] are probabilities (or any score compared with
+ * `threshold`), labels [B,C] in {0,1}, C <= 32.  out (DEVICE, 7 + C doubles): sample_acc, label_acc, hamming_score,
+ * exact_match, top1_acc (the reference's any-over-batch quirk, :277), top3_acc, f1_score, then per-class accuracy in %. */
+size_t b200clip_multilabel_metrics_workspace_bytes(long long B);
+int b200clip_multilabel_metrics(const float* predictions, long long ld_pred, const float* labels, long long ld_labels,
+                                long long B, int C, float threshold, double* out, void* workspace,
+                                size_t workspace_bytes, void* stream);
+/* per-disease mean of L2-normalised prompt features (get_text_features_with_findings, 0426/disease_analysis.py:486-497);
+ * prompts of disease d are rows offsets[d] .. offsets[d+1]-1 of prompt_features [*, D] (offsets: DEVICE int[n+1]). */
+int b200clip_prompt_mean_pool(const float* prompt_features, const int* offsets, int num_diseases, int D, float eps,
+                              int renormalize, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

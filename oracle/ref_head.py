@@ -277,6 +277,88 @@ def zero_shot_posneg(image_features: Tensor, prompts: Tensor, temperature: float
     return q.argmax(dim=-1), q > threshold, q
 
 
+def zero_shot_lists_topk(image_features: Tensor, text_features: Tensor, disease_list: Sequence[str], top_k: int = 3,
+                         temperature: float = 0.07):
+    """The python lists 0426/disease_analysis.py:346-356 builds from the probabilities (batch branch): per image the top-k
+    disease names and their softmax probabilities."""
+    idx, vals = zero_shot_softmax_topk(image_features, text_features, top_k, temperature)
+    return [[disease_list[j] for j in row.tolist()] for row in idx], [row.tolist() for row in vals]
+
+
+def zero_shot_lists_multimodal(image_features: Tensor, text_features: Tensor, disease_list: Sequence[str],
+                               threshold: Union[float, Dict[str, float]] = 0.5, top_k: Optional[int] = None,
+                               temperature: float = 0.5):
+    """multimodal_attention/disease_analysis.py:349-413 after the (optional) attention module: per image, the diseases whose
+    sigmoid(cos/0.5) reaches the threshold (:368-383; dict thresholds skip diseases that are not keys, :370-373), topped up
+    from the ranking when the set is empty or shorter than top_k (:385-403), truncated to the best top_k when longer (:405-408)."""
+    _, probs, _ = zero_shot_sigmoid_threshold(image_features, text_features, 0.0, temperature)
+    names, scores = [], []
+    for pr in probs:
+        if isinstance(threshold, dict):
+            keep = [j for j, d in enumerate(disease_list) if d in threshold and bool(pr[j] >= threshold[d])]
+        else:
+            keep = (pr >= threshold).nonzero().flatten().tolist()
+        pn, ps = [disease_list[j] for j in keep], [float(pr[j]) for j in keep]
+        if not pn or (top_k is not None and len(pn) < top_k):
+            k = 1 if top_k is None else top_k
+            vals, idx = pr.topk(k)
+            if pn:
+                for j, v in zip(idx.tolist(), vals.tolist()):
+                    if disease_list[j] not in pn:
+                        pn.append(disease_list[j])
+                        ps.append(float(v))
+                        if len(pn) >= k:
+                            break
+            else:
+                pn, ps = [disease_list[j] for j in idx.tolist()], [float(v) for v in vals]
+        elif top_k is not None and len(pn) > top_k:
+            order = sorted(range(len(pn)), key=lambda t: ps[t], reverse=True)[:top_k]
+            pn, ps = [pn[t] for t in order], [ps[t] for t in order]
+        names.append(pn)
+        scores.append(ps)
+    return names, scores
+
+
+# ----------------------------------------------------------------------------------------------
+# step edges (SURVEY.md 8f rank 3/4)
+# ----------------------------------------------------------------------------------------------
+
+
+def calculate_multilabel_metrics(predictions: Tensor, labels: Tensor) -> Dict[str, float]:
+    """0426/train.py:251-302.  Note :277 reduces the top-1 hits with any(dim=0) over the BATCH (so top1_acc is 0 or 100);
+    the quirk is part of the reference's behaviour and is kept."""
+    hard = (predictions > 0.5).float()                                                   # :261
+    same = (hard == labels).float()
+    n = labels.shape[0]
+    rows = torch.arange(n)
+    top1 = predictions.argmax(dim=1)                                                     # :276
+    top3 = predictions.topk(k=min(3, predictions.shape[1]), dim=1).indices               # :280
+    tp = (hard * labels).sum(dim=1)                                                      # :286
+    prec = tp / (hard.sum(dim=1) + 1e-8)                                                 # :288
+    rec = tp / (labels.sum(dim=1) + 1e-8)                                                # :289
+    f1 = 2 * prec * rec / (prec + rec + 1e-8)                                            # :290
+    return {
+        "sample_acc": (same.mean(dim=1) * 100).mean().item(),                            # :264
+        "label_acc": (same.mean(dim=0) * 100).mean().item(),                             # :267
+        "hamming_score": same.mean().item() * 100,                                       # :270
+        "exact_match": (hard == labels).all(dim=1).float().mean().item() * 100,          # :273
+        "top1_acc": torch.any(labels[rows, top1] == 1, dim=0).float().mean().item() * 100,   # :277
+        "top3_acc": torch.any(labels.gather(1, top3) == 1, dim=1).float().mean().item() * 100,   # :281
+        "f1_score": f1.mean().item() * 100,                                              # :291
+    }
+
+
+def prompt_mean_pool(prompt_features: Tensor, counts: Sequence[int], renormalize: bool = False) -> Tensor:
+    """get_text_features_with_findings' pooling, 0426/disease_analysis.py:490-497 (same arithmetic in get_enhanced_text_features :230-237): per disease, F.normalize the projected prompt
+    features and average them (keepdim), concatenated over diseases.  `renormalize` adds the cosine head's re-normalisation."""
+    out, o = [], 0
+    for c in counts:
+        f = l2_normalize(prompt_features[o:o + c]).mean(dim=0, keepdim=True)             # :491-494
+        out.append(l2_normalize(f) if renormalize else f)
+        o += c
+    return torch.cat(out, dim=0)                                                         # :497
+
+
 # ----------------------------------------------------------------------------------------------
 # a-F / a-X   ("next" rows, SURVEY.md 8f)
 # ----------------------------------------------------------------------------------------------
