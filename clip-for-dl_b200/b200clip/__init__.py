@@ -9,8 +9,10 @@ from .modules import (MODEL_CONFIG, ClassificationAdapter, ImageProjection, Mult
 from .losses import (contrastive_clip_loss_function, contrastive_loss, fc_adapter_bce,  # noqa: F401
                      multilabel_asymmetric_loss,
                      multilabel_contrastive_loss, predict_multilabel)
-from .zero_shot import (dynamic_thresholds, merge_two_views, predict_zero_shot, unpack_mask,  # noqa: F401
-                        zero_shot_posneg, zero_shot_threshold, zero_shot_topk)
+from .zero_shot import (dynamic_thresholds, merge_two_views, predict_zero_shot, predict_zero_shot_multimodal,  # noqa: F401
+                        unpack_mask, zero_shot_posneg, zero_shot_threshold, zero_shot_topk)
+from . import metrics  # noqa: F401
+from .metrics import calculate_multilabel_metrics, inloop_accuracy, prompt_mean_pool  # noqa: F401
 from .head import ClipHead, ClipHeadFn, GraphedHeadStep  # noqa: F401
 from .ops import normalize  # noqa: F401
 from .install import install  # noqa: F401

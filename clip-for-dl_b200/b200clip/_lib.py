@@ -46,16 +46,17 @@ SIGNATURES = {
     "b200clip_l2norm_bwd": (i32, [vp, i32, vp, i32, ll, vp, vp, i32, ll, i32, f32, vp, vp, vp]),
     "b200clip_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, ll, i32, f32, f32, vp]),
     "b200clip_layernorm_bwd_workspace_bytes": (sz, [ll, i32]),
-    "b200clip_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, ll, i32, f32, C.c_uint, vp, sz, vp]),
+    "b200clip_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, ll, i32, f32, C.c_uint, vp, vp, sz, vp]),
+    "b200clip_dropout_seed_advance": (i32, [vp, vp]),
     "b200clip_colsum_workspace_bytes": (sz, [ll, i32]),
     "b200clip_colsum": (i32, [vp, i32, ll, ll, i32, vp, i32, vp, sz, vp]),
     "b200clip_cast_f32_bf16": (i32, [vp, vp, ll, vp]),
     "b200clip_dropout_mask": (i32, [vp, ll, i32, f32, C.c_uint, vp]),
     "b200clip_sum_f32": (i32, [vp, ll, vp, vp]),
-    "b200clip_proj_fwd": (i32, [vp, ll, i32, i32, vp, vp, vp, vp, vp, vp, f32, f32, C.c_uint, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "b200clip_proj_fwd": (i32, [vp, ll, i32, i32, vp, vp, vp, vp, vp, vp, f32, f32, C.c_uint, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "b200clip_proj_bwd_workspace_bytes": (sz, [ll, i32, i32]),
-    "b200clip_proj_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, ll, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, C.c_uint, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
-    "b200clip_layernorm_l2_bwd": (i32, [vp, i32, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, ll, i32, f32, C.c_uint, vp, sz, vp]),
+    "b200clip_proj_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, ll, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, C.c_uint, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "b200clip_layernorm_l2_bwd": (i32, [vp, i32, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, ll, i32, f32, C.c_uint, vp, vp, sz, vp]),
     "b200clip_infonce_workspace_bytes": (sz, [ll, ll]),
     "b200clip_infonce_fwd_stats": (i32, [vp, vp, i32, ll, ll, f32, vp, vp, vp, sz, vp]),
     "b200clip_infonce_loss": (i32, [vp, vp, i32, ll, ll, ll, f32, vp, vp, ll, ll, vp, vp, vp, vp, vp, sz, vp]),
@@ -111,6 +112,17 @@ def check(rc: int, what: str) -> None:
 
 
 def require_cuda(*tensors) -> None:
+    """Every op launches on the CURRENT device's current stream (stream_ptr) and the C side keeps per-device caches keyed by
+    cudaGetDevice: tensors on another GPU would be read through the wrong context.  One process per GPU is the supported
+    layout (torchrun sets the device once); anything else is rejected here instead of faulting in a kernel."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("b200clip: tensors must live on a CUDA device (B200); there is no CPU path")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError(f"b200clip: tensor on cuda:{t.device.index} but the current device is cuda:{cur}; "
+                               "call torch.cuda.set_device() (one process per GPU) or wrap the call in torch.cuda.device(...)")

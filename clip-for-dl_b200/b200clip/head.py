@@ -31,7 +31,7 @@ _world, _rank = dp.world, dp.rank
 
 
 def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop_p, drop_seed, params, need_grad,
-                 need_dx=(True, True), defer_loss=False):
+                 need_dx=(True, True), defer_loss=False, drop_seed_dev=None):
     """Forward pass of the fused head on this rank's local pairs.  Returns (loss, parts, state); `state` is what
     head_backward needs (None when need_grad is False); parts = [InfoNCE, text BCE, FC BCE].  With defer_loss the loss is
     not finalised here: loss is None and parts is a callable returning (loss, parts, status), to be called after the
@@ -52,10 +52,10 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
     # text first so its all-gather can overlap the image projection
     # independent dropout streams for the two projections (seed, seed+1)
     y_txt, that_loc, inv_txt, saved_t = ops.proj_fwd(xt, tw1b, f(tb1), tw2b, f(tb2), f(tg), f(tbeta), want_yhat=True,
-                                                     drop_p=drop_p, drop_seed=drop_seed + 1)
+                                                     drop_p=drop_p, drop_seed=drop_seed + 1, drop_seed_dev=drop_seed_dev)
     that_all, work = dp.gather_rows(that_loc, group, async_op=True)
     y_img, ihat, inv_img, saved_i = ops.proj_fwd(xi, iw1b, f(ib1), iw2b, f(ib2), f(ig), f(ibeta), want_yhat=True,
-                                                 drop_p=drop_p, drop_seed=drop_seed)
+                                                 drop_p=drop_p, drop_seed=drop_seed, drop_seed_dev=drop_seed_dev)
     C = class_text.shape[0]
     Cf = fw.shape[0]
     sums6 = torch.empty((6,), dtype=torch.float64, device=x_img.device)   # rank-local loss numerators (NCE 3 | BCE 3)
@@ -94,7 +94,7 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
     tensors = (xi, xt, iw1b, iw2b, tw1b, tw2b, f(ig), f(tg), y_img, y_txt, ihat, that_all, inv_img, inv_txt, rinvh, cinvh,
                d_bce, coef, db_raw, *saved_i, *saved_t)
     meta = dict(tau_nce=tau_nce, group=group, W=W, row0=row0, need_dx=tuple(need_dx), in_dtypes=(x_img.dtype, x_txt.dtype),
-                drop=(float(drop_p), int(drop_seed)), has_fc_bias=fb is not None)
+                drop=(float(drop_p), int(drop_seed)), drop_seed_dev=drop_seed_dev, has_fc_bias=fb is not None)
     return loss, parts, (tensors, meta)
 
 
@@ -106,6 +106,7 @@ def head_backward(tensors, meta, g):
     group, row0 = meta["group"], meta["row0"]
     need_dxi, need_dxt = meta["need_dx"]
     drop_p, drop_seed = meta["drop"]
+    seed_dev = meta.get("drop_seed_dev")
     g = ops._f32c(g).reshape(())
     d_ihat, d_that = ops.infonce_backward(ihat, that_all, meta["tau_nce"], rinvh, cinvh, g, row0=row0, allow_splits=True)
     d_that_loc, work = dp.scatter_sum_rows(d_that, group, async_op=True)
@@ -116,14 +117,14 @@ def head_backward(tensors, meta, g):
     else:
         dfw, dfb = ops.skinny_outer(coef, y_img, want_bias=True, out_scale=g)
     gi = ops.proj_bwd(None, xi, iw1b, iw2b, ig, saved_i, need_dxi, meta["in_dtypes"][0], drop_p=drop_p, drop_seed=drop_seed,
-                      l2=(d_ihat, ihat, inv_img, d_bce, g))
+                      l2=(d_ihat, ihat, inv_img, d_bce, g), drop_seed_dev=seed_dev)
     # image-side parameter gradients travel while the text side is still computing (SUM, not mean: every loss term is
     # normalised by the GLOBAL batch)
     img_grads, img_work = dp.allreduce_flat([gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], dfw, dfb], group, async_op=True)
     dp.wait(work)
     that_loc = that_all[row0:row0 + y_txt.shape[0]]                  # this rank's normalised text rows (bf16)
     gt = ops.proj_bwd(None, xt, tw1b, tw2b, tg, saved_t, need_dxt, meta["in_dtypes"][1], drop_p=drop_p, drop_seed=drop_seed + 1,
-                      l2=(d_that_loc, that_loc, inv_txt, None, None))
+                      l2=(d_that_loc, that_loc, inv_txt, None, None), drop_seed_dev=seed_dev)
     txt_grads = dp.allreduce_flat([gt[1], gt[2], gt[3], gt[4], gt[5], gt[6]], group)
     dp.wait(img_work)
     grads = [*img_grads[:6], *txt_grads, img_grads[6], img_grads[7]]
@@ -135,6 +136,10 @@ def head_backward(tensors, meta, g):
 class ClipHeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop_p, drop_seed, *params):
+        if class_text.requires_grad:
+            # the reference computes the class prompts under no_grad (0426/train.py:333); a silent None gradient would be a bug
+            raise RuntimeError("b200clip.ClipHead: class_text_features must not require grad (compute them under torch.no_grad() "
+                               "as 0426/train.py:333 does, or use b200clip.multilabel_contrastive_loss, which returns d text)")
         need_grad = any(t is not None and t.requires_grad for t in (x_img, x_txt, *params))
         loss, parts, state = head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop_p, drop_seed, params,
                                           need_grad, need_dx=(x_img.requires_grad, x_txt.requires_grad))
@@ -193,15 +198,24 @@ class GraphedHeadStep:
         step = GraphedHeadStep(head, x_img, x_txt, class_text, labels)
         loss = step(x_img, x_txt, class_text, labels)      # same semantics as head(...) followed by loss.backward()
 
-    Parameter gradients are OVERWRITTEN by each replay (equivalent to zero_grad + backward).  Dropout must be off
-    (the keep-mask seed is a launch argument and would be frozen into the graph)."""
+    Dropout (head.train() with dropout_rate > 0, the reference's nn.Dropout(0.1), 0426/train.py:81,93) is captured too: the
+    keep-mask seed lives in a device word (`seed_dev`) that a one-thread kernel at the head of the graph advances on every
+    replay; the projection kernels add it to their (frozen) seed argument.
+
+    Parameter gradients are OVERWRITTEN by each replay (equivalent to zero_grad + backward); every call re-binds the
+    parameters' .grad to the graph's output tensors, so `opt.zero_grad(); step(...); opt.step()` works.  The returned loss
+    ALIASES a static buffer that the next replay overwrites -- `.clone()` it to keep a history.
+    """
 
     def __init__(self, head: "ClipHead", image_embeddings, text_embeddings, class_text_features, labels, warmup: int = 3,
                  input_grads: bool = True):
-        if head.training and head.dropout_rate > 0:
-            raise RuntimeError("GraphedHeadStep: dropout seeds cannot be captured; use head.eval() or dropout_rate=0")
         ops.require_cuda(image_embeddings, text_embeddings, class_text_features, labels)
         self.head = head
+        self.drop_p = float(head.dropout_rate) if head.training else 0.0
+        self.drop_seed0 = ops.new_dropout_seed() if self.drop_p > 0 else 0
+        # device-resident seed word, advanced by the first node of the graph (read it after a replay to reconstruct the mask:
+        # effective seeds are drop_seed0 + seed_dev for the image projection, drop_seed0 + 1 + seed_dev for the text projection)
+        self.seed_dev = torch.zeros((), dtype=torch.int32, device=image_embeddings.device) if self.drop_p > 0 else None
         self.x_img = image_embeddings.detach().clone()
         self.x_txt = text_embeddings.detach().clone()
         self.class_text = class_text_features.detach().clone()
@@ -227,9 +241,12 @@ class GraphedHeadStep:
         """forward + backward as plain calls (no autograd engine: its worker thread and AccumulateGrad streams do not
         belong in a capture)."""
         h = self.head
+        if self.seed_dev is not None:
+            ops.dropout_seed_advance(self.seed_dev)
         _, finish, (tensors, meta) = head_forward(self.x_img, self.x_txt, self.class_text, self.labels, h.tau_nce, h.tau_bce,
-                                                  h.group, 0.0, 0, h.params(), True,
-                                                  need_dx=(self.input_grads, self.input_grads), defer_loss=True)
+                                                  h.group, self.drop_p, self.drop_seed0, h.params(), True,
+                                                  need_dx=(self.input_grads, self.input_grads), defer_loss=True,
+                                                  drop_seed_dev=self.seed_dev)
         dxi, dxt, grads = head_backward(tensors, meta, self._one)
         loss, self.parts, self.status = finish()          # loss value: after the backward kernels, off the critical path
         return loss, dxi, dxt, grads
@@ -262,4 +279,5 @@ class GraphedHeadStep:
                                        f"{tuple(dst.shape)} (capture a new GraphedHeadStep for a different batch size)")
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        self.bind_grads()               # optimizer.zero_grad(set_to_none=True) between steps must not detach the graph's outputs
         return self.loss

@@ -137,6 +137,12 @@ def dropout_mask(rows: int, cols: int, p: float, seed: int, device) -> torch.Ten
     return out
 
 
+def dropout_seed_advance(seed_dev: torch.Tensor) -> None:
+    """Advance a device-resident dropout seed word in stream order (one node of GraphedHeadStep's graph)."""
+    require_cuda(seed_dev)
+    check(load().b200clip_dropout_seed_advance(ptr(seed_dev), stream_ptr()), "dropout_seed_advance")
+
+
 def new_dropout_seed() -> int:
     """A fresh 32-bit seed from torch's CPU generator (honours torch.manual_seed; no device sync)."""
     return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
@@ -145,7 +151,9 @@ def new_dropout_seed() -> int:
 # --------------------------------------------------------------------------------------------------------------
 # a-P1 / a-P2 projection block
 # --------------------------------------------------------------------------------------------------------------
-def proj_fwd(x_bf16, w1_bf16, b1, w2_bf16, b2, gamma, beta, want_yhat: bool, drop_p: float = 0.0, drop_seed: int = 0):
+def proj_fwd(x_bf16, w1_bf16, b1, w2_bf16, b2, gamma, beta, want_yhat: bool, drop_p: float = 0.0, drop_seed: int = 0,
+             drop_seed_dev: Optional[torch.Tensor] = None):
+    """drop_seed_dev: optional device int32 word added to drop_seed inside the kernels (GraphedHeadStep's per-replay seed)."""
     B, E = x_bf16.shape
     D = w1_bf16.shape[0]
     dev = x_bf16.device
@@ -158,14 +166,14 @@ def proj_fwd(x_bf16, w1_bf16, b1, w2_bf16, b2, gamma, beta, want_yhat: bool, dro
     yhat = torch.empty((B, D), dtype=torch.bfloat16, device=dev) if want_yhat else None
     inv = torch.empty((B,), dtype=torch.float32, device=dev) if want_yhat else None
     check(load().b200clip_proj_fwd(ptr(x_bf16), B, E, D, ptr(w1_bf16), ptr(b1), ptr(w2_bf16), ptr(b2), ptr(gamma), ptr(beta),
-                                   LN_EPS, float(drop_p), int(drop_seed) & 0xFFFFFFFF, ptr(p), ptr(h), ptr(z), ptr(y), ptr(yhat),
+                                   LN_EPS, float(drop_p), int(drop_seed) & 0xFFFFFFFF, ptr(drop_seed_dev), ptr(p), ptr(h), ptr(z), ptr(y), ptr(yhat),
                                    ptr(mean), ptr(rstd), ptr(inv),
                                    stream_ptr()), "proj_fwd")
     return y, yhat, inv, (p, h, z, mean, rstd)
 
 
 def proj_bwd(dy, x_bf16, w1_bf16, w2_bf16, gamma, saved, need_dx: bool, dx_dtype=torch.float32, drop_p: float = 0.0,
-             drop_seed: int = 0, l2=None):
+             drop_seed: int = 0, l2=None, drop_seed_dev: Optional[torch.Tensor] = None):
     """dy: gradient w.r.t. the block's output y.  Fused form: dy=None and l2=(dyhat, yhat_bf16, inv_norm, addend,
     addend_scale) -- the gradient w.r.t. the L2-normalised output ([S,]B,D partial sums allowed), the normalised bf16
     output, 1/||y|| and an optional f32 addend times a device scalar; the L2-norm backward runs inside LayerNorm's."""
@@ -189,7 +197,7 @@ def proj_bwd(dy, x_bf16, w1_bf16, w2_bf16, gamma, saved, need_dx: bool, dx_dtype
     nb = load().b200clip_proj_bwd_workspace_bytes(B, E, D)
     ws = _ws(nb, dev)
     check(load().b200clip_proj_bwd(ptr(dy), ptr(dyhat), parts, ptr(yhat), ptr(inv), ptr(addend), ptr(ascale), ptr(x_bf16), B, E, D, ptr(w1_bf16), ptr(w2_bf16), ptr(gamma), ptr(p), ptr(h), ptr(z),
-                                   ptr(mean), ptr(rstd), float(drop_p), int(drop_seed) & 0xFFFFFFFF, ptr(None if dx_bf else dx), ptr(dx if dx_bf else None), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dg), ptr(dbeta),
+                                   ptr(mean), ptr(rstd), float(drop_p), int(drop_seed) & 0xFFFFFFFF, ptr(drop_seed_dev), ptr(None if dx_bf else dx), ptr(dx if dx_bf else None), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dg), ptr(dbeta),
                                    ptr(ws), ws.numel(), stream_ptr()), "proj_bwd")
     return dx, dw1, db1, dw2, db2, dg, dbeta
 

@@ -18,7 +18,7 @@ namespace b200 {
 int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, int K, long long lda, long long ldb,
               int epi, float alpha, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
               const void* resid, long long ld_res, const float* aux, long long ld_aux, int split_k, cudaStream_t stream,
-              float drop_p = 0.f, unsigned int drop_seed = 0u, int aux_is_bf16 = 0);
+              float drop_p = 0.f, unsigned int drop_seed = 0u, int aux_is_bf16 = 0, const unsigned int* drop_seed_dev = nullptr);
 
 constexpr int AT_MAXC = 16;
 constexpr int AT_MAXD = 512;
@@ -337,12 +337,8 @@ extern "C" int b200clip_attention_bwd(const float* d_out, const float* d_w, cons
   p.ip = ip; p.tp = tp; p.wa = wa; p.ba = ba; p.B = (int)B; p.C = C; p.D = D; p.w = const_cast<float*>(w); p.de = de; p.dw_up = d_w;
   p.dip = static_cast<__nv_bfloat16*>(dip_bf); p.partial = partial;
   const size_t smem = (static_cast<size_t>(C + 1) * D + static_cast<size_t>(AT_BWD_THREADS / 32) * (C + 2) * D) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>((static_cast<size_t>(AT_MAXC + 1) * AT_MAXD + 4ull * (AT_MAXC + 2) * AT_MAXD) * 4)));
-    configured = true;
-  }
+  static SmemAttrOnce attr;
+  B200_CHECK_CUDA(attr.ensure(attn_bwd_kernel, static_cast<int>((static_cast<size_t>(AT_MAXC + 1) * AT_MAXD + 4ull * (AT_MAXC + 2) * AT_MAXD) * 4)));
   attn_bwd_kernel<<<grid, AT_BWD_THREADS, smem, s>>>(p);
   B200_LAUNCH_CHECK();
   attn_reduce_kernel<<<((C + 2) * D + 255) / 256, 256, 0, s>>>(partial, grid, (C + 2) * D, red);

@@ -12,11 +12,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
                        cudaStream_t stream) {
   auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN, EPI>;
   constexpr int smem = gemm_smem_bytes<BN, STAGES>();
-  static bool configured = false;   // per-instantiation; idempotent, so a benign race
-  if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static SmemAttrOnce attr;          // per instantiation, per device
+  B200_CHECK_CUDA(attr.ensure(kern, smem));
   GemmParams q = p;
   q.splits = splits;
   const int items = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN) * splits;
@@ -28,7 +25,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, int K, long long lda, long long ldb,
               int epi, float alpha, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
               const void* resid, long long ld_res, const float* aux, long long ld_aux, int split_k,
-              cudaStream_t stream, float drop_p, unsigned int drop_seed, int aux_is_bf16) {
+              cudaStream_t stream, float drop_p, unsigned int drop_seed, int aux_is_bf16, const unsigned int* drop_seed_dev) {
   B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   B200_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
   // the epilogues use 256-bit global accesses: 32-byte aligned bases, leading dimensions a multiple of 16 elements
@@ -47,7 +44,7 @@ int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, in
   p.alpha = alpha;
   p.out0 = out0; p.ld0 = ld0; p.out1 = out1; p.ld1 = ld1; p.bias = bias;
   p.resid = reinterpret_cast<const __nv_bfloat16*>(resid); p.ld_res = ld_res; p.aux = aux; p.ld_aux = ld_aux;
-  p.drop_p = drop_p; p.drop_seed = drop_seed; p.aux_is_bf16 = aux_is_bf16;
+  p.drop_p = drop_p; p.drop_seed = drop_seed; p.aux_is_bf16 = aux_is_bf16; p.drop_seed_dev = drop_seed_dev;
 
   CUtensorMap ta, tb;
   int rc;
@@ -86,5 +83,5 @@ extern "C" int b200clip_gemm_bf16(const void* a, const void* b, int a_mn_major, 
                                   void* out1, long long ld1, const float* bias, const void* resid, long long ld_res,
                                   const float* aux, long long ld_aux, int split_k, void* stream) {
   return b200::gemm_bf16(a, b, a_mn_major, b_mn_major, M, N, K, lda, ldb, epilogue, alpha, out0, ld0, out1, ld1, bias,
-                         resid, ld_res, aux, ld_aux, split_k, static_cast<cudaStream_t>(stream), 0.f, 0u, 0);
+                         resid, ld_res, aux, ld_aux, split_k, static_cast<cudaStream_t>(stream), 0.f, 0u, 0, nullptr);
 }

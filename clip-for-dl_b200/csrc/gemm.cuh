@@ -36,6 +36,7 @@ struct GemmParams {
   int aux_is_bf16;          // EPI_GELU_BWD: aux points at bf16 data (dz as written for the GEMMs) instead of f32
   float drop_p;             // EPI_BIAS_RESID_F32: dropout on (acc + bias) before the residual add (0 = off)
   unsigned int drop_seed;
+  const unsigned int* drop_seed_dev;   // optional device word added to drop_seed (a captured CUDA graph draws a fresh mask per replay)
 };
 
 constexpr int GEMM_BM = 128;
@@ -104,10 +105,11 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
       if (p.drop_p > 0.f) {                       // nn.Dropout after the ReLU (MultiViewFusion, 0426/train.py:994)
+        const unsigned int eff_seed = p.drop_seed + (p.drop_seed_dev ? __ldg(p.drop_seed_dev) : 0u);
         const float sc = 1.0f / (1.0f - p.drop_p);
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          f[i] = dropout_keep(p.drop_seed, static_cast<uint32_t>(row), static_cast<uint32_t>(col + i), static_cast<uint32_t>(p.N), p.drop_p) ? f[i] * sc : 0.f;
+          f[i] = dropout_keep(eff_seed, static_cast<uint32_t>(row), static_cast<uint32_t>(col + i), static_cast<uint32_t>(p.N), p.drop_p) ? f[i] * sc : 0.f;
       }
     }
 #pragma unroll
@@ -131,10 +133,11 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
     const __nv_bfloat16* rs = p.resid + static_cast<long long>(row) * p.ld_res + col;
     float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col;
     if (p.drop_p > 0.f) {                         // nn.Dropout between fc and the residual add (0426/train.py:93)
+      const unsigned int eff_seed = p.drop_seed + (p.drop_seed_dev ? __ldg(p.drop_seed_dev) : 0u);
       const float sc = 1.0f / (1.0f - p.drop_p);
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        f[i] = dropout_keep(p.drop_seed, static_cast<uint32_t>(row), static_cast<uint32_t>(col + i), static_cast<uint32_t>(p.N), p.drop_p) ? f[i] * sc : 0.f;
+        f[i] = dropout_keep(eff_seed, static_cast<uint32_t>(row), static_cast<uint32_t>(col + i), static_cast<uint32_t>(p.N), p.drop_p) ? f[i] * sc : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 32; i += 16) {

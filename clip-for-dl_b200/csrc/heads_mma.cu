@@ -409,11 +409,8 @@ extern "C" int b200clip_bce_heads_mma_fwd(const void* yhat_bf16, const float* in
   p.dy = d_y; p.coefn = static_cast<__nv_bfloat16*>(coefn_bf16); p.db = db_fc; p.sums = sums;
   p.partial = static_cast<double*>(workspace);
   p.counter = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(workspace) + static_cast<size_t>(grid) * (3 + HM_C) * sizeof(double));
-  static bool configured = false;
-  if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(bce_heads_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HM_SMEM));
-    configured = true;
-  }
+  static SmemAttrOnce attr;
+  B200_CHECK_CUDA(attr.ensure(bce_heads_mma_kernel, HM_SMEM));
   B200_CHECK_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), s));
   bce_heads_mma_kernel<<<grid, HM_THREADS, HM_SMEM, s>>>(p);
   B200_LAUNCH_CHECK();

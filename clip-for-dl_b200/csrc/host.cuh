@@ -104,15 +104,36 @@ inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, 
   return B200_OK;
 }
 
-inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+// Per-device immutable attribute cache (SURVEY.md 8b "Threading"): SM counts, and which (kernel, device) pairs already carry
+// their opt-in dynamic shared-memory limit -- cudaFuncSetAttribute is a PER-DEVICE setting, so a process that touches a second
+// GPU must set it again there.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
+inline int num_sms() {
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = current_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+// One flag array per call site (a `static SmemAttrOnce` next to the launch): sets MaxDynamicSharedMemorySize once per device.
+struct SmemAttrOnce {
+  std::once_flag once[kMaxDevices];
+  cudaError_t err[kMaxDevices] = {};
+  template <typename F>
+  cudaError_t ensure(F* func, int bytes) {
+    const int dev = current_device();
+    std::call_once(once[dev], [&] { err[dev] = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
+    return err[dev];
+  }
+};
 
 }  // namespace b200

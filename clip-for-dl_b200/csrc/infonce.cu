@@ -1226,11 +1226,8 @@ extern "C" int b200clip_infonce_fwd_stats(const void* i_hat, const void* t_hat, 
   p.r_part = r_part; p.c_part = c_part; p.nrows_pad = pl.nrows_pad; p.x = static_cast<const __nv_bfloat16*>(i_hat);
   auto kern = nce_fwd_kernel<FWD_BN, FWD_STAGES, FWD_NWG, FWD_XT>;
   constexpr int smem = nce_fwd_smem_bytes<FWD_BN, FWD_STAGES, FWD_NWG, FWD_XT>();
-  static bool configured = false;
-  if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static SmemAttrOnce attr;
+  B200_CHECK_CUDA(attr.ensure(kern, smem));
   kern<<<pl.grid, 128 + FWD_NWG * 128, smem, s>>>(tx, ty, p);
   B200_LAUNCH_CHECK();
   const int n = (int)std::max(b_loc, b_glob);
@@ -1301,14 +1298,13 @@ extern "C" int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D,
   p.nsplit[1] = 1; p.split_stride[1] = 0;
   p.prof = g_nce_prof;
   constexpr int smem = nce_bwd_smem_bytes();
-  static bool configured = false;
-  static int variant = 4;            // 4: CTA-pair kernel (default); 1: independent D-half CTAs (B200CLIP_BWD_VARIANT=1)
-  if (!configured) {
-    if (const char* e = getenv("B200CLIP_BWD_VARIANT")) variant = atoi(e) == 1 ? 1 : 4;
-    B200_CHECK_CUDA(cudaFuncSetAttribute(nce_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nce_bwd4_smem_bytes()));
-    B200_CHECK_CUDA(cudaFuncSetAttribute(nce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static SmemAttrOnce attr4, attr1;
+  static const int variant = [] {      // 4: CTA-pair kernel (default); 1: independent D-half CTAs (B200CLIP_BWD_VARIANT=1, tests only)
+    const char* e = getenv("B200CLIP_BWD_VARIANT");
+    return (e && atoi(e) == 1) ? 1 : 4;
+  }();
+  B200_CHECK_CUDA(attr4.ensure(nce_bwd4_kernel, nce_bwd4_smem_bytes()));
+  B200_CHECK_CUDA(attr1.ensure(nce_bwd_kernel, smem));
   const long long gx = std::max((b_glob + 127) / 128, ((b_loc + 127) / 128) * d_i_splits);
   dim3 grid(static_cast<unsigned>(variant == 4 ? gx : (b_glob + 127) / 128), 2, 2);
   B200_REQUIRE(variant == 4 || d_i_splits == 1, "infonce_bwd: column splits need the CTA-pair kernel");

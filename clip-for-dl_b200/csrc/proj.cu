@@ -14,7 +14,7 @@ namespace b200 {
 int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, int K, long long lda, long long ldb,
               int epi, float alpha, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
               const void* resid, long long ld_res, const float* aux, long long ld_aux, int split_k, cudaStream_t stream,
-              float drop_p = 0.f, unsigned int drop_seed = 0u, int aux_is_bf16 = 0);
+              float drop_p = 0.f, unsigned int drop_seed = 0u, int aux_is_bf16 = 0, const unsigned int* drop_seed_dev = nullptr);
 }
 using namespace b200;
 
@@ -28,7 +28,8 @@ static int split_for(int M, int N, int K) {
 
 extern "C" int b200clip_proj_fwd(const void* x_bf16, long long B, int E, int D, const void* w1_bf16, const float* b1,
                                  const void* w2_bf16, const float* b2, const float* gamma, const float* beta,
-                                 float ln_eps, float drop_p, unsigned int drop_seed, void* p_bf16, void* h_bf16,
+                                 float ln_eps, float drop_p, unsigned int drop_seed, const unsigned int* drop_seed_dev,
+                                 void* p_bf16, void* h_bf16,
                                  float* z_f32, float* y_f32, void* yhat_bf16, float* mean, float* rstd, float* inv_norm,
                                  void* stream) {
   B200_REQUIRE(B > 0 && E > 0 && D > 0, "proj_fwd: empty problem");
@@ -39,7 +40,7 @@ extern "C" int b200clip_proj_fwd(const void* x_bf16, long long B, int E, int D, 
                      nullptr, 0, 1, s);
   if (rc) return rc;
   rc = gemm_bf16(h_bf16, w2_bf16, 0, 0, (int)B, D, D, D, D, EPI_BIAS_RESID_F32, 1.0f, z_f32, D, nullptr, 0, b2, p_bf16, D,
-                 nullptr, 0, 1, s, drop_p, drop_seed);
+                 nullptr, 0, 1, s, drop_p, drop_seed, 0, drop_seed_dev);
   if (rc) return rc;
   return b200clip_layernorm_fwd(z_f32, gamma, beta, y_f32, yhat_bf16, mean, rstd, inv_norm, B, D, ln_eps, 1e-12f, stream);
 }
@@ -61,7 +62,7 @@ extern "C" int b200clip_proj_bwd(const float* dy, const float* dyhat, int dyhat_
                                  const void* x_bf16, long long B, int E, int D, const void* w1_bf16,
                                  const void* w2_bf16, const float* gamma, const void* p_bf16, const void* h_bf16,
                                  const float* z_f32, const float* mean, const float* rstd, float drop_p,
-                                 unsigned int drop_seed, float* dx_f32, void* dx_bf16,
+                                 unsigned int drop_seed, const unsigned int* drop_seed_dev, float* dx_f32, void* dx_bf16,
                                  float* dw1, float* db1, float* dw2, float* db2, float* dgamma, float* dbeta, void* workspace,
                                  size_t workspace_bytes, void* stream) {
   B200_REQUIRE(B > 0 && E % 8 == 0 && D % 128 == 0 && D <= 1024, "proj_bwd: bad shape B=%lld E=%d D=%d", B, E, D);
@@ -82,10 +83,10 @@ extern "C" int b200clip_proj_bwd(const float* dy, const float* dyhat, int dyhat_
   const bool need_f32_dz = drop_p > 0.f;
   B200_REQUIRE(dy != nullptr || (dyhat != nullptr && yhat_bf16 != nullptr && inv_norm != nullptr), "proj_bwd: need dy, or dyhat + yhat + inv_norm");
   int rc = dy ? b200clip_layernorm_bwd(dy, z_f32, mean, rstd, gamma, need_f32_dz ? dz : nullptr, dz_bf, dgamma, dbeta, db2, 0, B, D,
-                                       drop_p, drop_seed, ln_work, ln_ws, stream)
+                                       drop_p, drop_seed, drop_seed_dev, ln_work, ln_ws, stream)
               : b200clip_layernorm_l2_bwd(dyhat, dyhat_partials, yhat_bf16, inv_norm, 1e-12f, addend, addend_scale, z_f32, mean,
                                           rstd, gamma, need_f32_dz ? dz : nullptr, dz_bf, dgamma, dbeta, db2, 0, B, D, drop_p,
-                                          drop_seed, ln_work, ln_ws, stream);
+                                          drop_seed, drop_seed_dev, ln_work, ln_ws, stream);
   if (rc) return rc;
   // dW2[o][j] = sum_b dz[b][o] h[b][j]
   B200_CHECK_CUDA(cudaMemsetAsync(dw2, 0, static_cast<size_t>(D) * D * 4, s));

@@ -196,7 +196,9 @@ __global__ void __launch_bounds__(ROW_THREADS, MAX_V <= 4 ? 3 : 2) layernorm_bwd
                                                                     float* __restrict__ dz_f32,
                                                                     __nv_bfloat16* __restrict__ dz_bf16,
                                                                     float* __restrict__ partial /*[grid][3][D]*/, int rows,
-                                                                    int D, float drop_p, unsigned int drop_seed, const L2BwdArgs l2) {
+                                                                    int D, float drop_p, unsigned int drop_seed_arg,
+                                                                    const unsigned int* __restrict__ drop_seed_dev, const L2BwdArgs l2) {
+  const unsigned int drop_seed = drop_seed_arg + ((drop_p > 0.f && drop_seed_dev) ? __ldg(drop_seed_dev) : 0u);
   // per-warp column accumulators (dgamma, dbeta, column sum of dz) live in shared memory, [warp][3][D]: each lane owns its
   // columns, so the read-modify-write needs no synchronisation, and 48 registers per thread are free for loads in flight
   extern __shared__ __align__(16) float ln_acc[];
@@ -443,7 +445,8 @@ extern "C" size_t b200clip_layernorm_bwd_workspace_bytes(long long rows, int D) 
 extern "C" int b200clip_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd,
                                       const float* gamma, float* dz_f32, void* dz_bf16, float* dgamma, float* dbeta,
                                       float* dz_colsum, int accumulate_params, long long rows, int D, float drop_p,
-                                      unsigned int drop_seed, void* workspace, size_t workspace_bytes, void* stream) {
+                                      unsigned int drop_seed, const unsigned int* drop_seed_dev, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
   B200_REQUIRE(rows > 0 && D > 0 && D % 128 == 0 && D <= MAX_D, "layernorm_bwd: D=%d must be a multiple of 128, <= %d", D, MAX_D);
   const int grid = part_grid(rows);
   if (workspace_bytes < static_cast<size_t>(grid) * 3 * D * sizeof(float))
@@ -453,7 +456,7 @@ extern "C" int b200clip_layernorm_bwd(const float* dy, const float* z, const flo
   const size_t ln_smem = static_cast<size_t>(ROW_THREADS / 32) * 3 * D * sizeof(float);
   B200_DISPATCH_V(D, (cudaFuncSetAttribute(layernorm_bwd_kernel<MAX_V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ln_smem)));
   B200_DISPATCH_V(D, (layernorm_bwd_kernel<MAX_V, false><<<grid, ROW_THREADS, ln_smem, s>>>(
-      dy, z, mean, rstd, gamma, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), partial, (int)rows, D, drop_p, drop_seed, L2BwdArgs{})));
+      dy, z, mean, rstd, gamma, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), partial, (int)rows, D, drop_p, drop_seed, drop_seed_dev, L2BwdArgs{})));
   B200_LAUNCH_CHECK();
   reduce_partials_kernel<<<(3 * D + 31) / 32, 256, 0, s>>>(partial, 3LL * D, grid, 3 * D, D, dgamma, dbeta, dz_colsum,
                                                          accumulate_params);
@@ -466,8 +469,9 @@ extern "C" int b200clip_layernorm_l2_bwd(const float* dyhat, int dyhat_partials,
                                          float l2_eps, const float* addend, const float* addend_scale, const float* z,
                                          const float* mean, const float* rstd, const float* gamma, float* dz_f32,
                                          void* dz_bf16, float* dgamma, float* dbeta, float* dz_colsum, int accumulate_params,
-                                         long long rows, int D, float drop_p, unsigned int drop_seed, void* workspace,
-                                         size_t workspace_bytes, void* stream) {
+                                         long long rows, int D, float drop_p, unsigned int drop_seed,
+                                         const unsigned int* drop_seed_dev, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
   B200_REQUIRE(rows > 0 && D > 0 && D % 128 == 0 && D <= MAX_D, "layernorm_l2_bwd: D=%d must be a multiple of 128, <= %d", D, MAX_D);
   B200_REQUIRE(dyhat && yhat_bf16 && inv_norm && dyhat_partials >= 1 && dyhat_partials <= 8, "layernorm_l2_bwd: missing arguments");
   B200_REQUIRE(aligned16(dyhat) && aligned16(yhat_bf16) && aligned16(addend) && aligned16(z), "layernorm_l2_bwd: pointers must be 16-byte aligned");
@@ -480,7 +484,7 @@ extern "C" int b200clip_layernorm_l2_bwd(const float* dyhat, int dyhat_partials,
   const size_t ln_smem = static_cast<size_t>(ROW_THREADS / 32) * 3 * D * sizeof(float);
   B200_DISPATCH_V(D, (cudaFuncSetAttribute(layernorm_bwd_kernel<MAX_V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ln_smem)));
   B200_DISPATCH_V(D, (layernorm_bwd_kernel<MAX_V, true><<<grid, ROW_THREADS, ln_smem, s>>>(
-      nullptr, z, mean, rstd, gamma, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), partial, (int)rows, D, drop_p, drop_seed, l2)));
+      nullptr, z, mean, rstd, gamma, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), partial, (int)rows, D, drop_p, drop_seed, drop_seed_dev, l2)));
   B200_LAUNCH_CHECK();
   reduce_partials_kernel<<<(3 * D + 31) / 32, 256, 0, s>>>(partial, 3LL * D, grid, 3 * D, D, dgamma, dbeta, dz_colsum,
                                                          accumulate_params);
@@ -509,6 +513,17 @@ extern "C" int b200clip_colsum(const void* a, int a_is_bf16, long long lda, long
 #undef B200_COLSUM_LAUNCH
   B200_LAUNCH_CHECK();
   reduce_partials_kernel<<<(N + 31) / 32, 256, 0, s>>>(partial, N, grid, N, N, out, nullptr, nullptr, accumulate);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+__global__ void dropout_seed_advance_kernel(unsigned int* seed) { *seed = *seed * 1664525u + 1013904223u; }
+
+// advances a device-resident dropout seed word (Numerical Recipes LCG); one node of a captured step graph, so that every
+// replay applies a fresh keep-mask although the kernels' launch arguments are frozen
+extern "C" int b200clip_dropout_seed_advance(unsigned int* seed_dev, void* stream) {
+  B200_REQUIRE(seed_dev != nullptr, "dropout_seed_advance: null pointer");
+  dropout_seed_advance_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(seed_dev);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

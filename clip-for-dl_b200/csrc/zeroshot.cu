@@ -428,11 +428,8 @@ extern "C" int b200clip_zeroshot_score(const void* x_bf16, long long ldx, long l
   p.scores = scores; p.guard_count = guard_count;
   const long long nblk16 = (n + 15) / 16;
   const int grid = static_cast<int>(std::min<long long>(nblk16, static_cast<long long>(num_sms())));
-  static bool configured = false;
-  if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(zeroshot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ZS_SMEM_BYTES));
-    configured = true;
-  }
+  static SmemAttrOnce attr;
+  B200_CHECK_CUDA(attr.ensure(zeroshot_kernel, ZS_SMEM_BYTES));
   zeroshot_kernel<<<grid, ZS_THREADS2, ZS_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(p);
   B200_LAUNCH_CHECK();
   return B200_OK;

@@ -58,20 +58,25 @@ size_t b200clip_layernorm_bwd_workspace_bytes(long long rows, int D);
 int b200clip_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
                            float* dz_f32, void* dz_bf16, float* dgamma, float* dbeta, float* dz_colsum,
                            int accumulate_params, long long rows, int D, float drop_p, unsigned int drop_seed,
-                           void* workspace, size_t workspace_bytes, void* stream);
+                           const unsigned int* drop_seed_dev, void* workspace, size_t workspace_bytes, void* stream);
 /* LayerNorm backward with the backward of F.normalize(LayerNorm output) fused in front: dy = inv (g - yhat (yhat . g))
  * [+ addend * *addend_scale], g = sum of dyhat_partials partial sums (rows*D elements apart), yhat bf16 [rows,D]. */
 int b200clip_layernorm_l2_bwd(const float* dyhat, int dyhat_partials, const void* yhat_bf16, const float* inv_norm,
                               float l2_eps, const float* addend, const float* addend_scale, const float* z, const float* mean,
                               const float* rstd, const float* gamma, float* dz_f32, void* dz_bf16, float* dgamma, float* dbeta,
                               float* dz_colsum, int accumulate_params, long long rows, int D, float drop_p,
-                              unsigned int drop_seed, void* workspace, size_t workspace_bytes, void* stream);
+                              unsigned int drop_seed, const unsigned int* drop_seed_dev, void* workspace,
+                              size_t workspace_bytes, void* stream);
 size_t b200clip_colsum_workspace_bytes(long long rows, int N);
 int b200clip_colsum(const void* a, int a_is_bf16, long long lda, long long rows, int N, float* out, int accumulate,
                     void* workspace, size_t workspace_bytes, void* stream);
 int b200clip_cast_f32_bf16(const float* in, void* out_bf16, long long n, void* stream);
 /* scaled keep-mask of the fused dropout (nn.Dropout, 0426/train.py:81,93): keep ? 1/(1-p) : 0, a pure function of (seed,row,col) */
 int b200clip_dropout_mask(float* out, long long rows, int cols, float p, unsigned int seed, void* stream);
+/* The effective seed of every fused dropout is drop_seed + *drop_seed_dev (drop_seed_dev: optional DEVICE word).  A captured
+ * CUDA graph freezes launch arguments; this one-thread kernel, captured at the head of the step graph, advances the device
+ * word (seed <- seed * 1664525 + 1013904223) so that every replay trains with a fresh nn.Dropout mask (0426/train.py:81,93). */
+int b200clip_dropout_seed_advance(unsigned int* seed_dev, void* stream);
 int b200clip_sum_f32(const float* a, long long n, float* out, void* stream);
 
 /* ---- a-P1 / a-P2: ImageProjection.forward 0426/train.py:84-96, TextProjection.forward :109-116 -----------------
@@ -80,8 +85,8 @@ int b200clip_sum_f32(const float* a, long long n, float* out, void* stream);
  * pass regenerates the dropout mask from (drop_p, drop_seed). */
 int b200clip_proj_fwd(const void* x_bf16, long long B, int E, int D, const void* w1_bf16, const float* b1,
                       const void* w2_bf16, const float* b2, const float* gamma, const float* beta, float ln_eps,
-                      float drop_p, unsigned int drop_seed, void* p_bf16, void* h_bf16, float* z_f32, float* y_f32, void* yhat_bf16, float* mean, float* rstd,
-                      float* inv_norm, void* stream);
+                      float drop_p, unsigned int drop_seed, const unsigned int* drop_seed_dev, void* p_bf16, void* h_bf16,
+                      float* z_f32, float* y_f32, void* yhat_bf16, float* mean, float* rstd, float* inv_norm, void* stream);
 size_t b200clip_proj_bwd_workspace_bytes(long long B, int E, int D);
 /* dy = gradient w.r.t. the LayerNorm output y.  Fused entry (dy == NULL): dyhat = gradient w.r.t. yhat = y/||y|| as
  * dyhat_partials partial sums, plus yhat, 1/||y|| and an optional addend (gradient that reaches y directly, times a device
@@ -89,7 +94,8 @@ size_t b200clip_proj_bwd_workspace_bytes(long long B, int E, int D);
 int b200clip_proj_bwd(const float* dy, const float* dyhat, int dyhat_partials, const void* yhat_bf16, const float* inv_norm,
                       const float* addend, const float* addend_scale, const void* x_bf16, long long B, int E, int D, const void* w1_bf16,
                       const void* w2_bf16, const float* gamma, const void* p_bf16, const void* h_bf16, const float* z_f32,
-                      const float* mean, const float* rstd, float drop_p, unsigned int drop_seed, float* dx_f32, void* dx_bf16,
+                      const float* mean, const float* rstd, float drop_p, unsigned int drop_seed,
+                      const unsigned int* drop_seed_dev, float* dx_f32, void* dx_bf16,
                       float* dw1, float* db1, float* dw2,
                       float* db2, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
 

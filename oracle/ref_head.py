@@ -411,13 +411,19 @@ def multimodal_attention(image_features: Tensor, text_features: Tensor, p: Dict[
 
 def head_step(x_img: Tensor, x_txt: Tensor, class_text: Tensor, labels: Tensor,
               img_p: Dict[str, Tensor], txt_p: Dict[str, Tensor], fc_w: Tensor, fc_b: Tensor,
-              tau_nce: float = 0.07, tau_bce: float = 1.0) -> Dict[str, Tensor]:
+              tau_nce: float = 0.07, tau_bce: float = 1.0, quantize=None, nce_fn=None) -> Dict[str, Tensor]:
     """proj(img), proj(txt) -> normalize -> contrastive_loss(tau_nce) + multilabel_contrastive_loss(tau_bce)
     + FC adapter BCEWithLogits; the three losses are summed and back-propagated by the caller."""
     y_img = projection_forward(x_img, img_p)
     y_txt = projection_forward(x_txt, txt_p)
     In, Tn = l2_normalize(y_img), l2_normalize(y_txt)
-    l_nce = contrastive_loss(In, Tn, tau_nce)
+    if quantize is not None:
+        # model of the CUDA path's storage precision (tests only): the normalised embeddings exist as bf16; `quantize` is a
+        # straight-through rounding (forward value rounded, gradient passed unchanged), `nce_fn` an InfoNCE whose backward
+        # rounds the softmax-gradient tile to bf16 like the kernel does
+        In, Tn = quantize(In), quantize(Tn)
+        y_img = In * y_img.norm(dim=-1, keepdim=True)
+    l_nce = (nce_fn or contrastive_loss)(In, Tn, tau_nce)
     l_bce = multilabel_contrastive_loss(y_img, class_text, labels, tau_bce)
     l_fc = fc_adapter_bce(y_img, fc_w, fc_b, labels)
     return {"loss": l_nce + l_bce + l_fc, "nce": l_nce, "bce": l_bce, "fc": l_fc,

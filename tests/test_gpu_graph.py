@@ -62,11 +62,48 @@ def test_graphed_step_rejects_other_shapes_and_use_after_close():
         step()
 
 
-def test_graphed_step_refuses_dropout():
+def test_graphed_step_trains_with_dropout():
+    """nn.Dropout(0.1) inside the captured step (0426/train.py:81,93): the seed is a device word advanced by the graph itself,
+    so every replay draws a fresh mask; a replay is reproduced by the eager step given the replay's effective seed, and the
+    projection output matches the oracle fed the same mask (ops.dropout_mask)."""
     import b200clip
-    import pytest
+    import ref_head as R
+    import synth
+    from b200clip import ops
     d = dev()
-    head = b200clip.ClipHead(768, 768, 512, 16, dropout_rate=0.1).to(d).train()
-    xi, xt, ct, lab = _inputs(1, 256, 768, 512, 16, d)
-    with pytest.raises(RuntimeError):
-        b200clip.GraphedHeadStep(head, xi, xt, ct, lab)
+    B, E, D, C, pdrop = 512, 768, 512, 16, 0.1
+    torch.manual_seed(0)
+    head = b200clip.ClipHead(E, E, D, C, dropout_rate=pdrop).to(d).train()
+    xi, xt, ct, lab = _inputs(1, B, E, D, C, d)
+    step = b200clip.GraphedHeadStep(head, xi, xt, ct, lab)
+    losses, seeds = [], []
+    for _ in range(3):
+        losses.append(float(step(xi, xt, ct, lab)))
+        seeds.append(int(step.seed_dev.item()) & 0xFFFFFFFF)
+    assert len(set(seeds)) == 3 and len(set(losses)) == 3            # fresh mask per replay
+    g_graph = step.grad_image.float().clone()
+    # the eager step with the replay's effective seed reproduces the last replay
+    eff = (step.drop_seed0 + seeds[-1]) & 0xFFFFFFFF
+    xe, te = xi.clone().requires_grad_(True), xt.clone().requires_grad_(True)
+    loss_e = b200clip.ClipHeadFn.apply(xe, te, ct, lab, head.tau_nce, head.tau_bce, None, pdrop, eff, *head.params())
+    loss_e.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss_e) - losses[-1]) <= 1e-6 * abs(losses[-1])
+    assert rel_l2(g_graph, xe.grad.float()) < 1e-5
+    step.bind_grads()
+    # keep-rate of the mask the replay used, and the oracle with that mask on the image side
+    mask = ops.dropout_mask(B, D, pdrop, eff, d).cpu()
+    assert abs((mask > 0).float().mean().item() - (1 - pdrop)) < 0.01
+    ip = head.image_projector
+    p = {k: v.detach().cpu().to(torch.bfloat16).float() if k in ("w1", "w2") else v.detach().cpu()
+         for k, v in dict(w1=ip.image_projection.weight, b1=ip.image_projection.bias, w2=ip.fc.weight, b2=ip.fc.bias,
+                          gamma=ip.layer_norm.weight, beta=ip.layer_norm.bias).items()}
+    x = xi.float().cpu()
+    proj = x @ p["w1"].T + p["b1"]
+    f = (R.gelu_erf(proj) @ p["w2"].T + p["b2"]) * mask
+    yref = torch.nn.functional.layer_norm(f + proj, (D,), p["gamma"], p["beta"], 1e-5)
+    y, _, _, _ = ops.proj_fwd(xi, ops.cast_bf16(ip.image_projection.weight), ip.image_projection.bias.detach(), ops.cast_bf16(ip.fc.weight),
+                              ip.fc.bias.detach(), ip.layer_norm.weight.detach(), ip.layer_norm.bias.detach(), want_yhat=False,
+                              drop_p=pdrop, drop_seed=step.drop_seed0, drop_seed_dev=step.seed_dev)
+    assert rel_l2(y, yref) < 1e-2
+    step.close()

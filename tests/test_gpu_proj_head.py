@@ -98,7 +98,36 @@ def test_projection_train_mode_dropout_matches_reference_with_same_mask():
     assert torch.equal(mod.eval()(xg), mod(xg))           # eval: dropout off, deterministic
 
 
-@pytest.mark.parametrize("B,E_img", [(256, 2048), (1024, 768), (200, 768)])      # 200: ragged (not a multiple of 16 / 128)
+class _QuantGNce(torch.autograd.Function):
+    """contrastive_loss whose BACKWARD models the kernel's design quantisation: the softmax-gradient tile G (scaled by B) is
+    rounded to bf16 before the two gradient products (csrc/infonce.cu); everything else in fp64."""
+
+    @staticmethod
+    def forward(ctx, In, Tn, tau):
+        ctx.save_for_backward(In, Tn)
+        ctx.tau = tau
+        return R.contrastive_loss(In, Tn, tau)
+
+    @staticmethod
+    def backward(ctx, g):
+        In, Tn = (t.double() for t in ctx.saved_tensors)
+        B, tau = In.shape[0], ctx.tau
+        S = (In @ Tn.T) / tau
+        pr, pc = torch.softmax(S, dim=1), torch.softmax(S, dim=0)
+        G = 0.5 * (pr + pc) - torch.eye(B, dtype=torch.float64)               # = B * dLoss/dS
+        Gq = G.to(torch.bfloat16).double()
+        dI = (Gq @ Tn) / (B * tau)
+        dT = (Gq.T @ In) / (B * tau)
+        return (g * dI).to(ctx.saved_tensors[0].dtype), (g * dT).to(ctx.saved_tensors[1].dtype), None
+
+
+def _ste_bf16(x):
+    return x + (synth.bf16_round(x) - x).detach()
+
+
+# (256, 2048), (1024, 768): small cases; 200: ragged (not a multiple of 16 / 128); (4096, 2048) = BASELINE.json configs[1]
+# (cfg 2) at its full size; (8192, 768) = the bench shape's widths at the largest batch the CPU oracle finishes in seconds
+@pytest.mark.parametrize("B,E_img", [(256, 2048), (1024, 768), (200, 768), (4096, 2048), (8192, 768)])
 def test_fused_head_step(B, E_img):
     import b200clip
     D, E_txt, C = 512, 768, 16
@@ -106,16 +135,21 @@ def test_fused_head_step(B, E_img):
     tp = _round_params(synth.projection_params(200, E_txt, D))
     fw, fb = synth.uniform(31, -0.04, 0.04, C, D), synth.uniform(32, -0.04, 0.04, C)
     x_img, x_txt = synth.bf16_round(synth.randn(1, B, E_img)), synth.bf16_round(synth.randn(2, B, E_txt))
-    # correlate text with image inputs a little so the diagonal is informative
     class_text = synth.unit_rows(3, C, D)
     labels = synth.labels(4, B, C)
-    ipr = {k: v.clone().requires_grad_(True) for k, v in ip.items()}
-    tpr = {k: v.clone().requires_grad_(True) for k, v in tp.items()}
-    fwr, fbr = fw.clone().requires_grad_(True), fb.clone().requires_grad_(True)
-    xi_r, xt_r = x_img.clone().requires_grad_(True), x_txt.clone().requires_grad_(True)
-    ref = R.head_step(xi_r, xt_r, class_text, labels, ipr, tpr, fwr, fbr)
-    ref["loss"].backward()
 
+    def oracle(**kw):
+        ipr = {k: v.clone().requires_grad_(True) for k, v in ip.items()}
+        tpr = {k: v.clone().requires_grad_(True) for k, v in tp.items()}
+        fwr, fbr = fw.clone().requires_grad_(True), fb.clone().requires_grad_(True)
+        xi_r, xt_r = x_img.clone().requires_grad_(True), x_txt.clone().requires_grad_(True)
+        ref = R.head_step(xi_r, xt_r, class_text, labels, ipr, tpr, fwr, fbr, **kw)
+        ref["loss"].backward()
+        return ref["loss"].item(), {"dx_img": xi_r.grad, "dx_txt": xt_r.grad, "iw1": ipr["w1"].grad, "iw2": ipr["w2"].grad,
+                                    "ig": ipr["gamma"].grad, "tw1": tpr["w1"].grad, "tw2": tpr["w2"].grad, "tbeta": tpr["beta"].grad,
+                                    "fw": fwr.grad, "fb": fbr.grad}
+
+    ref_loss, ref = oracle()
     head = b200clip.ClipHead(E_img, E_txt, D, C).to(dev())
     _load(head.image_projector, "image_projection", ip)
     _load(head.text_projector, "text_projection", tp)
@@ -124,19 +158,27 @@ def test_fused_head_step(B, E_img):
     xi, xt = x_img.to(dev()).requires_grad_(True), x_txt.to(dev()).requires_grad_(True)
     loss = head(xi, xt, class_text.to(dev()), labels.to(dev()))
     loss.backward()
-    assert abs(loss.item() - ref["loss"].item()) <= 1e-3 * abs(ref["loss"].item()), (loss.item(), ref["loss"].item())
-    checks = {
-        "dx_img": (xi.grad, xi_r.grad), "dx_txt": (xt.grad, xt_r.grad),
-        "iw1": (head.image_projector.image_projection.weight.grad, ipr["w1"].grad),
-        "iw2": (head.image_projector.fc.weight.grad, ipr["w2"].grad),
-        "ig": (head.image_projector.layer_norm.weight.grad, ipr["gamma"].grad),
-        "tw1": (head.text_projector.text_projection.weight.grad, tpr["w1"].grad),
-        "tw2": (head.text_projector.fc.weight.grad, tpr["w2"].grad),
-        "tbeta": (head.text_projector.layer_norm.bias.grad, tpr["beta"].grad),
-        "fw": (head.classifier.weight.grad, fwr.grad), "fb": (head.classifier.bias.grad, fbr.grad),
+    assert abs(loss.item() - ref_loss) <= 1e-3 * abs(ref_loss), (loss.item(), ref_loss)
+    got = {
+        "dx_img": xi.grad, "dx_txt": xt.grad,
+        "iw1": head.image_projector.image_projection.weight.grad, "iw2": head.image_projector.fc.weight.grad,
+        "ig": head.image_projector.layer_norm.weight.grad,
+        "tw1": head.text_projector.text_projection.weight.grad, "tw2": head.text_projector.fc.weight.grad,
+        "tbeta": head.text_projector.layer_norm.bias.grad,
+        "fw": head.classifier.weight.grad, "fb": head.classifier.bias.grad,
     }
-    # LayerNorm-bias / classifier-bias gradients are plain column sums of per-row gradients that cancel almost
-    # completely at random init (sum_j G_ij ~ 0), so the bf16 rounding noise of G (2^-9 per entry, which does NOT cancel)
-    # is a larger fraction of them than of the embedding gradients the 2e-2 bar is stated for.
-    for name, (a, b) in checks.items():
-        assert rel_l2(a, b) < (6e-2 if name in ("tbeta", "fb") else 2e-2), name
+    errs = {k: rel_l2(got[k], ref[k]) for k in got}
+    # The north_star bar (2e-2 rel-L2 vs the fp32 reference) holds for every embedding / weight gradient.  The text LayerNorm
+    # bias gradient is a plain column sum of per-row gradients that cancel almost completely at random init (sum_i G_ij ~ 0): the
+    # bf16 storage rounding of yhat and of the softmax-gradient tile G (2^-9 per entry, which does NOT cancel) is a larger
+    # fraction of the small sum than of the embedding gradients (the fp64 model of exactly those two roundings alone moves it by
+    # 2.4e-2 at B = 512).  That this -- and not an arithmetic error -- is the whole gap is shown by the second oracle below, which
+    # models the two roundings (fp64 otherwise): against it the same gradient is inside 2e-2 as well.
+    print({k: f"{v:.2e}" for k, v in errs.items()})
+    for name, e in errs.items():
+        assert e < (6e-2 if name == "tbeta" else 2e-2), (name, e)
+    if B <= 4096:
+        _, refq = oracle(quantize=_ste_bf16, nce_fn=_QuantGNce.apply)
+        for name in ("tbeta", "dx_txt", "dx_img"):
+            eq = rel_l2(got[name], refq[name])
+            assert eq < 2e-2, (name, eq, errs[name])

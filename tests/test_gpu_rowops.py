@@ -68,7 +68,7 @@ def test_layernorm_fwd_bwd(rows, D):
     nb = lib.b200clip_layernorm_bwd_workspace_bytes(rows, D)
     ws = torch.empty(nb, dtype=torch.uint8, device=d)
     _lib.check(lib.b200clip_layernorm_bwd(_lib.ptr(dy), _lib.ptr(z), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma),
-                                          _lib.ptr(dz), _lib.ptr(dzb), _lib.ptr(dg), _lib.ptr(db), _lib.ptr(dzs), 0, rows, D, 0.0, 0, _lib.ptr(ws), nb,
+                                          _lib.ptr(dz), _lib.ptr(dzb), _lib.ptr(dg), _lib.ptr(db), _lib.ptr(dzs), 0, rows, D, 0.0, 0, None, _lib.ptr(ws), nb,
                                           _lib.stream_ptr()), "lnb")
     assert rel_l2(dz, zr.grad) < 1e-5
     assert rel_l2(dzb.float(), zr.grad) < 4e-3
@@ -111,7 +111,7 @@ def test_layernorm_backward_with_fused_l2norm_backward(rows, D, parts, with_adde
     _lib.check(lib.b200clip_layernorm_l2_bwd(_lib.ptr(gp), parts, _lib.ptr(yhat_b), _lib.ptr(inv), 1e-12, _lib.ptr(add),
                                              _lib.ptr(sc if add is not None else None), _lib.ptr(z), _lib.ptr(mean.contiguous()),
                                              _lib.ptr(rstd.contiguous()), _lib.ptr(gamma), _lib.ptr(dz), _lib.ptr(dzb), _lib.ptr(dg),
-                                             _lib.ptr(db), _lib.ptr(dzs), 0, rows, D, 0.0, 0, _lib.ptr(ws), nb, _lib.stream_ptr()),
+                                             _lib.ptr(db), _lib.ptr(dzs), 0, rows, D, 0.0, 0, None, _lib.ptr(ws), nb, _lib.stream_ptr()),
                "ln_l2_bwd")
     assert rel_l2(dz, zr.grad) < 2e-5
     assert rel_l2(dzb.float(), zr.grad) < 4e-3
