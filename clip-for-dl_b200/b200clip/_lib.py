@@ -34,6 +34,9 @@ SIGNATURES = {
     "b200clip_softclip_workspace_bytes": (sz, [ll]),
     "b200clip_softclip_logits": (i32, [vp, vp, ll, i32, f32, vp, vp]),
     "b200clip_softclip_fwd_bwd": (i32, [vp, vp, ll, i32, f32, vp, vp, vp, vp, vp, sz, vp]),
+    "b200clip_infonce_general_fwd_bwd": (i32, [vp, vp, ll, i32, f32, vp, vp, vp, vp, vp, sz, vp]),
+    "b200clip_infonce_shift": (f64, [f32]),
+    "b200clip_rows_unit_check": (i32, [vp, ll, i32, f32, vp, vp]),
     "b200clip_adamw_tick": (i32, [vp, vp]),
     "b200clip_adamw_step": (i32, [vp, vp, vp, vp, ll, f32, f32, f32, f32, f32, vp, vp]),
     "b200clip_zs_thresholds_workspace_bytes": (sz, [ll, i32]),

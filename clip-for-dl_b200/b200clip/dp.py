@@ -81,8 +81,18 @@ def allreduce_flat(tensors: Sequence[torch.Tensor], group=None, async_op: bool =
 
 
 def infonce_loss_from_sums(sums: torch.Tensor, temperature: float, b_glob: int) -> torch.Tensor:
-    """sums = [sum_i log r_i, sum_j log c_j, sum_i S_ii] (already summed over ranks); fixed shift m = 1/tau."""
-    return (1.0 / temperature + (sums[0] + sums[1]) / (2.0 * b_glob) - sums[2] / b_glob).to(torch.float32)
+    """sums = [sum_i log r_i, sum_j log c_j, sum_i S_ii] (already summed over ranks); m = the kernels' fixed shift
+    (b200clip_infonce_shift: 1/tau, lowered for tau < 0.036 so that exp2 cannot flush whole rows)."""
+    return (infonce_shift(temperature) + (sums[0] + sums[1]) / (2.0 * b_glob) - sums[2] / b_glob).to(torch.float32)
+
+
+def infonce_shift(temperature: float) -> float:
+    """The shift m, restated for device-agnostic callers (the gloo tests): mirrors csrc/host.cuh nce_shift in float32."""
+    import numpy as np
+    log2e = np.float32(1.4426950408889634)
+    k1 = log2e / np.float32(temperature)
+    off = np.float32(min(max(float(k1) - 40.0, 0.0), 88.0))
+    return float(np.float64(np.float32(k1 - off)) / np.float64(log2e))
 
 
 def bce_losses_from_sums(sums: torch.Tensor, label_sum: torch.Tensor, total_text: float, total_fc: float):

@@ -9,13 +9,33 @@ from . import ops
 from .modules import MODEL_CONFIG
 
 
-def contrastive_loss(image_features, text_features, temperature=1.0):
-    """0426/train.py:154-176.  image_features/text_features [B, D] L2-normalised (as at the only call site, :228)."""
+GENERAL_PATH_MAX_N = 8192
+
+
+def contrastive_loss(image_features, text_features, temperature=1.0, inputs_normalized=None):
+    """0426/train.py:154-176: symmetric cross-entropy of I T^T / tau against arange(B), any inputs.
+
+    Two kernels paths, chosen by what the inputs ARE, never silently wrong:
+      * L2-normalised rows (what the reference's only call site passes, :228) -> the flash tensor-core path (bf16 operands,
+        no B x B matrix, any B);
+      * anything else -> the fp32 general path with true row / column maxima (B <= 8192; un-normalised LayerNorm outputs reach
+        |logit| ~ 10^3-10^4 at tau = 0.07, which bf16 operands and a fixed shift cannot represent).
+    `inputs_normalized=None` checks the rows on the device (one flag read, like the reference's own host syncs at :198, :224);
+    pass True / False to skip the check (True on non-unit rows is a contract violation)."""
     if image_features.shape != text_features.shape:
         # F.cross_entropy(logits[B,C], arange(B)) raises for C < B in the reference too
         raise RuntimeError(f"contrastive_loss: logits must be square, got {tuple(image_features.shape)} x "
                            f"{tuple(text_features.shape)}")
-    return ops.InfoNCEFn.apply(image_features, text_features, float(temperature))
+    ops.require_cuda(image_features, text_features)
+    if inputs_normalized is None:
+        inputs_normalized = ops.rows_are_unit(image_features.detach(), text_features.detach())
+    if inputs_normalized:
+        return ops.InfoNCEFn.apply(image_features, text_features, float(temperature))
+    if image_features.shape[0] > GENERAL_PATH_MAX_N:
+        raise RuntimeError(f"contrastive_loss: inputs are not L2-normalised and B={image_features.shape[0]} exceeds the "
+                           f"{GENERAL_PATH_MAX_N} rows the fp32 general path covers; normalise the features (b200clip.normalize) "
+                           "to use the flash path")
+    return ops.InfoNCEGeneralFn.apply(image_features, text_features, float(temperature))
 
 
 def contrastive_clip_loss_function(text_projection, image_projection, temperature=MODEL_CONFIG["temperature"], mode="eval"):

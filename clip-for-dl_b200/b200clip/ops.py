@@ -437,6 +437,46 @@ class InfoNCEFn(torch.autograd.Function):
         return d_i.to(ctx.dtypes[0]), d_t.to(ctx.dtypes[1]), None
 
 
+def rows_are_unit(*tensors: torch.Tensor, tol: float = 2e-2) -> bool:
+    """True when every row of every tensor is a unit vector (| ||x||^2 - 1 | <= tol; bf16-rounded unit vectors are inside
+    4e-3).  One tiny kernel per tensor + ONE host read of a device flag."""
+    flag = torch.zeros((), dtype=torch.int32, device=tensors[0].device)
+    for t in tensors:
+        x = _f32c(t)
+        check(load().b200clip_rows_unit_check(ptr(x), x.shape[0], x.shape[1], float(tol), ptr(flag), stream_ptr()), "rows_unit_check")
+    return int(flag.item()) == 0
+
+
+class InfoNCEGeneralFn(torch.autograd.Function):
+    """contrastive_loss for inputs that are not unit vectors (0426/train.py:154-176 accepts anything): fp32 logits with true
+    row / column maxima, n <= 8192 (b200clip_infonce_general_fwd_bwd).  Forward computes the gradients too (one pass)."""
+
+    @staticmethod
+    def forward(ctx, image_features, text_features, temperature):
+        require_cuda(image_features, text_features)
+        lib = load()
+        i, t = _f32c(image_features), _f32c(text_features)
+        n, D = i.shape
+        dev = i.device
+        need = image_features.requires_grad or text_features.requires_grad
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        di = torch.empty((n, D), dtype=torch.float32, device=dev) if need else None
+        dt = torch.empty((n, D), dtype=torch.float32, device=dev) if need else None
+        ws = _ws(lib.b200clip_softclip_workspace_bytes(n), dev)
+        check(lib.b200clip_infonce_general_fwd_bwd(ptr(i), ptr(t), n, D, float(temperature), None, ptr(loss), ptr(di), ptr(dt), ptr(ws),
+                                                   ws.numel(), stream_ptr()), "infonce_general_fwd_bwd")
+        if need:
+            ctx.save_for_backward(di, dt)
+        ctx.dtypes = (image_features.dtype, text_features.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        di, dt = ctx.saved_tensors
+        g = _f32c(g)
+        return (di * g).to(ctx.dtypes[0]), (dt * g).to(ctx.dtypes[1]), None
+
+
 # --------------------------------------------------------------------------------------------------------------
 # a-B multi-label BCE on sigmoid(cos/tau)
 # --------------------------------------------------------------------------------------------------------------

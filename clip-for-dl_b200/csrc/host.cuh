@@ -104,6 +104,21 @@ inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, 
   return B200_OK;
 }
 
+// The fixed log-sum-exp shift of the flash InfoNCE, in log2 units (csrc/infonce.cu, head_loss_finalize in smallc.cu).
+// E = exp2(s k1 - k2) with k1 = log2(e) / tau and cosines s in [-1, 1].  k2 = k1 (shift m = 1/tau) keeps E <= 1, but at small
+// tau a whole row can flush to zero: exp2 flushes below 2^-126, i.e. when every cosine of the row is below 1 - 126/k1 (0.125 at
+// tau = 0.01, CLIP's lower clamp -- normal early in training).  So the shift is lowered by off = clamp(k1 - 40, 0, 88):
+// E <= 2^off, sums of < 2^30 terms stay below 2^118, and a row only underflows if all its cosines are below 1 - (126 + off)/k1
+// (-0.49 at tau = 0.01).  tau >= 0.008 is required; tau >= 0.036 (k1 <= 40) gives off = 0: bit-identical to plain m = 1/tau.
+constexpr float NCE_LOG2E = 1.4426950408889634f;
+constexpr float NCE_MIN_TAU = 0.008f;
+inline float nce_k2(float temperature) {
+  const float k1 = NCE_LOG2E / temperature;
+  const float off = k1 - 40.f < 0.f ? 0.f : (k1 - 40.f > 88.f ? 88.f : k1 - 40.f);
+  return k1 - off;
+}
+inline double nce_shift(float temperature) { return static_cast<double>(nce_k2(temperature)) / static_cast<double>(NCE_LOG2E); }
+
 // Per-device immutable attribute cache (SURVEY.md 8b "Threading"): SM counts, and which (kernel, device) pairs already carry
 // their opt-in dynamic shared-memory limit -- cudaFuncSetAttribute is a PER-DEVICE setting, so a process that touches a second
 // GPU must set it again there.

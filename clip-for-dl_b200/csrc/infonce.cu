@@ -1205,7 +1205,8 @@ extern "C" int b200clip_infonce_fwd_stats(const void* i_hat, const void* t_hat, 
                                           size_t workspace_bytes, void* stream) {
   B200_REQUIRE(D == NCE_D, "infonce: D=%d unsupported (kernels are built for D=%d)", D, NCE_D);
   B200_REQUIRE(b_loc > 0 && b_glob > 0 && b_loc <= b_glob, "infonce: need 0 < b_loc <= b_glob (got %lld, %lld)", b_loc, b_glob);
-  B200_REQUIRE(temperature > 0.f, "infonce: temperature must be positive");
+  B200_REQUIRE(temperature >= NCE_MIN_TAU, "infonce: temperature %g is below %g: the fixed-shift exponentials would underflow "
+               "(CLIP clamps tau at 0.01)", temperature, NCE_MIN_TAU);
   B200_REQUIRE(b_glob < (1ll << 30), "infonce: batch too large");
   const NceFwdPlan pl = plan_fwd(b_loc, b_glob);
   if (workspace_bytes < pl.total_bytes) return fail(B200_ERR_WORKSPACE, "infonce_fwd: workspace %zu < %zu", workspace_bytes, pl.total_bytes);
@@ -1222,7 +1223,7 @@ extern "C" int b200clip_infonce_fwd_stats(const void* i_hat, const void* t_hat, 
   if (rc) return rc;
   NceFwdParams p{};
   p.nrows = (int)b_loc; p.ncols = (int)b_glob; p.num_col_tiles = pl.col_tiles; p.total_tiles = pl.total_tiles;
-  p.tiles_per_cta = pl.tiles_per_cta; p.r_slots = pl.r_slots; p.k1 = LOG2E / temperature; p.k2 = LOG2E / temperature;
+  p.tiles_per_cta = pl.tiles_per_cta; p.r_slots = pl.r_slots; p.k1 = LOG2E / temperature; p.k2 = nce_k2(temperature);
   p.r_part = r_part; p.c_part = c_part; p.nrows_pad = pl.nrows_pad; p.x = static_cast<const __nv_bfloat16*>(i_hat);
   auto kern = nce_fwd_kernel<FWD_BN, FWD_STAGES, FWD_NWG, FWD_XT>;
   constexpr int smem = nce_fwd_smem_bytes<FWD_BN, FWD_STAGES, FWD_NWG, FWD_XT>();
@@ -1254,7 +1255,7 @@ extern "C" int b200clip_infonce_loss(const void* i_hat, const void* t_hat, int D
   int grid = (int)std::min<long long>((b_glob + 63) / 64, 1024);      // 8 rows of the diagonal per warp at B = 32768
   nce_loss_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(i_hat), static_cast<const __nv_bfloat16*>(t_hat),
                                        (int)b_loc, (int)b_glob, (int)row0, 1.0f / temperature, r, c, (int)c_lo, (int)c_hi,
-                                       rinvh, cinvh, partial, counter, sums, loss, 1.0f / temperature);
+                                       rinvh, cinvh, partial, counter, sums, loss, static_cast<float>(nce_shift(temperature)));
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -1290,7 +1291,7 @@ extern "C" int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D,
   p.row_stat[0] = rinvh; p.col_stat[0] = cinvh; p.out[0] = d_i;
   p.xmat[0] = static_cast<const __nv_bfloat16*>(i_hat); p.xmat[1] = static_cast<const __nv_bfloat16*>(t_hat);
   p.row_stat[1] = cinvh; p.col_stat[1] = rinvh; p.out[1] = d_t_partial;
-  p.k1 = LOG2E / temperature; p.k2 = LOG2E / temperature;
+  p.k1 = LOG2E / temperature; p.k2 = nce_k2(temperature);
   p.out_scale = 1.0f / (static_cast<float>(b_glob) * temperature);
   p.grad_scale = grad_scale;
   B200_REQUIRE(d_i_splits >= 1 && d_i_splits <= 8, "infonce_bwd: d_i_splits=%d out of range", d_i_splits);
@@ -1315,3 +1316,6 @@ extern "C" int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D,
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
+
+// the shift m (natural-log units) that b200clip_infonce_loss's sums are relative to: loss = m + (sums[0] + sums[1]) / (2B) - sums[2] / B
+extern "C" double b200clip_infonce_shift(float temperature) { return temperature > 0.f ? nce_shift(temperature) : 0.0; }

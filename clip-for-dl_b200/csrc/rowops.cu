@@ -622,3 +622,29 @@ extern "C" int b200clip_cast_f32_bf16(const float* in, void* out, long long n, v
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
+
+// contract check of the flash InfoNCE path: flag |= 1 when some row of x is not a unit vector (| ||x||^2 - 1 | > tol) or is
+// non-finite.  One warp per row, fp32 input.
+namespace b200 {
+__global__ void __launch_bounds__(256) rows_unit_check_kernel(const float* __restrict__ x, long long rows, int D, float tol,
+                                                              int* __restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) >> 5;
+  const long long nw = (static_cast<long long>(gridDim.x) * 256) >> 5;
+  for (long long row = w; row < rows; row += nw) {
+    const float* p = x + row * D;
+    float ss = 0.f;
+    for (int i = lane; i < D; i += 32) { const float v = p[i]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    if (lane == 0 && !(fabsf(ss - 1.f) <= tol)) atomicOr(flag, 1);
+  }
+}
+}  // namespace b200
+
+extern "C" int b200clip_rows_unit_check(const float* x, long long rows, int D, float tol, int* flag, void* stream) {
+  B200_REQUIRE(x && flag && rows > 0 && D > 0, "rows_unit_check: bad arguments");
+  const int grid = static_cast<int>(std::min<long long>((rows + 7) / 8, 4ll * b200::num_sms()));
+  b200::rows_unit_check_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, D, tol, flag);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}

@@ -446,7 +446,7 @@ __global__ void head_loss_finalize_kernel(const double* __restrict__ sums6, cons
                                           double inv_tau_nce, double b_glob, double total_text, double total_fc,
                                           float* __restrict__ loss, float* __restrict__ parts, int* __restrict__ status) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const double l_nce = inv_tau_nce + (sums6[0] + sums6[1]) / (2.0 * b_glob) - sums6[2] / b_glob;   // fixed shift m = 1/tau
+  const double l_nce = inv_tau_nce + (sums6[0] + sums6[1]) / (2.0 * b_glob) - sums6[2] / b_glob;   // fixed shift m (host.cuh nce_shift; 1/tau for tau >= 0.036)
   const float Psum = *label_sum;
   const float Nsum = static_cast<float>(total_text - static_cast<double>(Psum));
   const float pos = static_cast<float>(-sums6[3]) / (Psum + 1e-8f);                 // 0426/train.py:218
@@ -602,7 +602,7 @@ extern "C" int b200clip_head_loss_finalize(const double* sums6, const float* lab
                                            double total_elems_text, double total_elems_fc, float* loss, float* parts3,
                                            int* status, void* stream) {
   B200_REQUIRE(sums6 && label_sum && loss && parts3 && temperature_nce > 0.f && b_glob > 0, "head_loss_finalize: bad arguments");
-  head_loss_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(sums6, label_sum, 1.0 / static_cast<double>(temperature_nce),
+  head_loss_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(sums6, label_sum, nce_shift(temperature_nce),
                                                                              b_glob, total_elems_text, total_elems_fc, loss, parts3, status);
   B200_LAUNCH_CHECK();
   return B200_OK;

@@ -187,6 +187,24 @@ static int sgemm(const float* A, long long sa_m, long long sa_k, const float* B,
   return B200_OK;
 }
 
+// P <- identity (hard targets: the general-input contrastive_loss below)
+__global__ void __launch_bounds__(256) eye_kernel(float* __restrict__ P, int n) {
+  const long long idx = blockIdx.x * 256ll + threadIdx.x;
+  if (idx >= static_cast<long long>(n) * n) return;
+  P[idx] = (idx / n == idx % n) ? 1.f : 0.f;
+}
+
+// in place: L <- dL for identity targets (dQ does not exist: hard targets carry no gradient)
+__global__ void __launch_bounds__(256) hard_grad_kernel(float* __restrict__ L, const float* __restrict__ lse_r, const float* __restrict__ lse_c,
+                                                        const float* __restrict__ grad_scale, int n) {
+  const long long idx = blockIdx.x * 256ll + threadIdx.x;
+  if (idx >= static_cast<long long>(n) * n) return;
+  const int i = static_cast<int>(idx / n), j = static_cast<int>(idx - static_cast<long long>(i) * n);
+  const float g = (grad_scale ? *grad_scale : 1.0f) / (2.0f * n);
+  const float l = L[idx];
+  L[idx] = g * (expf(l - lse_r[i]) + expf(l - lse_c[j]) - (i == j ? 2.f : 0.f));
+}
+
 constexpr long long SOFT_MAX_N = 8192;
 
 }  // namespace b200
@@ -250,5 +268,50 @@ extern "C" int b200clip_softclip_fwd_bwd(const float* text, const float* image, 
   if ((rc = sgemm(Lt, n, 1, text, D, 1, d_text, D, N, D, N, 1.0f, 1, s))) return rc;             //     += S T
   if ((rc = sgemm(L, 1, n, text, D, 1, d_image, D, N, D, N, inv_tau, 0, s))) return rc;          // dI  = dL^T T / tau
   if ((rc = sgemm(Lt, n, 1, image, D, 1, d_image, D, N, D, N, 1.0f, 1, s))) return rc;           //     += S I
+  return B200_OK;
+}
+
+// contrastive_loss (0426/train.py:154-176) for ARBITRARY inputs: fp32 logits with true row / column maxima (F.cross_entropy's
+// own stabilisation), n <= 8192.  The flash tensor-core path of infonce.cu covers the L2-normalised case the reference's call
+// site passes (:228); this entry is what b200clip.contrastive_loss dispatches to when the inputs are not unit vectors
+// (un-normalised LayerNorm outputs reach |logit| ~ 10^3-10^4 at tau = 0.07: bf16 operands and a fixed shift cannot represent
+// that).  Same kernels as the soft-target loss with identity targets: L = I T^T / tau, loss = -(1/2n) sum_i (2 L_ii - lse_r[i] -
+// lse_c[i]), dL = (softmax_row(L) + softmax_col(L) - 2 I_n) / (2n), dI = dL T / tau, dT = dL^T I / tau.
+extern "C" int b200clip_infonce_general_fwd_bwd(const float* image, const float* text, long long n, int D, float temperature,
+                                                const float* grad_scale, float* loss, float* d_image, float* d_text,
+                                                void* workspace, size_t workspace_bytes, void* stream) {
+  B200_REQUIRE(n > 0 && D > 0 && temperature > 0.f && text && image && loss, "infonce_general: bad arguments");
+  if (n > SOFT_MAX_N) return fail(B200_ERR_UNSUPPORTED, "infonce_general: n=%lld exceeds the %lld the fp32 general path covers "
+                                  "(L2-normalise the inputs to use the flash path)", n, SOFT_MAX_N);
+  B200_REQUIRE((d_text == nullptr) == (d_image == nullptr), "infonce_general: pass both gradients or neither");
+  if (workspace_bytes < b200clip_softclip_workspace_bytes(n)) return fail(B200_ERR_WORKSPACE, "infonce_general: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int N = static_cast<int>(n);
+  const long long nn = n * n;
+  float* L = static_cast<float*>(workspace);
+  float* Lt = L + nn;
+  float* P = Lt + nn;
+  float* vec = P + nn + nn;
+  float* lse_r = vec; float* lse_c = vec + n; float* rowloss = vec + 3 * n;
+  const float inv_tau = 1.0f / temperature;
+  const int eg = static_cast<int>((nn + 255) / 256);
+  int rc;
+  if ((rc = sgemm(image, D, 1, text, 1, D, L, n, N, N, D, inv_tau, 0, s))) return rc;            // :166  logits = I T^T / tau
+  if ((rc = sgemm(text, D, 1, image, 1, D, Lt, n, N, N, D, inv_tau, 0, s))) return rc;           // logits^T (column statistics as rows)
+  eye_kernel<<<eg, 256, 0, s>>>(P, N);                                                           // :170 labels = arange(B)
+  B200_LAUNCH_CHECK();
+  row_lse_kernel<<<N, 256, 0, s>>>(L, N, lse_r);
+  B200_LAUNCH_CHECK();
+  row_lse_kernel<<<N, 256, 0, s>>>(Lt, N, lse_c);
+  B200_LAUNCH_CHECK();
+  soft_rowloss_kernel<<<N, 256, 0, s>>>(L, P, lse_r, lse_c, N, rowloss);                         // :173-174
+  B200_LAUNCH_CHECK();
+  soft_loss_final_kernel<<<1, 256, 0, s>>>(rowloss, N, loss);                                    // :176
+  B200_LAUNCH_CHECK();
+  if (!d_text) return B200_OK;
+  hard_grad_kernel<<<eg, 256, 0, s>>>(L, lse_r, lse_c, grad_scale, N);
+  B200_LAUNCH_CHECK();
+  if ((rc = sgemm(L, n, 1, text, D, 1, d_image, D, N, D, N, inv_tau, 0, s))) return rc;          // dI = dL T / tau
+  if ((rc = sgemm(L, 1, n, image, D, 1, d_text, D, N, D, N, inv_tau, 0, s))) return rc;          // dT = dL^T I / tau
   return B200_OK;
 }

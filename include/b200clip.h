@@ -247,6 +247,16 @@ int b200clip_zeroshot_score(const void* x_bf16, long long ldx, long long n, cons
                             int mask_is_u32, uint8_t* topk_idx, float* topk_val, float* scores,
                             unsigned long long* guard_count, void* stream);
 
+/* contrastive_loss(image_features, text_features, temperature) -- 0426/train.py:154-176 -- for inputs that are NOT unit
+ * vectors: fp32 logits, true row/column maxima, n <= 8192 (workspace: b200clip_softclip_workspace_bytes(n)).  The flash path
+ * (b200clip_infonce_*) requires L2-normalised rows; b200clip_rows_unit_check sets *flag |= 1 when a row violates that. */
+int b200clip_infonce_general_fwd_bwd(const float* image, const float* text, long long n, int D, float temperature,
+                                     const float* grad_scale, float* loss, float* d_image, float* d_text, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+/* the fixed shift m of the flash path: loss = m + (sums[0] + sums[1]) / (2 B) - sums[2] / B  (1/tau for tau >= 0.036) */
+double b200clip_infonce_shift(float temperature);
+int b200clip_rows_unit_check(const float* x, long long rows, int D, float tol, int* flag, void* stream);
+
 /* ---- step edges --------------------------------------------------------------------------
  * calculate_multilabel_metrics(predictions, labels) -- 0426/train.py:251-302 -- and the in-loop accuracy counters of
  * train_epoch / validate (0426/train.py:437-447).  predictions [B,C] are probabilities (or any score compared with

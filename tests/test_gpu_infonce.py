@@ -161,3 +161,52 @@ def test_rejects_unsupported_shapes():
         b200clip.contrastive_loss(I, I, 0.07)              # D != 512: loud failure, no fallback
     with pytest.raises(RuntimeError):
         b200clip.contrastive_loss(torch.randn(64, 512, device=dev()), torch.randn(16, 512, device=dev()), 0.07)
+
+
+@pytest.mark.parametrize("B,tau,corr", [(200, 0.01, 0.0), (1000, 0.01, 0.5), (512, 0.02, 0.0), (256, 0.008, 0.3)])
+def test_small_temperature_does_not_underflow(B, tau, corr):
+    """CLIP clamps tau at 0.01.  With the plain shift m = 1/tau every exponential of a row whose cosines are all below
+    1 - 126 tau ln2 (0.125 at tau = 0.01: any untrained batch) flushes to zero -> r = 0 -> inf loss, NaN gradients.  The
+    kernels lower the shift (csrc/host.cuh nce_k2); loss and gradients must match the reference's stable F.cross_entropy."""
+    import b200clip
+    I, T = _inputs(B, seed=21, corr=corr)
+    loss_ref, dI_ref, dT_ref = _oracle(I.double(), T.double(), tau)
+    Ig, Tg = I.to(dev()).requires_grad_(True), T.to(dev()).requires_grad_(True)
+    loss = b200clip.contrastive_loss(Ig, Tg, tau)
+    loss.backward()
+    assert torch.isfinite(loss) and torch.isfinite(Ig.grad).all() and torch.isfinite(Tg.grad).all()
+    assert abs(loss.item() - loss_ref.item()) <= LOSS_TOL * abs(loss_ref.item()), (loss.item(), loss_ref.item())
+    assert rel_l2(Ig.grad, dI_ref) < GRAD_TOL and rel_l2(Tg.grad, dT_ref) < GRAD_TOL
+
+
+def test_temperature_below_supported_range_is_rejected():
+    import b200clip
+    I, T = _inputs(128)
+    with pytest.raises(RuntimeError, match="temperature"):
+        b200clip.contrastive_loss(I.to(dev()), T.to(dev()), 0.004)
+
+
+def test_unnormalised_inputs_take_the_general_path(golden):
+    """0426/train.py:154-176 accepts any inputs; the flash path needs unit rows.  The public function must detect the
+    difference and stay correct: reference golden (un-normalised randn, tau 1.0), then LayerNorm-scale inputs at tau 0.07
+    (|logit| ~ 10^3) and mildly off-unit rows against the fp64 oracle, loss AND gradients."""
+    import b200clip
+    from b200clip import ops
+    I, T = synth.randn(13, 20, 32), synth.randn(14, 20, 32)
+    assert not ops.rows_are_unit(I.to(dev()), T.to(dev()))
+    loss = b200clip.contrastive_loss(I.to(dev()), T.to(dev()), 1.0)
+    assert abs(loss.item() - float(golden["nce_loss_unnorm"])) <= 1e-5 * abs(float(golden["nce_loss_unnorm"]))
+    for B, D, scale, tau in ((300, 512, 22.6, 0.07), (64, 512, 1.3, 0.07), (1000, 128, 4.0, 0.5)):
+        I, T = synth.unit_rows(31, B, D) * scale, synth.unit_rows(32, B, D) * scale
+        loss_ref, dI_ref, dT_ref = _oracle(I.double(), T.double(), tau)
+        Ig, Tg = I.to(dev()).requires_grad_(True), T.to(dev()).requires_grad_(True)
+        loss = b200clip.contrastive_loss(Ig, Tg, tau)
+        (loss * 3.0).backward()
+        assert abs(loss.item() - loss_ref.item()) <= 1e-4 * abs(loss_ref.item()), (B, loss.item(), loss_ref.item())
+        assert rel_l2(Ig.grad, 3.0 * dI_ref) < 1e-3 and rel_l2(Tg.grad, 3.0 * dT_ref) < 1e-3
+    # unit rows keep the flash path; an explicit (wrong) inputs_normalized=True is the caller's contract
+    Iu, Tu = _inputs(256)
+    assert ops.rows_are_unit(Iu.to(dev()), Tu.to(dev()))
+    big = torch.randn(8200, 512, device=dev())
+    with pytest.raises(RuntimeError, match="not L2-normalised"):
+        b200clip.contrastive_loss(big, big, 0.07)
