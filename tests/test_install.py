@@ -28,7 +28,9 @@ def test_install_patches_module_globals():
 def test_signatures_match_reference_defaults():
     import inspect
     sig = inspect.signature(b200clip.contrastive_loss)
-    assert list(sig.parameters) == ["image_features", "text_features", "temperature"] and sig.parameters["temperature"].default == 1.0
+    # the reference's three parameters, in order, same default; one extra keyword with a default (inputs_normalized) is allowed
+    assert list(sig.parameters)[:3] == ["image_features", "text_features", "temperature"] and sig.parameters["temperature"].default == 1.0
+    assert all(p.default is not inspect.Parameter.empty for p in list(sig.parameters.values())[3:])
     sig = inspect.signature(b200clip.multilabel_contrastive_loss)
     assert list(sig.parameters)[:4] == ["image_features", "text_features", "labels", "temperature"]
     sig = inspect.signature(b200clip.contrastive_clip_loss_function)
