@@ -31,6 +31,13 @@ class FusedAdamW(torch.optim.Optimizer):
                     st["step"] = self._step
         return self._step
 
+    def state_dict(self):
+        """torch.optim.AdamW's layout: every parameter gets its OWN `step` tensor (a clone of the shared device counter) -- torch's
+        foreach implementation increments each state's tensor, so a shared one would be advanced once per parameter."""
+        sd = super().state_dict()
+        sd["state"] = {k: ({**v, "step": v["step"].detach().clone()} if "step" in v else dict(v)) for k, v in sd["state"].items()}
+        return sd
+
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._step = None                       # rebuilt from the loaded per-parameter steps on the next step()

@@ -156,14 +156,16 @@ def test_properties_at_full_size():
 
 def test_rejects_unsupported_shapes():
     import b200clip
-    I = torch.randn(64, 256, device=dev())
+    I = synth.unit_rows(5, 64, 192).to(dev())
     with pytest.raises(RuntimeError):
-        b200clip.contrastive_loss(I, I, 0.07)              # D != 512: loud failure, no fallback
+        b200clip.contrastive_loss(I, I, 0.07)              # unit rows -> flash path; D = 192 is not built: loud failure, no fallback
     with pytest.raises(RuntimeError):
         b200clip.contrastive_loss(torch.randn(64, 512, device=dev()), torch.randn(16, 512, device=dev()), 0.07)
 
 
-@pytest.mark.parametrize("B,tau,corr", [(200, 0.01, 0.0), (1000, 0.01, 0.5), (512, 0.02, 0.0), (256, 0.008, 0.3)])
+# corr is kept small: with a dominant diagonal at these temperatures the softmax saturates (loss ~ 1e-12, G ~ -1e-12) and any fp32
+# implementation -- the reference's F.cross_entropy included -- only carries rounding noise relative to the fp64 truth
+@pytest.mark.parametrize("B,tau,corr", [(200, 0.01, 0.0), (1000, 0.01, 0.12), (512, 0.02, 0.0), (256, 0.008, 0.1)])
 def test_small_temperature_does_not_underflow(B, tau, corr):
     """CLIP clamps tau at 0.01.  With the plain shift m = 1/tau every exponential of a row whose cosines are all below
     1 - 126 tau ln2 (0.125 at tau = 0.01: any untrained batch) flushes to zero -> r = 0 -> inf loss, NaN gradients.  The
