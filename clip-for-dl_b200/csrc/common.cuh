@@ -449,6 +449,44 @@ __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): two CTAs of a cluster whose ranks differ in the last bit run ONE tcgen05.mma of M = 256; each
+// CTA supplies its 128 rows of A and half of the N rows of B from its own shared memory and receives its 128 rows of D in its
+// own TMEM.  The leader (even rank) issues; TMA loads of both CTAs complete on the LEADER's mbarrier; commits are multicast.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result, uint32_t ncols) {   // same warp id in BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 2-D TMA load whose completion bytes go to the mbarrier at shared::cluster address `cluster_bar` (the leader CTA's)
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ss_lo_2cta(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(static_cast<uint32_t>(accumulate)), "r"(DESC_HI_SW128)
+      : "memory");
+}
+// commit of the pair's MMAs, arriving on the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void tc_commit_2cta_multicast_a(uint32_t bar_addr, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar_addr), "h"(cta_mask)
+               : "memory");
+}
+
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -325,6 +325,258 @@ nce_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   if (warp == 2) tmem_dealloc(tmem_base, XT ? 512 : NWG * BN);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pass 1, CTA-pair kernel (default).  nce_fwd_kernel above is shared-memory-port bound: per 64-clk N = 128 MMA the port
+// serves 8 KB of operand reads plus 4 KB of TMA writes = 192 B/clk against 128 B/clk available (measured: tensor pipe 67 %).
+// Here two CTAs (a cluster 2x1x1 = one TPC) own two stacked row blocks and issue ONE tcgen05.mma.cta_group::2 of M = 256,
+// N = 256 per K16 step: each CTA supplies its own 128 rows of X and only HALF of the Y tile (128 of the 256 columns), so per
+// 128-clk MMA its port serves 4 KB (A) + 4 KB (B half) + 4 KB (TMA writes of that half) = 96 B/clk -- under the limit, the
+// pass is tensor-bound.  TMEM: two 256-column S buffers (all 512 columns) per CTA, each CTA's epilogue (16 warps: lane
+// quadrant q x column quarter h) turns its own 128 x 256 fp32 tile into row / column exp-sums exactly like the 1-CTA kernel.
+// Protocol: both CTAs' TMA loads complete on the LEADER's full barriers (cta_group::2 TMA, expect-tx armed by the leader for
+// both halves); the leader's commits are multicast to both CTAs' empty / s_full barriers; the epilogue warps of both CTAs
+// arrive on the leader's s_empty.  XSTAT = true (D = 512): the X row block is stationary in shared memory (128 KB);
+// XSTAT = false (any D = 64 KC): X chunks are streamed next to the Y chunks (D = 768 would need 192 KB for a stationary X).
+// ------------------------------------------------------------------------------------------------
+constexpr int FWD2_BN = 256;               // S tile columns (= Y rows) per MMA
+constexpr int FWD2_EPI_WG = 4;             // epilogue warpgroups: column quarters of the tile
+constexpr int FWD2_THREADS = 128 + FWD2_EPI_WG * 128;
+constexpr int FWD2_CHUNK = 128 * 128;      // [128 rows x 64 bf16]: one X chunk, or one CTA's half of a Y chunk
+template <int KC, bool XSTAT>      // KC = 0: run-time K-chunk count (streamed X only)
+__host__ __device__ constexpr int nce_fwd2_stages() { return XSTAT ? (227 * 1024 - KC * FWD2_CHUNK - 6 * 1024) / FWD2_CHUNK : 6; }
+template <int KC, bool XSTAT>
+constexpr int nce_fwd2_smem_bytes() {
+  return (XSTAT ? KC * FWD2_CHUNK + nce_fwd2_stages<KC, XSTAT>() * FWD2_CHUNK : nce_fwd2_stages<KC, XSTAT>() * 2 * FWD2_CHUNK) +
+         16 * 64 * 4 + 512 + 1024;
+}
+
+struct NceFwd2Params {
+  int nrows, ncols;         // valid X rows (b_loc), valid Y rows (b_glob)
+  int ct2;                  // column super-tiles: ceil(ncols / 256)
+  int total;                // row super-blocks * ct2
+  int tiles_per_cluster;
+  float k1, k2;
+  float* r_part;            // [r_slots][nrows_pad]  zero-initialised by the host
+  float* c_part;            // [row_blocks(128)][ncols]
+  int nrows_pad;
+  int kc;                   // D / 64 (used when the kernel is instantiated with a run-time chunk count)
+};
+
+template <int KC_T, bool XSTAT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD2_THREADS, 1)
+nce_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const NceFwd2Params p) {
+  static_assert(!XSTAT || KC_T > 0, "a stationary X needs a compile-time chunk count");
+  constexpr int STAGES = nce_fwd2_stages<KC_T, XSTAT>();
+  constexpr int STAGE_BYTES = XSTAT ? FWD2_CHUNK : 2 * FWD2_CHUNK;       // streamed: [X chunk | Y half chunk]
+  const int KC = KC_T > 0 ? KC_T : p.kc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sX = smem;
+  uint8_t* sY = sX + (XSTAT ? KC_T * FWD2_CHUNK : 0);
+  float* scratch = reinterpret_cast<float*>(sY + STAGES * STAGE_BYTES);   // [16 warps][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 16 * 64);
+  uint64_t* x_full = bars;                     // leader: 1 arrival + both CTAs' X bytes
+  uint64_t* x_empty = bars + 1;                // each CTA: 1 (multicast commit)
+  uint64_t* y_full = bars + 2;                 // leader: 1 arrival + both CTAs' stage bytes
+  uint64_t* y_empty = y_full + STAGES;         // each CTA: 1 (multicast commit)
+  uint64_t* s_full = y_empty + STAGES;         // each CTA: 1 (multicast commit)            [2]
+  uint64_t* s_empty = s_full + 2;              // leader: 2 CTAs x 16 epilogue warps        [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cr = cluster_ctarank();       // 0 = leader
+  const int cl = static_cast<int>(blockIdx.x >> 1);
+  const int t0 = cl * p.tiles_per_cluster;
+  const int t1 = min(p.total, t0 + p.tiles_per_cluster);
+  const int CT = p.ct2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_y);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&y_full[s], 1);
+      mbar_init(&y_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&s_empty[b], 2 * FWD2_EPI_WG * 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_slot, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();                          // barrier inits visible to the peer before any remote arrive / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own X rows, own half of every Y tile) =====================
+    const uint32_t xf_lead = mapa_u32(smem_u32(x_full), 0), yf0_lead = mapa_u32(smem_u32(y_full), 0);
+    const uint32_t xf = smem_u32(x_full), xe = smem_u32(x_empty), yf0 = smem_u32(y_full), ye0 = smem_u32(y_empty);
+    const uint32_t sx = smem_u32(sX), sy = smem_u32(sY);
+    int s = 0, cur_rb = -1;
+    uint32_t ph = 0, xph = 0;
+    int rb = t0 / CT, ct = t0 - rb * CT;
+    for (int t = t0; t < t1; ++t) {
+      const int xrow = rb * 256 + static_cast<int>(cr) * 128, yrow = ct * FWD2_BN + static_cast<int>(cr) * 128;
+      if constexpr (XSTAT) {
+        if (rb != cur_rb) {
+          mbar_wait_a(xe, xph ^ 1);
+          if (elect_one()) {
+            if (cr == 0) mbar_arrive_expect_tx_a(xf, 2 * KC_T * FWD2_CHUNK);
+#pragma unroll
+            for (int kc = 0; kc < KC_T; ++kc) tma_load_2d_2cta(sx + kc * FWD2_CHUNK, &tmap_x, xf_lead, kc * 64, xrow);
+          }
+          __syncwarp();
+          xph ^= 1;
+          cur_rb = rb;
+        }
+      }
+#pragma unroll 1
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait_a(ye0 + 8 * s, ph ^ 1);
+        if (elect_one()) {
+          if (cr == 0) mbar_arrive_expect_tx_a(yf0 + 8 * s, 2 * STAGE_BYTES);
+          if constexpr (!XSTAT) tma_load_2d_2cta(sy + s * STAGE_BYTES, &tmap_x, yf0_lead + 8 * s, kc * 64, xrow);
+          tma_load_2d_2cta(sy + s * STAGE_BYTES + (XSTAT ? 0 : FWD2_CHUNK), &tmap_y, yf0_lead + 8 * s, kc * 64, yrow);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      if (++ct == CT) { ct = 0; ++rb; }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (cr == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, FWD2_BN, false, false);
+      const uint32_t xf = smem_u32(x_full), xe = smem_u32(x_empty), yf0 = smem_u32(y_full), ye0 = smem_u32(y_empty);
+      const uint32_t sf0 = smem_u32(s_full), se0 = smem_u32(s_empty);
+      const uint32_t x_lo = desc_lo(smem_u32(sX), 16), y_lo = desc_lo(smem_u32(sY), 16);
+      int s = 0, cur_rb = -1, buf = 0;
+      uint32_t ph = 0, xph = 0, sph = 0;
+      int rb = t0 / CT, ct = t0 - rb * CT;
+      for (int t = t0; t < t1; ++t) {
+        if constexpr (XSTAT) {
+          if (rb != cur_rb) {
+            mbar_wait_cluster_a(xf, xph);
+            xph ^= 1;
+            cur_rb = rb;
+          }
+        }
+        mbar_wait_cluster_a(se0 + 8 * buf, sph ^ 1);        // both CTAs' epilogues have drained this S buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * FWD2_BN;
+#pragma unroll 1
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_wait_cluster_a(yf0 + 8 * s, ph);              // both halves (and, streamed, both X chunks) have landed
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a = XSTAT ? x_lo + kc * (FWD2_CHUNK >> 4) : y_lo + s * (STAGE_BYTES >> 4);
+            const uint32_t b = y_lo + s * (STAGE_BYTES >> 4) + (XSTAT ? 0 : (FWD2_CHUNK >> 4));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_ss_lo_2cta(d_tmem, a + 2 * j, b + 2 * j, idesc, (kc | j) != 0);
+            tc_commit_2cta_multicast_a(ye0 + 8 * s, 0x3);
+          }
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        const bool last_of_rb = (ct + 1 == CT) || (t + 1 == t1);
+        if (elect_one()) {
+          tc_commit_2cta_multicast_a(sf0 + 8 * buf, 0x3);
+          if (XSTAT && last_of_rb) tc_commit_2cta_multicast_a(xe, 0x3);
+        }
+        __syncwarp();
+        if (++buf == 2) { buf = 0; sph ^= 1; }
+        if (++ct == CT) { ct = 0; ++rb; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: 16 warps = lane quadrant q (warp & 3) x column quarter h; every warp sees every tile =====
+    const int h = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int tid_wg = threadIdx.x - 128 - h * 128;
+    float* my_scratch = scratch + h * 4 * 64;                 // [4 quadrants][64 columns] of this column quarter
+    const uint32_t sf0 = smem_u32(s_full);
+    const uint32_t se0_lead = mapa_u32(smem_u32(s_empty), 0);
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 64;
+    float rsum = 0.f;
+    int cur_rb = -1, buf = 0;
+    uint32_t sph = 0;
+    auto flush_rsum = [&](int rb) {
+      const int row = rb * 256 + static_cast<int>(cr) * 128 + q * 32 + lane;
+      const int first_cl = (rb * CT) / p.tiles_per_cluster;
+      const int slot = FWD2_EPI_WG * (cl - first_cl) + h;
+      if (row < p.nrows) p.r_part[static_cast<long long>(slot) * p.nrows_pad + row] = rsum;
+      rsum = 0.f;
+    };
+    int rb = t0 / CT, ct = t0 - rb * CT;
+    for (int t = t0; t < t1; ++t) {
+      if (rb != cur_rb) {
+        if (cur_rb >= 0) flush_rsum(cur_rb);
+        cur_rb = rb;
+      }
+      const int row0 = rb * 256 + static_cast<int>(cr) * 128;
+      const int row = row0 + q * 32 + lane;
+      const int col_base = ct * FWD2_BN + h * 64;
+      const bool interior = (row0 + 128 <= p.nrows) && (ct * FWD2_BN + FWD2_BN <= p.ncols);   // warp-uniform
+      mbar_wait_a(sf0 + 8 * buf, sph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(t_lane + buf * FWD2_BN + c, v);
+        tmem_ld_wait();
+        if (c == 32) {                              // last TMEM read of this tile: hand the buffer back to the leader's MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_a(se0_lead + 8 * buf);
+        }
+        float e[32];
+        if (interior) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            e[i] = fast_exp2(fmaf(__uint_as_float(v[i]), p.k1, -p.k2));
+            rsum += e[i];
+          }
+        } else {
+          const bool row_ok = row < p.nrows;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = fast_exp2(fmaf(__uint_as_float(v[i]), p.k1, -p.k2));
+            e[i] = (row_ok && (col_base + c + i) < p.ncols) ? x : 0.f;
+            rsum += e[i];
+          }
+        }
+        my_scratch[q * 64 + c + lane] = warp_colsum32(e, lane);
+      }
+      named_bar_sync(1 + h, 128);
+      {
+        const int col = col_base + tid_wg;
+        const int rb128 = rb * 2 + static_cast<int>(cr);
+        if (tid_wg < 64 && col < p.ncols && rb128 * 128 < p.nrows)
+          p.c_part[static_cast<long long>(rb128) * p.ncols + col] =
+              (my_scratch[tid_wg] + my_scratch[64 + tid_wg]) + (my_scratch[128 + tid_wg] + my_scratch[192 + tid_wg]);
+      }
+      named_bar_sync(1 + h, 128);
+      if (++buf == 2) { buf = 0; sph ^= 1; }
+      if (++ct == CT) { ct = 0; ++rb; }
+    }
+    if (cur_rb >= 0) flush_rsum(cur_rb);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                          // the peer may still be arriving on / reading through this CTA's barriers
+  if (warp == 2) tmem_dealloc_2cta(tmem_base, 512);
+}
+
 // ================================================================================================
 // Pass 2: gradients
 // ================================================================================================
@@ -1079,7 +1331,7 @@ __global__ void __launch_bounds__(256) nce_reduce_stats_kernel(const float* __re
 // sums[0] = sum_i log r_i (local rows), sums[1] = sum_{j in [c_lo,c_hi)} log c_j, sums[2] = sum_i S_ii  (S_ii = I_i.T_{row0+i}/tau)
 // also writes rinvh = 0.5 / r, cinvh = 0.5 / c.  Deterministic: per-block partials, last block folds them in order.
 __global__ void __launch_bounds__(256) nce_loss_kernel(const __nv_bfloat16* __restrict__ I, const __nv_bfloat16* __restrict__ T,
-                                                       int b_loc, int b_glob, int row0, float inv_tau,
+                                                       int D, int b_loc, int b_glob, int row0, float inv_tau,
                                                        const float* __restrict__ r, const float* __restrict__ c, int c_lo,
                                                        int c_hi, float* __restrict__ rinvh, float* __restrict__ cinvh,
                                                        double* __restrict__ partial /*[grid][3]*/,
@@ -1101,13 +1353,12 @@ __global__ void __launch_bounds__(256) nce_loss_kernel(const __nv_bfloat16* __re
     cinvh[j] = 0.5f / cj;
     if (j >= c_lo && j < c_hi) a_logc += static_cast<double>(logf(cj));
   }
-  // diagonal: one warp per row, 512 bf16 = 16 per lane
+  // diagonal: one warp per row, D bf16 = D/8 16-byte pieces dealt round-robin to the lanes
   for (int i = blockIdx.x * 8 + warp; i < b_loc; i += gridDim.x * 8) {
-    const uint4* pi = reinterpret_cast<const uint4*>(I + static_cast<long long>(i) * NCE_D) + lane * 2;
-    const uint4* pt = reinterpret_cast<const uint4*>(T + static_cast<long long>(row0 + i) * NCE_D) + lane * 2;
+    const uint4* pi = reinterpret_cast<const uint4*>(I + static_cast<long long>(i) * D);
+    const uint4* pt = reinterpret_cast<const uint4*>(T + static_cast<long long>(row0 + i) * D);
     float d = 0.f;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = lane; k < (D >> 3); k += 32) {
       const uint4 a = pi[k], b = pt[k];
       d += bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) + bf16_hi(a.y) * bf16_hi(b.y) +
            bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) + bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
@@ -1173,6 +1424,8 @@ constexpr int FWD_NWG = 4;                 // epilogue warpgroups = TMEM S buffe
 struct NceFwdPlan {
   int row_blocks, col_tiles, total_tiles, tiles_per_cta, grid, r_slots, nrows_pad;
   size_t r_part_bytes, c_part_bytes, total_bytes;
+  // CTA-pair kernel: 256 x 256 super-tiles walked by clusters of two CTAs
+  int rb2, ct2, total2, tiles_per_cluster, grid2, r_slots2, nrows_pad2;
 };
 static NceFwdPlan plan_fwd(long long b_loc, long long b_glob) {
   NceFwdPlan pl{};
@@ -1185,7 +1438,16 @@ static NceFwdPlan plan_fwd(long long b_loc, long long b_glob) {
   pl.grid = (pl.total_tiles + pl.tiles_per_cta - 1) / pl.tiles_per_cta;
   pl.r_slots = FWD_NWG * ((pl.col_tiles + pl.tiles_per_cta - 1) / pl.tiles_per_cta + 1);
   pl.nrows_pad = pl.row_blocks * 128;
-  pl.r_part_bytes = static_cast<size_t>(pl.r_slots) * pl.nrows_pad * sizeof(float);
+  pl.rb2 = static_cast<int>((b_loc + 255) / 256);
+  pl.ct2 = static_cast<int>((b_glob + FWD2_BN - 1) / FWD2_BN);
+  pl.total2 = pl.rb2 * pl.ct2;
+  const int clusters = std::max(1, sms / 2);
+  pl.tiles_per_cluster = std::max(1, (pl.total2 + clusters - 1) / clusters);
+  pl.grid2 = 2 * ((pl.total2 + pl.tiles_per_cluster - 1) / pl.tiles_per_cluster);
+  pl.r_slots2 = FWD2_EPI_WG * ((pl.ct2 + pl.tiles_per_cluster - 1) / pl.tiles_per_cluster + 1);
+  pl.nrows_pad2 = pl.rb2 * 256;
+  // one workspace serves either kernel: size it for the larger partial-sum buffer
+  pl.r_part_bytes = std::max(static_cast<size_t>(pl.r_slots) * pl.nrows_pad, static_cast<size_t>(pl.r_slots2) * pl.nrows_pad2) * sizeof(float);
   pl.c_part_bytes = static_cast<size_t>(pl.row_blocks) * b_glob * sizeof(float);
   pl.total_bytes = ((pl.r_part_bytes + 255) & ~size_t(255)) + ((pl.c_part_bytes + 255) & ~size_t(255)) + 4096 * 3 * sizeof(double) + 256;
   return pl;
@@ -1200,10 +1462,12 @@ extern "C" size_t b200clip_infonce_workspace_bytes(long long b_loc, long long b_
   return plan_fwd(b_loc, b_glob).total_bytes;
 }
 
+static bool nce_dim_supported(int D) { return D >= 64 && D <= 1024 && D % 64 == 0; }
+
 extern "C" int b200clip_infonce_fwd_stats(const void* i_hat, const void* t_hat, int D, long long b_loc, long long b_glob,
                                           float temperature, float* r, float* c_partial, void* workspace,
                                           size_t workspace_bytes, void* stream) {
-  B200_REQUIRE(D == NCE_D, "infonce: D=%d unsupported (kernels are built for D=%d)", D, NCE_D);
+  B200_REQUIRE(nce_dim_supported(D), "infonce: D=%d unsupported (need a multiple of 64, 64..1024)", D);
   B200_REQUIRE(b_loc > 0 && b_glob > 0 && b_loc <= b_glob, "infonce: need 0 < b_loc <= b_glob (got %lld, %lld)", b_loc, b_glob);
   B200_REQUIRE(temperature >= NCE_MIN_TAU, "infonce: temperature %g is below %g: the fixed-shift exponentials would underflow "
                "(CLIP clamps tau at 0.01)", temperature, NCE_MIN_TAU);
@@ -1215,24 +1479,48 @@ extern "C" int b200clip_infonce_fwd_stats(const void* i_hat, const void* t_hat, 
   float* r_part = reinterpret_cast<float*>(ws);
   float* c_part = reinterpret_cast<float*>(ws + ((pl.r_part_bytes + 255) & ~size_t(255)));
   B200_CHECK_CUDA(cudaMemsetAsync(r_part, 0, pl.r_part_bytes, s));
-
+  // B200CLIP_FWD_VARIANT=1: the single-CTA kernel (D = 512 only; kept for A/B measurements and as a cross-check in the tests)
+  static const int variant = [] { const char* e = getenv("B200CLIP_FWD_VARIANT"); return (e && atoi(e) == 1) ? 1 : 2; }();
   CUtensorMap tx, ty;
-  int rc = make_tmap_bf16_2d(&tx, i_hat, b_loc, D, D, 64, 128);
-  if (rc) return rc;
-  rc = make_tmap_bf16_2d(&ty, t_hat, b_glob, D, D, 64, FWD_BN);
-  if (rc) return rc;
-  NceFwdParams p{};
-  p.nrows = (int)b_loc; p.ncols = (int)b_glob; p.num_col_tiles = pl.col_tiles; p.total_tiles = pl.total_tiles;
-  p.tiles_per_cta = pl.tiles_per_cta; p.r_slots = pl.r_slots; p.k1 = LOG2E / temperature; p.k2 = nce_k2(temperature);
-  p.r_part = r_part; p.c_part = c_part; p.nrows_pad = pl.nrows_pad; p.x = static_cast<const __nv_bfloat16*>(i_hat);
-  auto kern = nce_fwd_kernel<FWD_BN, FWD_STAGES, FWD_NWG, FWD_XT>;
-  constexpr int smem = nce_fwd_smem_bytes<FWD_BN, FWD_STAGES, FWD_NWG, FWD_XT>();
-  static SmemAttrOnce attr;
-  B200_CHECK_CUDA(attr.ensure(kern, smem));
-  kern<<<pl.grid, 128 + FWD_NWG * 128, smem, s>>>(tx, ty, p);
-  B200_LAUNCH_CHECK();
+  int rc;
+  int r_slots, nrows_pad;
+  if (variant == 1 && D == NCE_D) {
+    if ((rc = make_tmap_bf16_2d(&tx, i_hat, b_loc, D, D, 64, 128))) return rc;
+    if ((rc = make_tmap_bf16_2d(&ty, t_hat, b_glob, D, D, 64, FWD_BN))) return rc;
+    NceFwdParams p{};
+    p.nrows = (int)b_loc; p.ncols = (int)b_glob; p.num_col_tiles = pl.col_tiles; p.total_tiles = pl.total_tiles;
+    p.tiles_per_cta = pl.tiles_per_cta; p.r_slots = pl.r_slots; p.k1 = LOG2E / temperature; p.k2 = nce_k2(temperature);
+    p.r_part = r_part; p.c_part = c_part; p.nrows_pad = pl.nrows_pad; p.x = static_cast<const __nv_bfloat16*>(i_hat);
+    auto kern = nce_fwd_kernel<FWD_BN, FWD_STAGES, FWD_NWG, FWD_XT>;
+    constexpr int smem = nce_fwd_smem_bytes<FWD_BN, FWD_STAGES, FWD_NWG, FWD_XT>();
+    static SmemAttrOnce attr;
+    B200_CHECK_CUDA(attr.ensure(kern, smem));
+    kern<<<pl.grid, 128 + FWD_NWG * 128, smem, s>>>(tx, ty, p);
+    B200_LAUNCH_CHECK();
+    r_slots = pl.r_slots; nrows_pad = pl.nrows_pad;
+  } else {
+    if ((rc = make_tmap_bf16_2d(&tx, i_hat, b_loc, D, D, 64, 128))) return rc;     // a CTA's own 128 rows of the 256-row super-block
+    if ((rc = make_tmap_bf16_2d(&ty, t_hat, b_glob, D, D, 64, 128))) return rc;    // a CTA's half of the 256-column tile
+    NceFwd2Params p{};
+    p.nrows = (int)b_loc; p.ncols = (int)b_glob; p.ct2 = pl.ct2; p.total = pl.total2; p.tiles_per_cluster = pl.tiles_per_cluster;
+    p.k1 = LOG2E / temperature; p.k2 = nce_k2(temperature);
+    p.r_part = r_part; p.c_part = c_part; p.nrows_pad = pl.nrows_pad2; p.kc = D / 64;
+    if (D == NCE_D) {
+      constexpr int smem = nce_fwd2_smem_bytes<NCE_KC, true>();
+      static SmemAttrOnce attr;
+      B200_CHECK_CUDA(attr.ensure(nce_fwd2_kernel<NCE_KC, true>, smem));
+      nce_fwd2_kernel<NCE_KC, true><<<pl.grid2, FWD2_THREADS, smem, s>>>(tx, ty, p);
+    } else {
+      constexpr int smem = nce_fwd2_smem_bytes<0, false>();
+      static SmemAttrOnce attr;
+      B200_CHECK_CUDA(attr.ensure(nce_fwd2_kernel<0, false>, smem));
+      nce_fwd2_kernel<0, false><<<pl.grid2, FWD2_THREADS, smem, s>>>(tx, ty, p);
+    }
+    B200_LAUNCH_CHECK();
+    r_slots = pl.r_slots2; nrows_pad = pl.nrows_pad2;
+  }
   const int n = (int)std::max(b_loc, b_glob);
-  nce_reduce_stats_kernel<<<(n + 63) / 64, 256, 0, s>>>(r_part, pl.r_slots, pl.nrows_pad, (int)b_loc, c_part, pl.row_blocks,
+  nce_reduce_stats_kernel<<<(n + 63) / 64, 256, 0, s>>>(r_part, r_slots, nrows_pad, (int)b_loc, c_part, pl.row_blocks,
                                                         (int)b_glob, r, c_partial);
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -1242,7 +1530,7 @@ extern "C" int b200clip_infonce_loss(const void* i_hat, const void* t_hat, int D
                                      long long row0, float temperature, const float* r, const float* c, long long c_lo,
                                      long long c_hi, float* rinvh, float* cinvh, double* sums, float* loss, void* workspace,
                                      size_t workspace_bytes, void* stream) {
-  B200_REQUIRE(D == NCE_D, "infonce: D=%d unsupported (kernels are built for D=%d)", D, NCE_D);
+  B200_REQUIRE(nce_dim_supported(D), "infonce: D=%d unsupported (need a multiple of 64, 64..1024)", D);
   B200_REQUIRE(b_loc > 0 && b_glob > 0 && row0 >= 0 && row0 + b_loc <= b_glob, "infonce_loss: bad row range");
   const NceFwdPlan pl = plan_fwd(b_loc, b_glob);
   if (workspace_bytes < pl.total_bytes) return fail(B200_ERR_WORKSPACE, "infonce_loss: workspace too small");
@@ -1254,7 +1542,7 @@ extern "C" int b200clip_infonce_loss(const void* i_hat, const void* t_hat, int D
   B200_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
   int grid = (int)std::min<long long>((b_glob + 63) / 64, 1024);      // 8 rows of the diagonal per warp at B = 32768
   nce_loss_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(i_hat), static_cast<const __nv_bfloat16*>(t_hat),
-                                       (int)b_loc, (int)b_glob, (int)row0, 1.0f / temperature, r, c, (int)c_lo, (int)c_hi,
+                                       D, (int)b_loc, (int)b_glob, (int)row0, 1.0f / temperature, r, c, (int)c_lo, (int)c_hi,
                                        rinvh, cinvh, partial, counter, sums, loss, static_cast<float>(nce_shift(temperature)));
   B200_LAUNCH_CHECK();
   return B200_OK;

@@ -122,6 +122,10 @@ __device__ __forceinline__ void bulk_load_g2s(uint32_t smem_dst, const void* gsr
 // Rows are staged by a producer warp with asynchronous bulk copies (one 16 KB copy per 16-row block) into
 // a 10-stage ring, so ~160 KB of loads are in flight per SM independent of the consumers' registers and occupancy;
 // the 8 consumer warps take 16-row blocks round-robin and read their MMA fragments from the padded rows.
+// PAIR / TOPK are compile-time: the decision code below is branch-heavy and the common call (pair mode or plain labels, no
+// top-k) should not carry the other modes' instructions (ncu, round 2: the kernel was ISSUE-bound -- 2458 warp instructions
+// per 16-row block at 53 % issue utilisation against 3.5 TB/s of DRAM reads).
+template <bool PAIR, bool TOPK>
 __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams p) {
   extern __shared__ __align__(128) uint8_t zs_smem[];
   // prompt fragments in consumption order: frag[(s*4 + t)*32 + lane] = P[8t + lane/4][32s + 8(lane%4) .. +7]
@@ -194,13 +198,21 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
     for (int t = 0; t < 4; ++t)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
-    float ss_a = 0.f, ss_b = 0.f;
+    // Row norms on the tensor cores too: with B[k][n] = X[n][k] the B fragment of lane (g = lane/4, q) IS that lane's own A data
+    // of row g, so one extra MMA per k16 step accumulates the Gram block X[0..15] . X[0..7]^T (and one more X . X[8..15]^T);
+    // ||row g||^2 is its diagonal: C[g][g] = c[g & 1] of lane 4g + g/2, C'[g+8][g] = c[2 + (g & 1)] of the same lane.  The
+    // unpack-and-FMA version cost 768 of the 2458 instructions per block (256 FFMA + 512 shift/mask).
+    float na[4] = {0.f, 0.f, 0.f, 0.f}, nb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
     for (int s = 0; s < 16; ++s) {
       const uint4 xa = ok_a ? pa[s * 4] : make_uint4(0u, 0u, 0u, 0u);
       const uint4 xb = ok_b ? pb[s * 4] : make_uint4(0u, 0u, 0u, 0u);
-      ss_a += sumsq8(xa);
-      ss_b += sumsq8(xb);
+      if (p.normalize_x) {
+        mma_bf16_16816(na, xa.x, xb.x, xa.y, xb.y, xa.x, xa.y);
+        mma_bf16_16816(na, xa.z, xb.z, xa.w, xb.w, xa.z, xa.w);
+        mma_bf16_16816(nb, xa.x, xb.x, xa.y, xb.y, xb.x, xb.y);
+        mma_bf16_16816(nb, xa.z, xb.z, xa.w, xb.w, xb.z, xb.w);
+      }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const uint4 f = s_frag[(s * 4 + t) * 32 + lane];
@@ -210,9 +222,10 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
     }
     __syncwarp();
     if (lane == 0) mbar_arrive_a(empty_a + 8 * st);       // stage consumed (smem reads above are complete: values are in registers)
-    // row norms: the 4 lanes of a quad hold disjoint K slices of rows r and r+8
-    ss_a += __shfl_xor_sync(0xffffffffu, ss_a, 1); ss_a += __shfl_xor_sync(0xffffffffu, ss_a, 2);
-    ss_b += __shfl_xor_sync(0xffffffffu, ss_b, 1); ss_b += __shfl_xor_sync(0xffffffffu, ss_b, 2);
+    // row norms: the diagonal entries live in lane 4r + r/2 of each quad
+    const int nsrc = (lane & 28) | (r >> 1);
+    const float ss_a = __shfl_sync(0xffffffffu, (r & 1) ? na[1] : na[0], nsrc);
+    const float ss_b = __shfl_sync(0xffffffffu, (r & 1) ? nb[3] : nb[2], nsrc);
     const float ka = (p.normalize_x ? 1.0f / fmaxf(sqrtf(ss_a), 1e-12f) : 1.0f) * p.inv_tau;
     const float kb = (p.normalize_x ? 1.0f / fmaxf(sqrtf(ss_b), 1e-12f) : 1.0f) * p.inv_tau;
 
@@ -225,7 +238,7 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
       float sc[8];
       int id[8];
       int cnt;
-      if (p.pair_mode) {
+      if (PAIR) {
         cnt = 4;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -262,12 +275,12 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
         if (ob > best || (ob == best && oi < best_id)) { best = ob; best_id = oi; }
       }
       bool near_top = false;
-      const bool rank_matters = (p.argmax != nullptr) || (p.topk > 0);
+      const bool rank_matters = (p.argmax != nullptr) || TOPK;
 #pragma unroll
       for (int t = 0; t < 8; ++t)
         if (t < cnt && id[t] < L && id[t] != best_id) near_top |= (best - sc[t]) < p.guard;
       // with top-k > 1 every adjacent gap matters; be conservative: any two labels closer than the guard
-      if (p.topk > 1) {
+      if (TOPK && p.topk > 1) {
 #pragma unroll
         for (int a = 0; a < 8; ++a)
 #pragma unroll
@@ -297,7 +310,7 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
         for (int t = 0; t < 8; ++t)
           if (t < cnt && id[t] < L) p.scores[row * L + id[t]] = sc[t];
       }
-      if (p.topk > 0 && p.topk_idx) {                     // warp-uniform branch: shuffles run on all lanes
+      if (TOPK && p.topk_idx) {                          // warp-uniform branch: shuffles run on all lanes
         // quad-cooperative top-k by repeated arg-max with removal
         const float mx = best;
         float den = 0.f;
@@ -392,7 +405,7 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
       }
       if (lane == 0) {
         double sc[ZS_MAXP];
-        for (int lab = 0; lab < L; ++lab) sc[lab] = p.pair_mode ? (l[2 * lab] - l[2 * lab + 1]) : l[lab];
+        for (int lab = 0; lab < L; ++lab) sc[lab] = PAIR ? (l[2 * lab] - l[2 * lab + 1]) : l[lab];
         emit_row_fp64(p, row, sc);
         if (p.guard_count) atomicAdd(p.guard_count, 1ull);
       }
@@ -428,9 +441,18 @@ extern "C" int b200clip_zeroshot_score(const void* x_bf16, long long ldx, long l
   p.scores = scores; p.guard_count = guard_count;
   const long long nblk16 = (n + 15) / 16;
   const int grid = static_cast<int>(std::min<long long>(nblk16, static_cast<long long>(num_sms())));
-  static SmemAttrOnce attr;
-  B200_CHECK_CUDA(attr.ensure(zeroshot_kernel, ZS_SMEM_BYTES));
-  zeroshot_kernel<<<grid, ZS_THREADS2, ZS_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(p);
+  static SmemAttrOnce attr[4];
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define B200_ZS_CASE(PAIR, TOPK, IDX)                                                         \
+  if ((pair_mode != 0) == PAIR && (topk > 0) == TOPK) {                                       \
+    B200_CHECK_CUDA(attr[IDX].ensure(zeroshot_kernel<PAIR, TOPK>, ZS_SMEM_BYTES));            \
+    zeroshot_kernel<PAIR, TOPK><<<grid, ZS_THREADS2, ZS_SMEM_BYTES, s>>>(p);                  \
+  }
+  B200_ZS_CASE(false, false, 0)
+  B200_ZS_CASE(false, true, 1)
+  B200_ZS_CASE(true, false, 2)
+  B200_ZS_CASE(true, true, 3)
+#undef B200_ZS_CASE
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -13,10 +13,10 @@ LOSS_TOL = 1e-3
 GRAD_TOL = 2e-2
 
 
-def _inputs(B, seed=11, corr=0.5):
+def _inputs(B, seed=11, corr=0.5, D=512):
     """unit rows, bf16-rounded; text correlated with image so the diagonal carries signal like trained CLIP."""
-    I = synth.unit_rows(seed, B, 512)
-    T = synth.unit_rows(seed + 1, B, 512)
+    I = synth.unit_rows(seed, B, D)
+    T = synth.unit_rows(seed + 1, B, D)
     T = R.l2_normalize(corr * I + (1 - corr) * T)
     return synth.bf16_round(I), synth.bf16_round(T)
 
@@ -43,21 +43,34 @@ def test_loss_and_grads_match_reference(B, tau):
     assert rel_l2(Tg.grad, dT_ref) < GRAD_TOL
 
 
-def test_statistics_match_flash_oracle():
+# D = 512: stationary-X CTA-pair kernel; other widths (768 = BASELINE.json configs[4], 256, 1024, 64): streamed-X variant.
+# b_loc < b_glob: a data-parallel rank's row block against all columns; 1: a single row; ragged sizes exercise the masks.
+@pytest.mark.parametrize("b_loc,b_glob,D", [(640, 640, 512), (300, 300, 512), (256, 1024, 512), (1, 130, 512), (4096, 4096, 512),
+                                            (640, 640, 768), (300, 1000, 768), (384, 384, 256), (200, 200, 1024), (129, 257, 64)])
+def test_statistics_match_flash_oracle(b_loc, b_glob, D):
     from b200clip import _lib, ops
     lib = _lib.load()
-    B, tau = 640, 0.07
-    I, T = _inputs(B)
-    r_ref, c_ref, diag_ref, m = R.contrastive_loss_flash(I.double(), T.double(), tau)
+    tau = 0.07
+    I, T = _inputs(b_glob, D=D)
+    row0 = (b_glob - b_loc) // 2 // 64 * 64
+    I = I[row0:row0 + b_loc]
+    r_ref, c_ref, diag_ref, m = R.contrastive_loss_flash(I.double(), T.double(), tau, row0=row0)
     d = dev()
-    ib, tb = I.to(d).to(torch.bfloat16), T.to(d).to(torch.bfloat16)
-    nb = lib.b200clip_infonce_workspace_bytes(B, B)
+    ib, tb = I.to(d).to(torch.bfloat16).contiguous(), T.to(d).to(torch.bfloat16)
+    nb = lib.b200clip_infonce_workspace_bytes(b_loc, b_glob)
     ws = torch.empty(nb, dtype=torch.uint8, device=d)
-    r, c = torch.empty(B, device=d), torch.empty(B, device=d)
-    _lib.check(lib.b200clip_infonce_fwd_stats(_lib.ptr(ib), _lib.ptr(tb), 512, B, B, tau, _lib.ptr(r), _lib.ptr(c), _lib.ptr(ws),
+    r, c = torch.empty(b_loc, device=d), torch.empty(b_glob, device=d)
+    _lib.check(lib.b200clip_infonce_fwd_stats(_lib.ptr(ib), _lib.ptr(tb), D, b_loc, b_glob, tau, _lib.ptr(r), _lib.ptr(c), _lib.ptr(ws),
                                               nb, _lib.stream_ptr()), "stats")
     assert rel_l2(r, r_ref) < 1e-4
     assert rel_l2(c, c_ref) < 1e-4
+    # the loss numerators (diagonal included) for this width
+    rinvh, cinvh = torch.empty_like(r), torch.empty_like(c)
+    sums = torch.empty(3, dtype=torch.float64, device=d)
+    _lib.check(lib.b200clip_infonce_loss(_lib.ptr(ib), _lib.ptr(tb), D, b_loc, b_glob, row0, tau, _lib.ptr(r), _lib.ptr(c), 0, b_glob,
+                                         _lib.ptr(rinvh), _lib.ptr(cinvh), _lib.ptr(sums), None, _lib.ptr(ws), nb, _lib.stream_ptr()), "loss")
+    assert abs(sums[2].item() - diag_ref.item()) <= 1e-4 * abs(diag_ref.item())
+    assert abs(sums[0].item() - torch.log(r_ref).sum().item()) <= 1e-4 * abs(torch.log(r_ref).sum().item()) + 1e-3
 
 
 def test_upstream_gradient_scale_and_determinism():
