@@ -169,9 +169,9 @@ def test_properties_at_full_size():
 
 def test_rejects_unsupported_shapes():
     import b200clip
-    I = synth.unit_rows(5, 64, 192).to(dev())
+    I = synth.unit_rows(5, 64, 200).to(dev())
     with pytest.raises(RuntimeError):
-        b200clip.contrastive_loss(I, I, 0.07)              # unit rows -> flash path; D = 192 is not built: loud failure, no fallback
+        b200clip.contrastive_loss(I, I, 0.07)              # unit rows -> flash path; D = 200 is not a multiple of 64: loud failure, no fallback
     with pytest.raises(RuntimeError):
         b200clip.contrastive_loss(torch.randn(64, 512, device=dev()), torch.randn(16, 512, device=dev()), 0.07)
 

@@ -62,7 +62,7 @@ def test_fused_adamw_state_dict_round_trip_and_torch_checkpoint():
     assert all(float(s["step"]) == 4.0 for s in ck["state"].values())
     a2 = [torch.nn.Parameter(p.detach().clone()) for p in a]
     oa2 = b200clip.FusedAdamW(a2, **kw)
-    oa2.load_state_dict(ck)
+    oa2.load_state_dict(copy.deepcopy(ck))          # load_state_dict adopts the tensors it is given: keep ck pristine
     run(oa2, a2, range(4, 7))
     # (2) torch.optim.AdamW checkpoint after 4 steps resumed by FusedAdamW
     b = [torch.nn.Parameter(p.clone()) for p in init]
@@ -75,7 +75,7 @@ def test_fused_adamw_state_dict_round_trip_and_torch_checkpoint():
     # (3) FusedAdamW checkpoint resumed by torch.optim.AdamW
     c2 = [torch.nn.Parameter(p.detach().clone()) for p in a]
     oc2 = torch.optim.AdamW(c2, **kw)
-    oc2.load_state_dict(ck)
+    oc2.load_state_dict(copy.deepcopy(ck))
     run(oc2, c2, range(4, 7))
     torch.cuda.synchronize()
     for got in (a2, b2, c2):
