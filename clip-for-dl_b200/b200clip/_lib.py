@@ -64,7 +64,7 @@ SIGNATURES = {
     "b200clip_infonce_fwd_stats": (i32, [vp, vp, i32, ll, ll, f32, vp, vp, vp, sz, vp]),
     "b200clip_infonce_loss": (i32, [vp, vp, i32, ll, ll, ll, f32, vp, vp, ll, ll, vp, vp, vp, vp, vp, sz, vp]),
     "b200clip_infonce_bwd_splits": (i32, [ll, ll]),
-    "b200clip_infonce_bwd": (i32, [vp, vp, i32, ll, ll, ll, f32, vp, vp, vp, vp, i32, vp, vp]),
+    "b200clip_infonce_bwd": (i32, [vp, vp, i32, ll, ll, ll, f32, vp, vp, vp, vp, i32, vp, i32, vp]),
     "b200clip_smallc_workspace_bytes": (sz, [ll, i32, i32]),
     "b200clip_mlbce_fwd_bwd": (i32, [vp, ll, vp, vp, i32, ll, ll, i32, i32, f32, vp, f64, vp, vp, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "b200clip_fc_bce_fwd_bwd": (i32, [vp, ll, vp, vp, vp, ll, ll, i32, i32, f64, f32, vp, vp, i32, vp, vp, vp, vp, vp, vp, sz, vp]),

@@ -392,15 +392,16 @@ def _timing_events():
 
 
 def infonce_backward(i_hat, t_hat, temperature, rinvh, cinvh, grad_scale: Optional[torch.Tensor], row0: int = 0,
-                     allow_splits: bool = False):
+                     allow_splits: bool = False, directions: int = 3):
     """Returns d_i [b_loc, D] f32 and d_t_partial [b_glob, D] f32 (this rank's contribution).  With allow_splits (data
-    parallel, b_loc << b_glob) d_i may come back as [S, b_loc, D] partial sums over column ranges (l2norm_bwd adds them)."""
+    parallel, b_loc << b_glob) d_i may come back as [S, b_loc, D] partial sums over column ranges (l2norm_bwd adds them).
+    directions: 3 = both gradients in one launch; 1 = d_i only (d_t is None); 2 = d_t only (d_i is None)."""
     b_loc, D = i_hat.shape
     b_glob = t_hat.shape[0]
     dev = i_hat.device
     splits = int(load().b200clip_infonce_bwd_splits(b_loc, b_glob)) if allow_splits else 1
-    d_i = torch.empty((splits, b_loc, D) if splits > 1 else (b_loc, D), dtype=torch.float32, device=dev)
-    d_t = torch.empty((b_glob, D), dtype=torch.float32, device=dev)
+    d_i = torch.empty((splits, b_loc, D) if splits > 1 else (b_loc, D), dtype=torch.float32, device=dev) if directions & 1 else None
+    d_t = torch.empty((b_glob, D), dtype=torch.float32, device=dev) if directions & 2 else None
     gs = None
     if grad_scale is not None:
         gs = _f32c(grad_scale.reshape(()))
@@ -409,7 +410,7 @@ def infonce_backward(i_hat, t_hat, temperature, rinvh, cinvh, grad_scale: Option
         e0, e1 = _timing_events()
         e0.record()
     check(load().b200clip_infonce_bwd(ptr(i_hat), ptr(t_hat), D, b_loc, b_glob, row0, temperature, ptr(rinvh), ptr(cinvh),
-                                      ptr(gs), ptr(d_i), splits, ptr(d_t), stream_ptr()), "infonce_bwd")
+                                      ptr(gs), ptr(d_i), splits, ptr(d_t), int(directions), stream_ptr()), "infonce_bwd")
     if ev is not None:
         e1.record()
         ev.append((e0, e1))

@@ -32,7 +32,12 @@ int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, in
   auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
   B200_REQUIRE(out0 != nullptr && al32(out0) && al32(out1) && al32(resid) && al32(aux), "gemm: out0/out1/resid/aux must be 32-byte aligned");
   B200_REQUIRE(ld0 % 16 == 0 && ld1 % 16 == 0 && ld_res % 16 == 0 && ld_aux % 16 == 0, "gemm: output/resid/aux leading dimensions must be multiples of 16 elements");
-  const int BN = (N % 256 == 0) ? 256 : 128;
+  // 128 x 256 tiles unless they would leave SMs idle: a [4096 x 512] output is only 64 such tiles for 148 SMs, and the kernel
+  // is then one wave of half-empty hardware (data-parallel ranks and BASELINE configs[1] live there); 128 x 128 tiles double
+  // the CTA count at the price of re-streaming the A tile twice (L2-resident at these sizes)
+  // (split-K launches already size their split count to one wave of 128 x 256 tiles)
+  const int tiles256 = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + 255) / 256);
+  const int BN = (N % 256 == 0 && (split_k > 1 || tiles256 >= num_sms())) ? 256 : 128;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.k_chunks = (K + GEMM_BK - 1) / GEMM_BK;

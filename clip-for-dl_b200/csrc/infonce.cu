@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "host.cuh"
+#include "infonce_bwd.cuh"
 #include "../../include/b200clip.h"
 
 namespace b200 {
@@ -598,25 +599,7 @@ constexpr int BWD_THREADS = 384;            // warp 0 TMA, 1 S-MMA issuer, 2 TME
 constexpr int nce_bwd4_smem_bytes() {
   return BWD4_XS * X_CHUNK_BYTES + (BWD4_TA + BWD4_TB) * BWD_GROUP_BYTES + 2 * BWD_G_BYTES + 512 + 1024;
 }
-constexpr int nce_bwd_smem_bytes() {
-  return NCE_KC * X_CHUNK_BYTES + (BWD_TA + BWD_TB) * BWD_GROUP_BYTES + BWD_G_BYTES + 512 + 1024;
-}
 
-struct NceBwdParams {
-  int nrows[2];             // valid X rows per direction
-  int ncols[2];             // valid Y rows per direction
-  int diag_off[2];          // diagonal: y column == x row + diag_off   (dir0: +row0, dir1: -row0)
-  const float* row_stat[2]; // 0.5 / r or c for X rows
-  const float* col_stat[2]; // 0.5 / c or r for Y rows
-  float* out[2];            // dX [nrows, 512] f32
-  const __nv_bfloat16* xmat[2];   // X matrices (for the TMEM-resident K range of version 3)
-  float k1, k2;
-  float out_scale;          // 1 / (B_glob * tau)
-  const float* grad_scale;  // optional device scalar multiplied into out_scale (upstream dLoss)
-  long long* prof;          // debug: per-role wait-cycle counters of one cluster (b200clip_debug_set_nce_prof) or null
-  int nsplit[2];            // version 4: column splits per direction (each split is its own cluster, writes its own partial dX)
-  long long split_stride[2];   // elements between the partial outputs of consecutive splits
-};
 
 // debug instrumentation (build with B200CLIP_NCE_PROF=1 python build.py): cycles spent inside each wait, accumulated per
 // role, and a per-tile timeline, for one cluster.  Compiled out of the product build.
@@ -650,270 +633,9 @@ struct NceBwdParams {
 #define NCE_PROF_END(role) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(BWD_THREADS, 1)
-nce_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x0, const __grid_constant__ CUtensorMap tmap_y0,
-               const __grid_constant__ CUtensorMap tmap_x1, const __grid_constant__ CUtensorMap tmap_y1,
-               const NceBwdParams p) {
-  const int dir = blockIdx.z;
-  const int h = blockIdx.y;                         // D-half owned by this CTA
-  const int rb = blockIdx.x;
-  const int nrows = dir ? p.nrows[1] : p.nrows[0];
-  const int ncols = dir ? p.ncols[1] : p.ncols[0];
-  if (rb * 128 >= nrows) return;                    // uniform per CTA, before any barrier / allocation
-  const CUtensorMap* tmap_x = dir == 0 ? &tmap_x0 : &tmap_x1;
-  const CUtensorMap* tmap_y = dir == 0 ? &tmap_y0 : &tmap_y1;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sX = smem;
-  uint8_t* sA = sX + NCE_KC * X_CHUNK_BYTES;
-  uint8_t* sB = sA + BWD_TA * BWD_GROUP_BYTES;
-  uint8_t* sG = sB + BWD_TB * BWD_GROUP_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + BWD_G_BYTES);
-  uint64_t* x_full = bars;                          // 1
-  uint64_t* a_full = bars + 1;                      // TA
-  uint64_t* a_empty = a_full + BWD_TA;              // TA
-  uint64_t* b_full = a_empty + BWD_TA;              // TB
-  uint64_t* b_empty = b_full + BWD_TB;              // TB
-  uint64_t* s_full = b_empty + BWD_TB;              // 2
-  uint64_t* s_empty = s_full + 2;                   // 2
-  uint64_t* g_full = s_empty + 2;                   // 2
-  uint64_t* g_empty = g_full + 2;                   // 2
-  uint64_t* acc_full = g_empty + 2;                 // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int nt = (ncols + BWD_BN - 1) / BWD_BN;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(tmap_x);
-    tma_prefetch_desc(tmap_y);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(x_full, 1);
-    for (int s = 0; s < BWD_TA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < BWD_TB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], 128);
-      mbar_init(&g_full[b], 128);
-      mbar_init(&g_empty[b], 1);
-    }
-    mbar_init(acc_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_acc = tmem_base;              // 256 fp32 columns: dX[:, h*256 .. +256)
-  const uint32_t tmem_s = tmem_base + 256;          // 2 x 32 columns
-
-  if (warp == 0) {
-    // ===================== TMA producer: one 16 KB group (4 K-chunks) per barrier =====================
-    const uint32_t xf = smem_u32(x_full);
-    const uint32_t af0 = smem_u32(a_full), ae0 = smem_u32(a_empty), bf0 = smem_u32(b_full), be0 = smem_u32(b_empty);
-    const uint32_t sa = smem_u32(sA), sb = smem_u32(sB), sx = smem_u32(sX);
-    if (elect_one()) {
-      mbar_arrive_expect_tx_a(xf, NCE_KC * X_CHUNK_BYTES);
-#pragma unroll
-      for (int kc = 0; kc < NCE_KC; ++kc) tma_load_2d_a(sx + kc * X_CHUNK_BYTES, tmap_x, xf, kc * 64, rb * 128);
-    }
-    __syncwarp();
-    int ia = 0, ib = 0;
-    uint32_t pa = 0, pb = 0;
-    const int k_in = h * 256, k_out = (1 - h) * 256;          // element offsets of the two K halves
-    for (int n = 0; n < nt; ++n) {
-      mbar_wait_a(be0 + 8 * ib, pb ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx_a(bf0 + 8 * ib, BWD_GROUP_BYTES);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          tma_load_2d_a(sb + ib * BWD_GROUP_BYTES + c * BWD_SLOT_BYTES, tmap_y, bf0 + 8 * ib, k_in + c * 64, n * BWD_BN);
-      }
-      __syncwarp();
-      mbar_wait_a(ae0 + 8 * ia, pa ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx_a(af0 + 8 * ia, BWD_GROUP_BYTES);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          tma_load_2d_a(sa + ia * BWD_GROUP_BYTES + c * BWD_SLOT_BYTES, tmap_y, af0 + 8 * ia, k_out + c * 64, n * BWD_BN);
-      }
-      __syncwarp();
-      if (++ia == BWD_TA) { ia = 0; pa ^= 1; }
-      if (++ib == BWD_TB) { ib = 0; pb ^= 1; }
-    }
-  } else if (warp == 1) {
-    // ===================== S-MMA issuer: S[buf] = X (128 x 512) . Y_tile^T (32 x 512) =====================
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, BWD_BN, false, false);
-    const uint32_t af0 = smem_u32(a_full), ae0 = smem_u32(a_empty), bf0 = smem_u32(b_full);
-    const uint32_t sf0 = smem_u32(s_full), se0 = smem_u32(s_empty);
-    const uint32_t x_in = desc_lo(smem_u32(sX) + h * 4 * X_CHUNK_BYTES, 16);
-    const uint32_t x_out = desc_lo(smem_u32(sX) + (1 - h) * 4 * X_CHUNK_BYTES, 16);
-    const uint32_t a_lo0 = desc_lo(smem_u32(sA), 16), b_lo0 = desc_lo(smem_u32(sB), 16);
-    mbar_wait_a(smem_u32(x_full), 0);
-    int ia = 0, ib = 0;
-    uint32_t pa = 0, pb = 0;
-    for (int n = 0; n < nt; ++n) {
-      const int buf = n & 1;
-      mbar_wait_a(se0 + 8 * buf, ((n >> 1) & 1) ^ 1);
-      mbar_wait_a(bf0 + 8 * ib, pb);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_s + buf * BWD_BN;
-      if (elect_one()) {
-        const uint32_t yb = b_lo0 + ib * (BWD_GROUP_BYTES >> 4);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            mma_ss_lo(d_tmem, x_in + c * (X_CHUNK_BYTES >> 4) + 2 * j, yb + c * (BWD_SLOT_BYTES >> 4) + 2 * j, idesc_s, (c | j) != 0);
-      }
-      __syncwarp();
-      mbar_wait_a(af0 + 8 * ia, pa);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t ya = a_lo0 + ia * (BWD_GROUP_BYTES >> 4);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            mma_ss_lo(d_tmem, x_out + c * (X_CHUNK_BYTES >> 4) + 2 * j, ya + c * (BWD_SLOT_BYTES >> 4) + 2 * j, idesc_s, true);
-        tc_commit_a(ae0 + 8 * ia);                  // ring A group is free once these MMAs have read it
-        tc_commit_a(sf0 + 8 * buf);                 // S tile complete -> epilogue
-      }
-      __syncwarp();
-      if (++ia == BWD_TA) { ia = 0; pa ^= 1; }
-      if (++ib == BWD_TB) { ib = 0; pb ^= 1; }
-    }
-  } else if (warp == 2) {
-    // ===================== dX-MMA issuer: acc += G_tile (128 x 32, bf16 in smem) . Y_tile[:, half] (MN-major) ==========
-    constexpr uint32_t idesc_g = make_idesc_bf16(128, 256, false, true);
-    const uint32_t gf0 = smem_u32(g_full), ge0 = smem_u32(g_empty), be0 = smem_u32(b_empty);
-    const uint32_t g_lo = desc_lo(smem_u32(sG), 16);
-    const uint32_t y_lo0 = desc_lo(smem_u32(sB), BWD_SLOT_BYTES);       // LBO = stride between 64-wide D groups
-    int ib = 0;
-    for (int n = 0; n < nt; ++n) {
-      const int par = n & 1;
-      mbar_wait_a(gf0 + 8 * par, (n >> 1) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t yb = y_lo0 + ib * (BWD_GROUP_BYTES >> 4);
-#pragma unroll
-        for (int jj = 0; jj < BWD_BN / 16; ++jj)
-          mma_ss_lo(tmem_acc, g_lo + par * 4 + jj * 2, yb + jj * (2048 >> 4), idesc_g, (n | jj) != 0);
-        tc_commit_a(be0 + 8 * ib);                  // ring B group no longer needed
-        tc_commit_a(ge0 + 8 * par);                 // G half-buffer free
-      }
-      __syncwarp();
-      if (++ib == BWD_TB) ib = 0;
-    }
-    if (elect_one()) tc_commit(acc_full);
-    __syncwarp();
-  } else if (warp >= 4) {
-    // ===================== epilogue warpgroups: tile n -> warpgroup n & 1 =====================
-    const int w = (warp - 4) >> 2;
-    const int q = warp & 3;
-    const int row_l = q * 32 + lane;
-    const int row = rb * 128 + row_l;
-    const bool row_ok = row < nrows;
-    const float rstat = row_ok ? (dir ? p.row_stat[1] : p.row_stat[0])[row] : 0.f;
-    const float* cstat = dir ? p.col_stat[1] : p.col_stat[0];
-    const int diag_col = row + (dir ? p.diag_off[1] : p.diag_off[0]);
-    const int warp_diag_lo = rb * 128 + q * 32 + (dir ? p.diag_off[1] : p.diag_off[0]);   // diag cols of this warp's rows
-    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t sf = smem_u32(s_full) + 8 * w, se = smem_u32(s_empty) + 8 * w;
-    const uint32_t gf = smem_u32(g_full) + 8 * w, ge = smem_u32(g_empty) + 8 * w;
-    uint8_t* g_row = sG + row_l * 128;
-    uint32_t ph = 0;
-    for (int n = w; n < nt; n += 2) {
-      const int col0 = n * BWD_BN;
-      const bool full_tile = col0 + BWD_BN <= ncols;                                      // uniform
-      const bool diag_tile = (col0 < warp_diag_lo + 32) && (col0 + BWD_BN > warp_diag_lo);  // warp-uniform
-      // column statistics first: their L2 latency hides behind the wait for the S tile
-      float cs[32];
-      if (full_tile) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 c4 = __ldg(reinterpret_cast<const float4*>(cstat + col0 + i));
-          cs[i] = c4.x; cs[i + 1] = c4.y; cs[i + 2] = c4.z; cs[i + 3] = c4.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) cs[i] = (col0 + i < ncols) ? cstat[col0 + i] : 0.f;
-      }
-      mbar_wait_a(sf, ph);
-      tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_x32(tmem_s + lane_base + w * BWD_BN, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive_a(se);
-      uint32_t packed[16];
-      if (full_tile && !diag_tile) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float g0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.k1, -p.k2)) * (rstat + cs[i]);
-          const float g1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.k1, -p.k2)) * (rstat + cs[i + 1]);
-          packed[i / 2] = pack_bf16x2(g0, g1);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float g[2];
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int col = col0 + i + t;
-            float gv = fast_exp2(fmaf(__uint_as_float(v[i + t]), p.k1, -p.k2)) * (rstat + cs[i + t]);
-            if (col == diag_col) gv -= 1.0f;           // G_ii = p_ii - 1 rounded as a whole: error relative to G_ii itself
-            g[t] = (col < ncols) ? gv : 0.f;
-          }
-          packed[i / 2] = pack_bf16x2(g[0], g[1]);
-        }
-      }
-      mbar_wait_a(ge, ph ^ 1);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(g_row + (((w * 4 + c) ^ (row_l & 7)) << 4)) =
-            make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
-      fence_proxy_async_smem();
-      mbar_arrive_a(gf);
-      ph ^= 1;
-    }
-    // final: dX[:, h*256 + w*128 .. +128) = acc * scale
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    float scale = p.out_scale;
-    if (p.grad_scale) scale *= *p.grad_scale;
-    float* orow = (dir ? p.out[1] : p.out[0]) + static_cast<long long>(row) * NCE_D + h * 256 + w * 128;
-#pragma unroll 1
-    for (int c = 0; c < 128; c += 32) {
-      uint32_t v[32];
-      tmem_ld_x32(tmem_acc + lane_base + w * 128 + c, v);
-      tmem_ld_wait();
-      if (row_ok) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {           // 256-bit stores: full 32-byte sectors from a row-per-thread layout
-          float f8[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) f8[t] = __uint_as_float(v[i + t]) * scale;
-          st_global_f32x8(orow + c + i, f8);
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
-}
-
 // ------------------------------------------------------------------------------------------------
-// Pass 2, CTA-pair kernel (default).  The two D-half CTAs of a row block form a cluster (1x2x1).
+// Pass 2, CTA-pair kernel of round 1 (D = 512 only; kept behind B200CLIP_BWD_VARIANT=4 as the A/B baseline of
+// nce_bwdc_kernel<2> in infonce_bwd.cuh, which is the same design generalised to D = 256 NC).  The two D-half CTAs of a row block form a cluster (1x2x1).
 //  * Column tile n (32 columns) is OWNED by CTA (n & 1): only the owner recomputes S and forms G for it, so each logit is
 //    exponentiated once per direction instead of once per D-half (executed tensor work per direction: S once + dX).
 //  * The owner's epilogue warpgroup w = (own tile index & 1) owns G slot (owner, w) in BOTH CTAs: an 8 KB [128 x 32] bf16
@@ -1560,13 +1282,39 @@ extern "C" int b200clip_infonce_bwd_splits(long long b_loc, long long b_glob) {
   return static_cast<int>(std::max<long long>(1, std::min<long long>(8, s)));
 }
 
+template <int NC>
+static int launch_bwdc(const CUtensorMap& tx0, const CUtensorMap& ty0, const CUtensorMap& tx1, const CUtensorMap& ty1,
+                       const NceBwdParams& p, dim3 grid, cudaStream_t s) {
+  static SmemAttrOnce attr;
+  B200_CHECK_CUDA(attr.ensure(nce_bwdc_kernel<NC>, BcCfg<NC>::SMEM));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(BC_THREADS);
+  cfg.dynamicSmemBytes = BcCfg<NC>::SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = NC; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, nce_bwdc_kernel<NC>, tx0, ty0, tx1, ty1, p));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// directions: bit 0 = dI (direction 0), bit 1 = dT partial (direction 1).  The data-parallel step launches direction 1 first
+// so that its reduce-scatter overlaps direction 0; a single-GPU step launches both at once (3).
 extern "C" int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D, long long b_loc, long long b_glob,
                                     long long row0, float temperature, const float* rinvh, const float* cinvh,
-                                    const float* grad_scale, float* d_i, int d_i_splits, float* d_t_partial, void* stream) {
-  B200_REQUIRE(D == NCE_D, "infonce: D=%d unsupported (kernels are built for D=%d)", D, NCE_D);
+                                    const float* grad_scale, float* d_i, int d_i_splits, float* d_t_partial, int directions,
+                                    void* stream) {
+  B200_REQUIRE(D == 512 || D == 768, "infonce_bwd: D=%d unsupported (the backward kernel is built for D = 512 and 768)", D);
   B200_REQUIRE(b_loc > 0 && b_glob > 0 && row0 >= 0 && row0 + b_loc <= b_glob, "infonce_bwd: bad row range");
+  B200_REQUIRE(directions >= 1 && directions <= 3, "infonce_bwd: directions must be 1 (dI), 2 (dT) or 3 (both)");
+  B200_REQUIRE((!(directions & 1) || d_i) && (!(directions & 2) || d_t_partial), "infonce_bwd: missing output for a requested direction");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(d_i) & 31u) == 0 && (reinterpret_cast<uintptr_t>(d_t_partial) & 31u) == 0 &&
                aligned16(rinvh) && aligned16(cinvh), "infonce_bwd: d_i / d_t_partial must be 32-byte aligned, statistics 16-byte");
+  B200_REQUIRE(temperature >= NCE_MIN_TAU, "infonce: temperature %g is below %g", temperature, NCE_MIN_TAU);
   CUtensorMap tx0, ty0, tx1, ty1;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tx0, i_hat, b_loc, D, D, 64, 128))) return rc;      // dir 0: X = I rows
@@ -1586,23 +1334,22 @@ extern "C" int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D,
   p.nsplit[0] = d_i_splits; p.split_stride[0] = b_loc * static_cast<long long>(D);
   p.nsplit[1] = 1; p.split_stride[1] = 0;
   p.prof = g_nce_prof;
-  constexpr int smem = nce_bwd_smem_bytes();
-  static SmemAttrOnce attr4, attr1;
-  static const int variant = [] {      // 4: CTA-pair kernel (default); 1: independent D-half CTAs (B200CLIP_BWD_VARIANT=1, tests only)
-    const char* e = getenv("B200CLIP_BWD_VARIANT");
-    return (e && atoi(e) == 1) ? 1 : 4;
-  }();
-  B200_CHECK_CUDA(attr4.ensure(nce_bwd4_kernel, nce_bwd4_smem_bytes()));
-  B200_CHECK_CUDA(attr1.ensure(nce_bwd_kernel, smem));
-  const long long gx = std::max((b_glob + 127) / 128, ((b_loc + 127) / 128) * d_i_splits);
-  dim3 grid(static_cast<unsigned>(variant == 4 ? gx : (b_glob + 127) / 128), 2, 2);
-  B200_REQUIRE(variant == 4 || d_i_splits == 1, "infonce_bwd: column splits need the CTA-pair kernel");
-  if (variant == 4)
-    nce_bwd4_kernel<<<grid, BWD_THREADS, nce_bwd4_smem_bytes(), static_cast<cudaStream_t>(stream)>>>(tx0, ty0, tx1, ty1, p);
-  else
-    nce_bwd_kernel<<<grid, BWD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tx0, ty0, tx1, ty1, p);
-  B200_LAUNCH_CHECK();
-  return B200_OK;
+  p.dir_base = directions == 2 ? 1 : 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long gx0 = ((b_loc + 127) / 128) * d_i_splits, gx1 = (b_glob + 127) / 128;
+  const long long gx = directions == 3 ? std::max(gx0, gx1) : (directions == 1 ? gx0 : gx1);
+  const unsigned gz = directions == 3 ? 2u : 1u;
+  // B200CLIP_BWD_VARIANT=4: round 1's pair kernel (D = 512, both directions in one launch) for A/B measurements
+  static const int variant = [] { const char* e = getenv("B200CLIP_BWD_VARIANT"); return (e && atoi(e) == 4) ? 4 : 5; }();
+  if (variant == 4 && D == NCE_D && directions == 3) {
+    static SmemAttrOnce attr4;
+    B200_CHECK_CUDA(attr4.ensure(nce_bwd4_kernel, nce_bwd4_smem_bytes()));
+    nce_bwd4_kernel<<<dim3(static_cast<unsigned>(gx), 2, 2), BWD_THREADS, nce_bwd4_smem_bytes(), s>>>(tx0, ty0, tx1, ty1, p);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
+  if (D == 512) return launch_bwdc<2>(tx0, ty0, tx1, ty1, p, dim3(static_cast<unsigned>(gx), 2, gz), s);
+  return launch_bwdc<3>(tx0, ty0, tx1, ty1, p, dim3(static_cast<unsigned>(gx), 3, gz), s);
 }
 
 // the shift m (natural-log units) that b200clip_infonce_loss's sums are relative to: loss = m + (sums[0] + sums[1]) / (2B) - sums[2] / B

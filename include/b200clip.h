@@ -141,11 +141,13 @@ int b200clip_infonce_loss(const void* i_hat, const void* t_hat, int D, long long
                           float temperature, const float* r, const float* c, long long c_lo, long long c_hi, float* rinvh,
                           float* cinvh, double* sums, float* loss, void* workspace, size_t workspace_bytes, void* stream);
 /* d_i is [d_i_splits][b_loc][D]: partial sums over column ranges (1 <= splits <= 8; b200clip_infonce_bwd_splits suggests
- * a count that balances the grid when b_loc << b_glob); their sum is the gradient. */
+ * a count that balances the grid when b_loc << b_glob); their sum is the gradient.  D = 512 or 768.  directions: 1 = d_i only,
+ * 2 = d_t_partial only, 3 = both in one launch (the data-parallel step launches 2 first so that the reduce-scatter of
+ * d_t_partial overlaps 1). */
 int b200clip_infonce_bwd_splits(long long b_loc, long long b_glob);
 int b200clip_infonce_bwd(const void* i_hat, const void* t_hat, int D, long long b_loc, long long b_glob, long long row0,
                          float temperature, const float* rinvh, const float* cinvh, const float* grad_scale, float* d_i,
-                         int d_i_splits, float* d_t_partial, void* stream);
+                         int d_i_splits, float* d_t_partial, int directions, void* stream);
 
 /* ---- a-S: contrastive_clip_loss_function(text_projection, image_projection, temperature, mode) -- 0426/train.py:127-152
  * (soft targets softmax((I I^T + T T^T)/2 * tau), NOT detached; cross_entropy :118-125).  fp32 throughout (un-normalised inputs:

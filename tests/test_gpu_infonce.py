@@ -29,10 +29,13 @@ def _oracle(I, T, tau):
     return loss.detach(), I.grad, T.grad
 
 
-@pytest.mark.parametrize("B,tau", [(128, 0.07), (256, 0.07), (200, 0.07), (1000, 0.07), (384, 1.0), (2048, 0.07), (33, 0.5)])
-def test_loss_and_grads_match_reference(B, tau):
+# D = 768 (BASELINE.json configs[4], 0426/config.py:30 `shared_embedding_size`): 3-CTA clusters in the backward pass
+@pytest.mark.parametrize("B,tau,D", [(128, 0.07, 512), (256, 0.07, 512), (200, 0.07, 512), (1000, 0.07, 512), (384, 1.0, 512),
+                                     (2048, 0.07, 512), (33, 0.5, 512), (128, 0.07, 768), (200, 0.07, 768), (1000, 0.07, 768),
+                                     (2048, 0.07, 768), (97, 1.0, 768)])
+def test_loss_and_grads_match_reference(B, tau, D):
     import b200clip
-    I, T = _inputs(B)
+    I, T = _inputs(B, D=D)
     loss_ref, dI_ref, dT_ref = _oracle(I, T, tau)
     Ig = I.to(dev()).requires_grad_(True)
     Tg = T.to(dev()).requires_grad_(True)
@@ -87,15 +90,15 @@ def test_upstream_gradient_scale_and_determinism():
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])     # bit-reproducible
 
 
-@pytest.mark.parametrize("W", [2, 4, 8])
-def test_rank_partitioned_equals_monolithic(W):
+@pytest.mark.parametrize("W,D", [(2, 512), (4, 512), (8, 512), (4, 768)])
+def test_rank_partitioned_equals_monolithic(W, D):
     """Simulated data-parallel ranks on ONE GPU: each 'rank' runs the kernels on its row block against all columns;
     column sums are SUM-combined and dT partials summed (what all_reduce / reduce_scatter do across GPUs)."""
     from b200clip import _lib, ops
     lib = _lib.load()
     B, tau = 1024, 0.07
     n = B // W
-    I, T = _inputs(B)
+    I, T = _inputs(B, D=D)
     loss_ref, dI_ref, dT_ref = _oracle(I, T, tau)
     d = dev()
     ib, tb = I.to(d).to(torch.bfloat16), T.to(d).to(torch.bfloat16)
@@ -105,23 +108,28 @@ def test_rank_partitioned_equals_monolithic(W):
     for k in range(W):
         r, c = torch.empty(n, device=d), torch.empty(B, device=d)
         blk = ib[k * n:(k + 1) * n].contiguous()
-        _lib.check(lib.b200clip_infonce_fwd_stats(_lib.ptr(blk), _lib.ptr(tb), 512, n, B, tau, _lib.ptr(r), _lib.ptr(c),
+        _lib.check(lib.b200clip_infonce_fwd_stats(_lib.ptr(blk), _lib.ptr(tb), D, n, B, tau, _lib.ptr(r), _lib.ptr(c),
                                                   _lib.ptr(ws), nb, _lib.stream_ptr()), "stats")
         rs.append(r)
         cs += c
     total = torch.zeros(3, dtype=torch.float64, device=d)
-    dI, dT = [], torch.zeros(B, 512, device=d)
+    dI, dT = [], torch.zeros(B, D, device=d)
     for k in range(W):
         blk = ib[k * n:(k + 1) * n].contiguous()
         rinvh, cinvh = torch.empty(n, device=d), torch.empty(B, device=d)
         sums = torch.empty(3, dtype=torch.float64, device=d)
-        _lib.check(lib.b200clip_infonce_loss(_lib.ptr(blk), _lib.ptr(tb), 512, n, B, k * n, tau, _lib.ptr(rs[k]), _lib.ptr(cs),
+        _lib.check(lib.b200clip_infonce_loss(_lib.ptr(blk), _lib.ptr(tb), D, n, B, k * n, tau, _lib.ptr(rs[k]), _lib.ptr(cs),
                                              k * n, (k + 1) * n, _lib.ptr(rinvh), _lib.ptr(cinvh), _lib.ptr(sums), None,
                                              _lib.ptr(ws), nb, _lib.stream_ptr()), "loss")
         total += sums
         # allow_splits: with b_loc << b_glob the kernel cuts direction 0's columns into ranges (partial d_i sums)
         d_i, d_t = ops.infonce_backward(blk, tb, tau, rinvh, cinvh, None, row0=k * n, allow_splits=True)
         assert (d_i.dim() == 3) == (W >= 3), d_i.shape
+        # the two directions launched separately (the data-parallel step does that to overlap the reduce-scatter of d_t with
+        # direction 0) are bit-identical to the combined launch
+        d_i1, none_t = ops.infonce_backward(blk, tb, tau, rinvh, cinvh, None, row0=k * n, allow_splits=True, directions=1)
+        none_i, d_t2 = ops.infonce_backward(blk, tb, tau, rinvh, cinvh, None, row0=k * n, allow_splits=True, directions=2)
+        assert none_t is None and none_i is None and torch.equal(d_i1, d_i) and torch.equal(d_t2, d_t)
         dI.append(d_i.sum(0) if d_i.dim() == 3 else d_i)
         dT += d_t
     loss = 1.0 / tau + (total[0] + total[1]) / (2.0 * B) - total[2] / B
