@@ -265,7 +265,12 @@ def measure_head(args, cfg, rank, world, dev, steps, warmup, eager=False, want_e
 
         def step(xi=None, xt=None, lab=None):
             return gstep(xi, xt, None, lab)
-    graph_events = (list(ops.KERNEL_EVENTS["infonce_bwd"][-1:]), list(ops.KERNEL_EVENTS["infonce_fwd"][-1:]))
+    # Every event created while the graph was captured is referenced by one of its event-record nodes: they must stay alive as
+    # long as the graph does.  A data-parallel step launches the backward kernel twice (dT direction, then dI): its time is the
+    # sum of the two launches.
+    n_bwd = 2 if world > 1 else 1
+    keep_alive = (list(ops.KERNEL_EVENTS["infonce_bwd"]), list(ops.KERNEL_EVENTS["infonce_fwd"]))
+    graph_events = (keep_alive[0][-n_bwd:], keep_alive[1][-1:])
     ops.KERNEL_EVENTS["infonce_bwd"] = ops.KERNEL_EVENTS["infonce_fwd"] = None
 
     for _ in range(max(warmup, 3)):
@@ -288,18 +293,19 @@ def measure_head(args, cfg, rank, world, dev, steps, warmup, eager=False, want_e
     ms_total = e0.elapsed_time(e1)
     if eager:
         launches = (lib.b200clip_launch_count() - n0) // steps
-        bwd_ms = [a.elapsed_time(b) for a, b in ops.KERNEL_EVENTS["infonce_bwd"]]
+        ev = ops.KERNEL_EVENTS["infonce_bwd"]
+        bwd_ms = [sum(a.elapsed_time(b) for a, b in ev[i:i + n_bwd]) for i in range(0, len(ev), n_bwd)]
         fwd_ms = [a.elapsed_time(b) for a, b in ops.KERNEL_EVENTS["infonce_fwd"]]
         ops.KERNEL_EVENTS["infonce_bwd"] = ops.KERNEL_EVENTS["infonce_fwd"] = None
         kernel_timing = "CUDA events around every launch inside the timed region"
     else:
         # kernels per replay = kernels the library launched while the graph was captured (counted once, below)
-        last_bwd = [a.elapsed_time(b) for a, b in graph_events[0]]        # the last timed step's launch
+        last_bwd = [sum(a.elapsed_time(b) for a, b in graph_events[0])]   # the last timed step's launch(es)
         bwd_ms, fwd_ms = [], []
         for _ in range(steps):                           # same replay, read back step by step (sync between steps)
             step()
             torch.cuda.synchronize()
-            bwd_ms += [a.elapsed_time(b) for a, b in graph_events[0]]
+            bwd_ms.append(sum(a.elapsed_time(b) for a, b in graph_events[0]))
             fwd_ms += [a.elapsed_time(b) for a, b in graph_events[1]]
         kernel_timing = (f"external event-record nodes around the launch inside the step graph; mean of {steps} replays "
                          f"read back one by one right after the timed region (last timed step: {last_bwd[0]:.3f} ms)")
@@ -382,14 +388,14 @@ def measure_head(args, cfg, rank, world, dev, steps, warmup, eager=False, want_e
     torch.cuda.synchronize()
     par = {"loss": float(loss_n.item()), "dropout": "off for this leg"}
     if world > 1:
-        solo = [dist.new_group([r]) for r in range(world)]          # every rank creates every group; rank 0 uses its own
         gw_n = head.image_projector.fc.weight.grad.detach().clone()
         if rank == 0:
             fx_img, fx_txt, flab = synth_rows(cfg, 0, B)
             fxi, fxt = fx_img.to(dev).requires_grad_(True), fx_txt.to(dev).requires_grad_(True)
             for p in head.parameters():
                 p.grad = None
-            head.group = solo[0]
+            from b200clip import dp
+            head.group = dp.SOLO                         # world 1 on this rank: the single-GPU step on the full global batch
             loss_1 = head(fxi, fxt, class_text, flab.to(dev))
             loss_1.backward()
             head.group = None
@@ -400,12 +406,16 @@ def measure_head(args, cfg, rank, world, dev, steps, warmup, eager=False, want_e
                         "dx_img_rel_l2": rel(xi.grad.float(), fxi.grad[:b_loc].float()),
                         "dx_txt_rel_l2": rel(xt.grad.float(), fxt.grad[:b_loc].float()),
                         "dw_rel_l2": rel(gw_n, head.image_projector.fc.weight.grad)})
-            par["ok"] = bool(par["loss_rel"] <= 1e-5 and par["dx_img_rel_l2"] <= 1e-3 and par["dx_txt_rel_l2"] <= 1e-3 and
+            # the input gradients are bf16 tensors (bf16 inputs): fp32-level differences of the collectives' summation order
+            # (measured: d_ihat 2e-7, reduce-scattered d_that 3e-5, tools/dbg_dp_parity.py) flip a fraction of the bf16
+            # roundings along the projection backward, hence 5e-3 there and 1e-3 on the fp32 weight gradient
+            par["ok"] = bool(par["loss_rel"] <= 1e-5 and par["dx_img_rel_l2"] <= 5e-3 and par["dx_txt_rel_l2"] <= 5e-3 and
                              par["dw_rel_l2"] <= 1e-3)
         dist.barrier()
     out["parity"] = par
     if not eager:
-        gstep.close()                                    # a live graph holding NCCL kernels would block communicator teardown
+        gstep.close()
+    del keep_alive                                    # a live graph holding NCCL kernels would block communicator teardown
     return out
 
 

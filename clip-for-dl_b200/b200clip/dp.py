@@ -15,11 +15,26 @@ import torch
 import torch.distributed as dist
 
 
+class _Solo:
+    """Sentinel process group: "this rank alone" (world 1) even when torch.distributed is initialised -- lets a rank run the
+    single-GPU step next to the data-parallel one (bench.py's parity leg) without creating single-rank NCCL communicators."""
+
+    def __repr__(self):
+        return "dp.SOLO"
+
+
+SOLO = _Solo()
+
+
 def world(group=None) -> int:
+    if group is SOLO:
+        return 1
     return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
 
 
 def rank(group=None) -> int:
+    if group is SOLO:
+        return 0
     return dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
 
 
