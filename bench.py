@@ -294,18 +294,20 @@ def measure_head(args, cfg, rank, world, dev, steps, warmup, eager=False, want_e
     if eager:
         launches = (lib.b200clip_launch_count() - n0) // steps
         ev = ops.KERNEL_EVENTS["infonce_bwd"]
-        bwd_ms = [sum(a.elapsed_time(b) for a, b in ev[i:i + n_bwd]) for i in range(0, len(ev), n_bwd)]
+        bwd_ms = [max(ev[i][0].elapsed_time(e1) for _, e1 in ev[i:i + n_bwd]) for i in range(0, len(ev), n_bwd)]
         fwd_ms = [a.elapsed_time(b) for a, b in ops.KERNEL_EVENTS["infonce_fwd"]]
         ops.KERNEL_EVENTS["infonce_bwd"] = ops.KERNEL_EVENTS["infonce_fwd"] = None
         kernel_timing = "CUDA events around every launch inside the timed region"
     else:
         # kernels per replay = kernels the library launched while the graph was captured (counted once, below)
-        last_bwd = [sum(a.elapsed_time(b) for a, b in graph_events[0])]   # the last timed step's launch(es)
+        # data parallel: the two direction launches run concurrently on two streams -> span from the first start to the last end
+        span = lambda evs: max(evs[0][0].elapsed_time(e1) for _, e1 in evs)
+        last_bwd = [span(graph_events[0])]                                # the last timed step's launch(es)
         bwd_ms, fwd_ms = [], []
         for _ in range(steps):                           # same replay, read back step by step (sync between steps)
             step()
             torch.cuda.synchronize()
-            bwd_ms.append(sum(a.elapsed_time(b) for a, b in graph_events[0]))
+            bwd_ms.append(span(graph_events[0]))
             fwd_ms += [a.elapsed_time(b) for a, b in graph_events[1]]
         kernel_timing = (f"external event-record nodes around the launch inside the step graph; mean of {steps} replays "
                          f"read back one by one right after the timed region (last timed step: {last_bwd[0]:.3f} ms)")

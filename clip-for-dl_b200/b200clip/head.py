@@ -34,8 +34,8 @@ TWO_STREAM_MAX_ROWS = 8192
 _SIDE_STREAMS = {}
 
 
-def _side_stream(device) -> torch.cuda.Stream:
-    key = torch.device(device).index
+def _side_stream(device, which: int = 0) -> torch.cuda.Stream:
+    key = (torch.device(device).index, which)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]
@@ -133,22 +133,29 @@ def head_backward(tensors, meta, g):
     g = ops._f32c(g).reshape(())
     W = meta["W"]
     b_loc = y_txt.shape[0]
+    main = torch.cuda.current_stream()
+    side = _side_stream(ihat.device) if (b_loc <= TWO_STREAM_MAX_ROWS or W > 1) else None
+    nce_side = None
     if W > 1:
-        # direction 1 (dT partial, all B rows of T against the local columns) first: its reduce-scatter (58 MB per rank at
-        # B = 32768, W = 8) then travels while direction 0 (dI) computes
+        # The two directions are separate launches on two streams: direction 1 (dT partial, all B rows of T against the local
+        # columns) is enqueued first and its reduce-scatter (58 MB per rank at B = 32768, W = 8) starts the moment it ends;
+        # direction 0 (dI) runs concurrently and fills the SMs direction 1 leaves idle in its last wave (launched back to back
+        # on ONE stream the two kernels cost 16 % more than the combined launch: 256 long CTAs are 1.7 waves of 148 SMs).
+        nce_side = _side_stream(ihat.device, 1)
+        nce_side.wait_stream(main)
         _, d_that = ops.infonce_backward(ihat, that_all, meta["tau_nce"], rinvh, cinvh, g, row0=row0, directions=2)
         d_that_loc, work = dp.scatter_sum_rows(d_that, group, async_op=True)
-        d_ihat, _ = ops.infonce_backward(ihat, that_all, meta["tau_nce"], rinvh, cinvh, g, row0=row0, allow_splits=True, directions=1)
+        with torch.cuda.stream(nce_side):
+            d_ihat, _ = ops.infonce_backward(ihat, that_all, meta["tau_nce"], rinvh, cinvh, g, row0=row0, allow_splits=True,
+                                             directions=1)
     else:
         d_ihat, d_that = ops.infonce_backward(ihat, that_all, meta["tau_nce"], rinvh, cinvh, g, row0=row0, allow_splits=True)
         d_that_loc, work = d_that, None
-    side = _side_stream(ihat.device) if b_loc <= TWO_STREAM_MAX_ROWS else None
-    main = torch.cuda.current_stream()
     that_loc = that_all[row0:row0 + b_loc]                           # this rank's normalised text rows (bf16)
-    # text side (needs the reduce-scattered dT) on the side stream, image side on the main stream: two chains of ~12 kernels
-    # that are each a fraction of a wave at per-rank batch sizes
+    # text side (needs only the reduce-scattered dT) on the side stream, image side (needs dI) on the main stream: two chains of
+    # ~12 kernels that are each a fraction of a wave at per-rank batch sizes
     if side is not None:
-        side.wait_stream(main)
+        side.wait_stream(main)                       # forks after the dT kernel / reduce-scatter enqueue, NOT after dI
     with torch.cuda.stream(side if side is not None else main):
         if side is not None:
             dp.wait(work)
@@ -156,6 +163,8 @@ def head_backward(tensors, meta, g):
                               l2=(d_that_loc, that_loc, inv_txt, None, None), drop_seed_dev=seed_dev)
             txt_grads, txt_work = dp.allreduce_flat([gt[1], gt[2], gt[3], gt[4], gt[5], gt[6]], group, async_op=True)
             dp.wait(txt_work)
+    if nce_side is not None:
+        main.wait_stream(nce_side)
     # image side: the L2-normalisation backward (+ g * the two BCE heads' input gradient from the forward pass) runs inside
     # the projection block's LayerNorm-backward kernel
     if db_raw is not None:
