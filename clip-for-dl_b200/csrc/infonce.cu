@@ -1278,7 +1278,12 @@ extern "C" void b200clip_debug_set_nce_prof(void* buf) { g_nce_prof = static_cas
 // the grid; each split writes its own partial d_i (summed by the consumer, b200clip_l2norm_bwd's dy_partials).
 extern "C" int b200clip_infonce_bwd_splits(long long b_loc, long long b_glob) {
   if (b_loc <= 0 || b_glob <= 0) return 1;
-  const long long s = (b_glob + b_loc) / (2 * b_loc);        // round(nt0 / (2 nt1))
+  // equal-length CTAs in both directions: direction 1's row blocks sweep b_loc columns, direction 0's b_glob / splits, and the
+  // two launches share the SMs (7 waves of equal CTAs lose ~1 % to the tail; 2:1 mixes lose 10-15 %).  B200CLIP_BWD_SPLITS
+  // overrides (A/B measurements).
+  static const int forced = [] { const char* e = getenv("B200CLIP_BWD_SPLITS"); return e ? atoi(e) : 0; }();
+  if (forced >= 1 && forced <= 8) return b_loc < b_glob ? forced : 1;
+  const long long s = (b_glob + b_loc / 2) / b_loc;
   return static_cast<int>(std::max<long long>(1, std::min<long long>(8, s)));
 }
 
