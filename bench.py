@@ -432,7 +432,8 @@ def run_head(args, cfg):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner must not land on stdout (one JSON line)
-        dist.init_process_group("nccl", device_id=dev)
+        from b200clip import dp
+        dp.init_process_group(dev)                                   # NCCL with high-priority streams (dp.py)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     m = measure_head(args, cfg, rank, world, dev, args.steps, args.warmup, eager=args.eager)
     B, b_loc, ms_step = m["B"], m["b_loc"], m["ms_step"]

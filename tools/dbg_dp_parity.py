@@ -8,7 +8,7 @@ import b200clip, bench
 from b200clip import dp, ops, head as H
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank); dev = torch.device("cuda", rank)
-dist.init_process_group("nccl", device_id=dev)
+__import__("b200clip").dp.init_process_group(dev)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 cfg = dict(bench.CFG["cfg3"], B=B)
 b_loc = B // world

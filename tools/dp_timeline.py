@@ -15,7 +15,7 @@ rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1
 torch.cuda.set_device(rank)
 dev = torch.device("cuda", rank)
 if world > 1:
-    dist.init_process_group("nccl", device_id=dev)
+    __import__("b200clip").dp.init_process_group(dev)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 cfg = dict(bench.CFG["cfg3"], B=B)
 b_loc = B // world
