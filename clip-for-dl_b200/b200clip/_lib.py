@@ -74,7 +74,8 @@ SIGNATURES = {
     "b200clip_multilabel_metrics_workspace_bytes": (sz, [ll]),
     "b200clip_multilabel_metrics": (i32, [vp, ll, vp, ll, ll, i32, f32, vp, vp, sz, vp]),
     "b200clip_prompt_mean_pool": (i32, [vp, vp, i32, i32, f32, i32, vp, vp]),
-    "b200clip_zeroshot_score": (i32, [vp, ll, ll, vp, i32, i32, i32, i32, f32, C.POINTER(f32), i32, f32, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp]),
+    "b200clip_zeroshot_workspace_bytes": (sz, [ll]),
+    "b200clip_zeroshot_score": (i32, [vp, ll, ll, vp, i32, i32, i32, i32, f32, C.POINTER(f32), i32, f32, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, sz, vp]),
 }
 
 _lib = None

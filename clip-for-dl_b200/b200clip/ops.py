@@ -826,7 +826,8 @@ def _logit(p: float) -> float:
 def zeroshot_score(x_bf16: torch.Tensor, prompts_bf16: torch.Tensor, *, pair_mode: bool, temperature: float,
                    thresholds: Optional[Sequence[float]] = None, thr_inclusive: bool = False, normalize_x: bool = True,
                    topk: int = 0, value_mode: int = 0, want_argmax: bool = True, want_mask: bool = True,
-                   want_scores: bool = False, guard: Optional[float] = None, count_guard: bool = False):
+                   want_scores: bool = False, guard: Optional[float] = None, count_guard: bool = False,
+                   deferred_fixup: bool = True):
     """Scores N embeddings against <=32 prompts.  thresholds are PROBABILITY thresholds (one per label or a scalar
     list); a label passes when sigmoid(score) (>|>=) thr, evaluated exactly as score (>|>=) logit(thr)."""
     require_cuda(x_bf16, prompts_bf16)
@@ -855,8 +856,10 @@ def zeroshot_score(x_bf16: torch.Tensor, prompts_bf16: torch.Tensor, *, pair_mod
     tk_val = torch.empty((n, topk), dtype=torch.float32, device=dev) if topk > 0 else None
     scores = torch.empty((n, L), dtype=torch.float32, device=dev) if want_scores else None
     gcount = torch.zeros((1,), dtype=torch.int64, device=dev) if count_guard else None
+    # flagged rows (decision margin inside the guard band) are listed in this workspace and re-evaluated by a second kernel
+    ws = _ws(load().b200clip_zeroshot_workspace_bytes(n), dev) if deferred_fixup else None
     check(load().b200clip_zeroshot_score(ptr(x_bf16), D, n, ptr(prompts_bf16), np_, D, int(pair_mode), int(normalize_x),
                                          float(temperature), thr_arr, int(thr_inclusive), float(guard), topk, value_mode,
                                          ptr(argmax), ptr(mask), int(mask_u32), ptr(tk_idx), ptr(tk_val), ptr(scores),
-                                         ptr(gcount), stream_ptr()), "zeroshot_score")
+                                         ptr(gcount), ptr(ws), ws.numel() if ws is not None else 0, stream_ptr()), "zeroshot_score")
     return {"argmax": argmax, "mask": mask, "topk_idx": tk_idx, "topk_val": tk_val, "scores": scores, "guard_rows": gcount}

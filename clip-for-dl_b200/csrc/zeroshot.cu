@@ -40,6 +40,9 @@ struct ZsParams {
   float* topk_val;                   // [n, topk] or null
   float* scores;                     // [n, nlabels] f32 or null
   unsigned long long* guard_count;   // rows re-evaluated in fp64 (diagnostic) or null
+  unsigned int* fix_count;           // deferred re-evaluation: number of listed rows (device counter, zeroed by the host) or null
+  unsigned int* fix_rows;            // [fix_cap] row indices
+  unsigned int fix_cap;
 };
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -48,18 +51,6 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
-__device__ __forceinline__ float sumsq8(uint4 v) {
-  float s = 0.f;
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float a = bf16_lo(w[i]), b = bf16_hi(w[i]);
-    s = fmaf(a, a, s);
-    s = fmaf(b, b, s);
-  }
-  return s;
 }
 
 __device__ __forceinline__ bool passes(float s, float thr, int inclusive) { return inclusive ? (s >= thr) : (s > thr); }
@@ -103,11 +94,16 @@ __device__ void emit_row_fp64(const ZsParams& p, long long row, const double* sc
   }
 }
 
-constexpr int ZS_CONSUMERS = 12;                        // consumer warps (3 per SM sub-partition); the last warp is the bulk-copy producer
+// Rows per consumer iteration: 8 (one MMA N-tile).  Round 2 measurement: with 16-row blocks and 12 consumer warps the kernel was
+// LATENCY-bound (42 % issue utilisation, ~8 clk per instruction per warp, tensor pipe 36 %, DRAM 4.0 TB/s even with the fp64
+// path switched off): 3 warps per scheduler cannot hide LDS / HMMA / shuffle latencies.  The ring needs one stage per consumer
+// (see the static_assert), so more warps means smaller blocks: 24 consumers x 8-row (8 KB) stages = the same 192 KB in flight.
+constexpr int ZS_ROWS = 8;                              // rows per block = per stage
+constexpr int ZS_CONSUMERS = 24;                        // consumer warps (6 per SM sub-partition); the last warp is the bulk-copy producer
 constexpr int ZS_THREADS2 = (ZS_CONSUMERS + 1) * 32;
-constexpr int ZS_PITCH = ZS_D * 2;                      // dense rows: ONE 16 KB bulk copy per block (small copies cost ~75 clk each)
-constexpr int ZS_STAGE_BYTES = 16 * ZS_PITCH;           // one 16-row block
-constexpr int ZS_STAGES = 12;
+constexpr int ZS_PITCH = ZS_D * 2;                      // dense rows: ONE 8 KB bulk copy per block (small copies cost ~75 clk each)
+constexpr int ZS_STAGE_BYTES = ZS_ROWS * ZS_PITCH;      // one 8-row block
+constexpr int ZS_STAGES = 24;
 // a consumer may hold a claim at most ZS_CONSUMERS-1 blocks ahead of the oldest unconsumed block; with fewer stages than
 // consumers a claim could be two fills ahead of its stage's barrier and the parity wait would alias
 static_assert(ZS_STAGES >= ZS_CONSUMERS, "ring must have at least as many stages as consumer warps");
@@ -122,26 +118,116 @@ __device__ __forceinline__ void bulk_load_g2s(uint32_t smem_dst, const void* gsr
 // Rows are staged by a producer warp with asynchronous bulk copies (one 16 KB copy per 16-row block) into
 // a 10-stage ring, so ~160 KB of loads are in flight per SM independent of the consumers' registers and occupancy;
 // the 8 consumer warps take 16-row blocks round-robin and read their MMA fragments from the padded rows.
+// Exact re-evaluation of ONE row by a whole warp (rows whose fast-path decision margin was inside the guard band).
+template <bool PAIR>
+__device__ __forceinline__ void reevaluate_row(const ZsParams& p, long long row, int lane) {
+  const int L = p.nlabels;
+  // lane owns k in [16*lane, 16*lane+16)
+  const uint4* px = reinterpret_cast<const uint4*>(p.x + row * p.ldx) + lane * 2;
+  const uint4 x0 = __ldg(px), x1 = __ldg(px + 1);
+  const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+  double xs[16];
+  double ss = 0.0;
+#pragma unroll
+  for (int jx = 0; jx < 8; ++jx) {
+    xs[2 * jx] = static_cast<double>(bf16_lo(xw[jx]));
+    xs[2 * jx + 1] = static_cast<double>(bf16_hi(xw[jx]));
+    ss += xs[2 * jx] * xs[2 * jx] + xs[2 * jx + 1] * xs[2 * jx + 1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const double kk = (p.normalize_x ? 1.0 / fmax(sqrt(ss), 1e-12) : 1.0) * static_cast<double>(p.inv_tau);
+  // Dot products in double-float arithmetic on the fp32 pipe (B200's fp64 rate is 1/64: 28 x 16 DFMA per lane made this path
+  // cost ~50 us of a 270 us kernel at 0.4 % flagged rows).  bf16 x bf16 products are EXACT in fp32 (8 + 8 significand
+  // bits), and Knuth's TwoSum keeps the rounding error of every addition, so (hi, lo) carries the sum to ~2^-45: the
+  // decisions made from it are those of the fp64 evaluation unless a margin is below ~1e-13 of the score scale.
+  float xf[16];
+#pragma unroll
+  for (int jx = 0; jx < 8; ++jx) { xf[2 * jx] = bf16_lo(xw[jx]); xf[2 * jx + 1] = bf16_hi(xw[jx]); }
+  double l[ZS_MAXP];
+  // 4 prompts per trip: their TwoSum chains (16 dependent additions each) and L2 round trips are independent, so one row
+  // costs ~7 chain latencies instead of 28 (the fix-up kernel's duration IS one row's latency: every warp has 1-2 rows)
+#pragma unroll 4
+  for (int c = 0; c < p.np; ++c) {
+    // the prompts themselves (28 KB, L1/L2-resident) -- the fragment table is in MMA register order
+    const uint4* pp = reinterpret_cast<const uint4*>(p.prompts + static_cast<long long>(c) * ZS_D) + lane * 2;
+    const uint4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+    const uint32_t pw[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    float hi = 0.f, lo = 0.f;
+#pragma unroll
+    for (int jx = 0; jx < 16; ++jx) {
+      const float pv = (jx & 1) ? bf16_hi(pw[jx >> 1]) : bf16_lo(pw[jx >> 1]);
+      const float prod = __fmul_rn(xf[jx], pv);                         // exact
+      const float s = __fadd_rn(hi, prod);                              // TwoSum(hi, prod)
+      const float bb = __fsub_rn(s, hi);
+      lo = __fadd_rn(lo, __fadd_rn(__fsub_rn(hi, __fsub_rn(s, bb)), __fsub_rn(prod, bb)));
+      hi = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {                                  // TwoSum tree over the lanes
+      const float oh = __shfl_xor_sync(0xffffffffu, hi, o), ol = __shfl_xor_sync(0xffffffffu, lo, o);
+      const float s = __fadd_rn(hi, oh);
+      const float bb = __fsub_rn(s, hi);
+      lo = __fadd_rn(__fadd_rn(lo, ol), __fadd_rn(__fsub_rn(hi, __fsub_rn(s, bb)), __fsub_rn(oh, bb)));
+      hi = s;
+    }
+    l[c] = (static_cast<double>(hi) + static_cast<double>(lo)) * kk;
+  }
+  if (lane == 0) {
+    double sc[ZS_MAXP];
+    for (int lab = 0; lab < L; ++lab) sc[lab] = PAIR ? (l[2 * lab] - l[2 * lab + 1]) : l[lab];
+    emit_row_fp64(p, row, sc);
+    if (p.guard_count) atomicAdd(p.guard_count, 1ull);
+  }
+}
+
+// Second pass: one warp per listed row.  Inline, the re-evaluation cost 43 us of a 263 us kernel at 0.4 % flagged rows (28
+// dependent L2 round trips per row on ONE warp of an SM whose other warps wait on the same instruction cache); here the
+// rows are independent work items of a full grid.
+template <bool PAIR>
+__global__ void __launch_bounds__(256) zeroshot_fixup_kernel(const ZsParams p) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int nfix = min(*p.fix_count, p.fix_cap);
+  for (unsigned int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < nfix; i += gridDim.x * 8)
+    reevaluate_row<PAIR>(p, static_cast<long long>(p.fix_rows[i]), lane);
+}
+
 // PAIR / TOPK are compile-time: the decision code below is branch-heavy and the common call (pair mode or plain labels, no
-// top-k) should not carry the other modes' instructions (ncu, round 2: the kernel was ISSUE-bound -- 2458 warp instructions
-// per 16-row block at 53 % issue utilisation against 3.5 TB/s of DRAM reads).
+// top-k) should not carry the other modes' instructions.
+//
+// Operand roles (round 2, from two ncu source-page captures: the kernel was ISSUE-bound, 2458 then 1924 warp instructions per
+// 16-row block at 53 % issue utilisation against 3.5 TB/s of DRAM reads; 36 % of them IMAD.MOV):
+//   * the PROMPTS are the A operand (M = 16 prompts per tile, two tiles), the EMBEDDINGS the B operand (N = 8 rows): a B
+//     fragment is two registers holding consecutive K elements of ONE row, i.e. exactly the halves of the 16 bytes a lane
+//     loads, so no register shuffling is needed; the A fragments come from a table laid out in register order.  (With X as the
+//     A operand a fragment interleaves registers of rows r and r + 8: ptxas rebuilt that quad with 4 moves per MMA.)
+//   * dot products are invariant under a permutation of K, so a lane's 16 contiguous bytes of a row serve two k16 steps as
+//     long as the prompt table uses the same permutation: logical k pairs (2t, 2t+1 | 2t+8, 2t+9) of step j <-> elements
+//     32s + 8t + 4j + (0,1 | 2,3).
+//   * prompt -> M index: tile mt holds prompts 16mt + 2g (row g) and 16mt + 2g + 1 (row g + 8), so the (positive, negative)
+//     prompts of a label -- or two neighbouring labels -- meet in ONE lane: c0/c1 = prompt 16mt+2g x rows (2t, 2t+1),
+//     c2/c3 = prompt 16mt+2g+1 x the same rows.
+//   * row norms: diagonal of the Gram blocks X[0..15] . X[0..7]^T and X[0..15] . X[8..15]^T (one extra MMA pair per k16 with X
+//     as BOTH operands; the A quad of rows (r, r+8) costs 4 moves per k16, the only ones left).
 template <bool PAIR, bool TOPK>
 __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams p) {
   extern __shared__ __align__(128) uint8_t zs_smem[];
-  // prompt fragments in consumption order: frag[(s*4 + t)*32 + lane] = P[8t + lane/4][32s + 8(lane%4) .. +7]
+  // A fragments in consumption order: frag[((s*2 + mt)*2 + j)*32 + lane] = {P[pr0][kb..+1], P[pr1][kb..+1], P[pr0][kb+2..+3],
+  // P[pr1][kb+2..+3]}, pr0 = 16mt + 2(lane/4), pr1 = pr0 + 1, kb = 32s + 8(lane%4) + 4j
   uint4* s_frag = reinterpret_cast<uint4*>(zs_smem);
   uint8_t* ring = zs_smem + 16 * 4 * 32 * 16;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + ZS_STAGES * ZS_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + ZS_STAGES;
   int* next_claim = reinterpret_cast<int*>(empty_bar + ZS_STAGES);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int q = lane & 3, r = lane >> 2;
+  const int t = lane & 3, g = lane >> 2;
   for (int i = threadIdx.x; i < 16 * 4 * 32; i += ZS_THREADS2) {
-    const int l = i & 31, t = (i >> 5) & 3, s = i >> 7;
-    const int n = 8 * t + (l >> 2), k0 = 32 * s + 8 * (l & 3);
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (n < p.np) v = *reinterpret_cast<const uint4*>(p.prompts + static_cast<long long>(n) * ZS_D + k0);
-    s_frag[i] = v;
+    const int l = i & 31, j = (i >> 5) & 1, mt = (i >> 6) & 1, s = i >> 7;
+    const int pr0 = 16 * mt + 2 * (l >> 2), kb = 32 * s + 8 * (l & 3) + 4 * j;
+    uint2 v0 = make_uint2(0u, 0u), v1 = make_uint2(0u, 0u);
+    if (pr0 < p.np) v0 = *reinterpret_cast<const uint2*>(p.prompts + static_cast<long long>(pr0) * ZS_D + kb);
+    if (pr0 + 1 < p.np) v1 = *reinterpret_cast<const uint2*>(p.prompts + static_cast<long long>(pr0 + 1) * ZS_D + kb);
+    s_frag[i] = make_uint4(v0.x, v1.x, v0.y, v1.y);
   }
   if (threadIdx.x == 0) {
     *next_claim = 0;
@@ -153,7 +239,7 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
   }
   __syncthreads();
 
-  const long long nblocks16 = (p.n + 15) / 16;
+  const long long nblocks = (p.n + ZS_ROWS - 1) / ZS_ROWS;
   const int L = p.nlabels;
   const uint32_t ring_a = smem_u32(ring), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
 
@@ -161,10 +247,10 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
     // ===================== producer =====================
     int st = 0;
     uint32_t ph = 0;
-    for (long long blk = blockIdx.x; blk < nblocks16; blk += gridDim.x) {
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
       mbar_wait_a(empty_a + 8 * st, ph ^ 1);
-      const long long row0 = blk * 16;
-      const int valid = static_cast<int>(min(16ll, p.n - row0));
+      const long long row0 = blk * ZS_ROWS;
+      const int valid = static_cast<int>(min(static_cast<long long>(ZS_ROWS), p.n - row0));
       if (lane == 0) mbar_arrive_expect_tx_a(full_a + 8 * st, static_cast<uint32_t>(valid) * ZS_D * 2);
       __syncwarp();
       if (p.ldx == ZS_D) {
@@ -179,80 +265,86 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
   }
 
   // ===================== consumers: blocks are claimed dynamically (a warp busy with the rare fp64 re-evaluation must not
-  // stall the ring for the other seven); block i of this CTA lives in stage i % ZS_STAGES =====================
+  // stall the ring for the others); block i of this CTA lives in stage i % ZS_STAGES =====================
+  constexpr int CNT = PAIR ? 2 : 4;                       // label scores per (lane, row)
+  // the labels this lane decides are the same for every block: ids, validity and thresholds are loop invariants
+  int id[CNT];
+  float thr_l[CNT];
+  bool lab_ok[CNT];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    if (PAIR) {
+      id[mt] = 8 * mt + g;
+    } else {
+      id[2 * mt] = 16 * mt + 2 * g;
+      id[2 * mt + 1] = 16 * mt + 2 * g + 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) {
+    lab_ok[i] = id[i] < L;
+    thr_l[i] = lab_ok[i] ? p.thr_logit[id[i]] : INFINITY;
+  }
+  const bool incl = p.thr_inclusive != 0;
+  const bool want_mask = p.mask != nullptr, rank_matters = (p.argmax != nullptr) || TOPK;
+  const float guard = p.guard, inv_tau = p.inv_tau;
+  const bool normalize = p.normalize_x != 0;
   for (;;) {
     long long it = 0;
     if (lane == 0) it = atomicAdd(next_claim, 1);
     it = __shfl_sync(0xffffffffu, it, 0);
     const long long blk = static_cast<long long>(blockIdx.x) + it * gridDim.x;
-    if (blk >= nblocks16) break;
+    if (blk >= nblocks) break;
     const int st = static_cast<int>(it % ZS_STAGES);
     const uint32_t ph = static_cast<uint32_t>((it / ZS_STAGES) & 1);
-    const long long row_a = blk * 16 + r, row_b = row_a + 8;
-    const bool ok_a = row_a < p.n, ok_b = row_b < p.n;
     mbar_wait_a(full_a + 8 * st, ph);
-    const uint4* pa = reinterpret_cast<const uint4*>(ring + st * ZS_STAGE_BYTES + r * ZS_PITCH) + q;
-    const uint4* pb = reinterpret_cast<const uint4*>(ring + st * ZS_STAGE_BYTES + (r + 8) * ZS_PITCH) + q;
-    float acc[4][4];
+    // this lane's 16 bytes of row g at every 32-element step (B fragments: .x,.y = first k16, .z,.w = second); rows past the
+    // end of the matrix (last block only) read the last valid row of the stage: their results are never written
+    const int nvalid = static_cast<int>(min(static_cast<long long>(ZS_ROWS), p.n - blk * ZS_ROWS));
+    const uint4* pa = reinterpret_cast<const uint4*>(ring + st * ZS_STAGE_BYTES + min(g, nvalid - 1) * ZS_PITCH) + t;
+    float acc[2][4];                                      // [prompt tile mt][c0..c3]
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
-    // Row norms on the tensor cores too: with B[k][n] = X[n][k] the B fragment of lane (g = lane/4, q) IS that lane's own A data
-    // of row g, so one extra MMA per k16 step accumulates the Gram block X[0..15] . X[0..7]^T (and one more X . X[8..15]^T);
-    // ||row g||^2 is its diagonal: C[g][g] = c[g & 1] of lane 4g + g/2, C'[g+8][g] = c[2 + (g & 1)] of the same lane.  The
-    // unpack-and-FMA version cost 768 of the 2458 instructions per block (256 FFMA + 512 shift/mask).
-    float na[4] = {0.f, 0.f, 0.f, 0.f}, nb[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < 4; ++i) acc[mt][i] = 0.f;
+    float na[4] = {0.f, 0.f, 0.f, 0.f};                   // Gram block X . X^T for the row norms (A rows 8..15 are zero)
 #pragma unroll 4
     for (int s = 0; s < 16; ++s) {
-      const uint4 xa = ok_a ? pa[s * 4] : make_uint4(0u, 0u, 0u, 0u);
-      const uint4 xb = ok_b ? pb[s * 4] : make_uint4(0u, 0u, 0u, 0u);
-      if (p.normalize_x) {
-        mma_bf16_16816(na, xa.x, xb.x, xa.y, xb.y, xa.x, xa.y);
-        mma_bf16_16816(na, xa.z, xb.z, xa.w, xb.w, xa.z, xa.w);
-        mma_bf16_16816(nb, xa.x, xb.x, xa.y, xb.y, xb.x, xb.y);
-        mma_bf16_16816(nb, xa.z, xb.z, xa.w, xb.w, xb.z, xb.w);
+      const uint4 xa = pa[s * 4];
+      if (normalize) {
+        mma_bf16_16816(na, xa.x, 0u, xa.y, 0u, xa.x, xa.y);
+        mma_bf16_16816(na, xa.z, 0u, xa.w, 0u, xa.z, xa.w);
       }
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const uint4 f = s_frag[(s * 4 + t) * 32 + lane];
-        mma_bf16_16816(acc[t], xa.x, xb.x, xa.y, xb.y, f.x, f.y);
-        mma_bf16_16816(acc[t], xa.z, xb.z, xa.w, xb.w, f.z, f.w);
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint4 f0 = s_frag[((s * 2 + mt) * 2 + 0) * 32 + lane];
+        const uint4 f1 = s_frag[((s * 2 + mt) * 2 + 1) * 32 + lane];
+        mma_bf16_16816(acc[mt], f0.x, f0.y, f0.z, f0.w, xa.x, xa.y);
+        mma_bf16_16816(acc[mt], f1.x, f1.y, f1.z, f1.w, xa.z, xa.w);
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive_a(empty_a + 8 * st);       // stage consumed (smem reads above are complete: values are in registers)
-    // row norms: the diagonal entries live in lane 4r + r/2 of each quad
-    const int nsrc = (lane & 28) | (r >> 1);
-    const float ss_a = __shfl_sync(0xffffffffu, (r & 1) ? na[1] : na[0], nsrc);
-    const float ss_b = __shfl_sync(0xffffffffu, (r & 1) ? nb[3] : nb[2], nsrc);
-    const float ka = (p.normalize_x ? 1.0f / fmaxf(sqrtf(ss_a), 1e-12f) : 1.0f) * p.inv_tau;
-    const float kb = (p.normalize_x ? 1.0f / fmaxf(sqrtf(ss_b), 1e-12f) : 1.0f) * p.inv_tau;
 
-    // label scores held by this lane.  pair mode: label 4t+q from prompts (8t+2q, 8t+2q+1) -> 4 labels per row;
-    // single mode: labels 8t+2q, 8t+2q+1 -> 8 labels per row.
-    unsigned int flag_bits = 0;                           // bit0: row a near a decision boundary, bit1: row b
+    // decisions: this lane holds, for the 2 rows 2t + j, the scores of labels (PAIR: 8mt + g | single: 16mt + 2g, +1);
+    // a row's labels are spread over the 8 lanes with the same t (xor 4, 8, 16)
+    unsigned int flag_rows = 0;                           // bit j: this row needs the fp64 re-evaluation
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const float kk = which ? kb : ka;
-      float sc[8];
-      int id[8];
-      int cnt;
-      if (PAIR) {
-        cnt = 4;
+    for (int j = 0; j < 2; ++j) {
+      const long long row = blk * ZS_ROWS + 2 * t + j;
+      const bool ok = row < p.n;
+      // ||row||^2: diagonal entry C[i][i] (i = 2t + j) of the Gram block lives in lane 4i + i/2 = 9t + 4j, register j
+      const float ss = __shfl_sync(0xffffffffu, na[j], 9 * t + 4 * j);
+      // 1 / max(||x||, 1e-12) / tau  (rsqrt: the rounding of this scale only matters inside the guard band)
+      const float kk = (normalize ? rsqrtf(fmaxf(ss, 1e-24f)) : 1.0f) * inv_tau;
+      float sc[CNT];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          sc[t] = (acc[t][which * 2] - acc[t][which * 2 + 1]) * kk;
-          id[t] = 4 * t + q;
-        }
-#pragma unroll
-        for (int t = 4; t < 8; ++t) { sc[t] = 0.f; id[t] = 1 << 20; }
-      } else {
-        cnt = 8;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          sc[2 * t] = acc[t][which * 2] * kk;          id[2 * t] = 8 * t + 2 * q;
-          sc[2 * t + 1] = acc[t][which * 2 + 1] * kk;  id[2 * t + 1] = 8 * t + 2 * q + 1;
+      for (int mt = 0; mt < 2; ++mt) {
+        if (PAIR) {
+          sc[mt] = (acc[mt][j] - acc[mt][2 + j]) * kk;
+        } else {
+          sc[2 * mt] = acc[mt][j] * kk;
+          sc[2 * mt + 1] = acc[mt][2 + j] * kk;
         }
       }
       unsigned int mask = 0;
@@ -260,85 +352,79 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
       float best = -INFINITY;
       int best_id = 1 << 20;
 #pragma unroll
-      for (int t = 0; t < 8; ++t)
-        if (t < cnt && id[t] < L) {
-          const float thr = p.thr_logit[id[t]];
-          if (passes(sc[t], thr, p.thr_inclusive)) mask |= 1u << id[t];
-          near_thr |= fabsf(sc[t] - thr) < p.guard;
-          if (sc[t] > best || (sc[t] == best && id[t] < best_id)) { best = sc[t]; best_id = id[t]; }
-        }
+      for (int i = 0; i < CNT; ++i) {
+        const float s_i = lab_ok[i] ? sc[i] : -INFINITY;          // labels past L never pass, never win
+        mask |= ((s_i > thr_l[i]) || (incl && s_i == thr_l[i])) ? (1u << id[i]) : 0u;
+        near_thr |= fabsf(s_i - thr_l[i]) < guard;
+        if (s_i > best) { best = s_i; best_id = id[i]; }          // ids ascend with i: the first maximum wins ties
+      }
 #pragma unroll
-      for (int o = 1; o <= 2; o <<= 1) {
+      for (int o = 4; o <= 16; o <<= 1) {
         mask |= __shfl_xor_sync(0xffffffffu, mask, o);
         const float ob = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, best_id, o);
         if (ob > best || (ob == best && oi < best_id)) { best = ob; best_id = oi; }
       }
       bool near_top = false;
-      const bool rank_matters = (p.argmax != nullptr) || TOPK;
+      if (rank_matters) {
 #pragma unroll
-      for (int t = 0; t < 8; ++t)
-        if (t < cnt && id[t] < L && id[t] != best_id) near_top |= (best - sc[t]) < p.guard;
-      // with top-k > 1 every adjacent gap matters; be conservative: any two labels closer than the guard
+        for (int i = 0; i < CNT; ++i) near_top |= lab_ok[i] && id[i] != best_id && (best - sc[i]) < guard;
+      }
       if (TOPK && p.topk > 1) {
+        // with top-k > 1 every adjacent gap matters; be conservative: any two labels of the row closer than the guard
 #pragma unroll
-        for (int a = 0; a < 8; ++a)
+        for (int a = 0; a < CNT; ++a)
 #pragma unroll
-          for (int b = a + 1; b < 8; ++b)
-            if (a < cnt && b < cnt && id[a] < L && id[b] < L) near_top |= fabsf(sc[a] - sc[b]) < p.guard;
-        // cross-lane pairs: compare against the three other lanes' scores
+          for (int b = a + 1; b < CNT; ++b)
+            if (lab_ok[a] && lab_ok[b]) near_top |= fabsf(sc[a] - sc[b]) < guard;
 #pragma unroll
-        for (int o = 1; o <= 3; ++o)
+        for (int o = 4; o < 32; o += 4)                    // the seven other lanes of this row
 #pragma unroll
-          for (int b = 0; b < 8; ++b) {
+          for (int b = 0; b < CNT; ++b) {
             const float other = __shfl_xor_sync(0xffffffffu, sc[b], o);
             const int oid = __shfl_xor_sync(0xffffffffu, id[b], o);
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
-              if (a < cnt && id[a] < L && oid < L) near_top |= fabsf(sc[a] - other) < p.guard;
+            for (int a = 0; a < CNT; ++a)
+              if (lab_ok[a] && oid < L) near_top |= fabsf(sc[a] - other) < guard;
           }
       }
-      unsigned int fl = (near_thr && p.mask != nullptr) || (near_top && rank_matters) ? 1u : 0u;
-      fl |= __shfl_xor_sync(0xffffffffu, fl, 1);
-      fl |= __shfl_xor_sync(0xffffffffu, fl, 2);
-      const long long row = which ? row_b : row_a;
-      const bool ok = which ? ok_b : ok_a;
-      if (fl) flag_bits |= 1u << which;
+      unsigned int fl = ((near_thr && want_mask) || near_top) ? 1u : 0u;
+#pragma unroll
+      for (int o = 4; o <= 16; o <<= 1) fl |= __shfl_xor_sync(0xffffffffu, fl, o);
+      if (fl) flag_rows |= 1u << j;
       const bool emit = ok && !fl;
       if (emit && p.scores) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
-          if (t < cnt && id[t] < L) p.scores[row * L + id[t]] = sc[t];
+        for (int i = 0; i < CNT; ++i)
+          if (lab_ok[i]) p.scores[row * L + id[i]] = sc[i];
       }
-      if (TOPK && p.topk_idx) {                          // warp-uniform branch: shuffles run on all lanes
-        // quad-cooperative top-k by repeated arg-max with removal
+      if (TOPK && p.topk_idx) {                           // warp-uniform branch: shuffles run on all lanes
+        // top-k of the row by repeated arg-max with removal over its 8 lanes
         const float mx = best;
         float den = 0.f;
         if (p.value_mode == 1) {
 #pragma unroll
-          for (int t = 0; t < 8; ++t)
-            if (t < cnt && id[t] < L) den += expf(sc[t] - mx);
-          den += __shfl_xor_sync(0xffffffffu, den, 1);
-          den += __shfl_xor_sync(0xffffffffu, den, 2);
+          for (int i = 0; i < CNT; ++i)
+            if (lab_ok[i]) den += expf(sc[i] - mx);
+#pragma unroll
+          for (int o = 4; o <= 16; o <<= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
         }
         unsigned int taken = 0;
         for (int k = 0; k < p.topk; ++k) {
           float bv = -INFINITY;
           int bi = 1 << 20;
 #pragma unroll
-          for (int t = 0; t < 8; ++t)
-            if (t < cnt && id[t] < L && !((taken >> id[t]) & 1u) && (sc[t] > bv || (sc[t] == bv && id[t] < bi))) {
-              bv = sc[t]; bi = id[t];
-            }
+          for (int i = 0; i < CNT; ++i)
+            if (lab_ok[i] && !((taken >> id[i]) & 1u) && (sc[i] > bv || (sc[i] == bv && id[i] < bi))) { bv = sc[i]; bi = id[i]; }
 #pragma unroll
-          for (int o = 1; o <= 2; o <<= 1) {
+          for (int o = 4; o <= 16; o <<= 1) {
             const float ob = __shfl_xor_sync(0xffffffffu, bv, o);
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ob > bv || (ob == bv && oi < bi)) { bv = ob; bi = oi; }
           }
           if (bi >= L) bi = 0;
           taken |= 1u << bi;
-          if (emit && q == 0) {
+          if (emit && g == 0) {
             p.topk_idx[row * p.topk + k] = static_cast<uint8_t>(bi);
             if (p.topk_val) {
               float v = bv;
@@ -349,7 +435,7 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
           }
         }
       }
-      if (emit && q == 0) {
+      if (emit && g == 0) {
         if (p.argmax) p.argmax[row] = static_cast<uint8_t>(best_id);
         if (p.mask) {
           if (p.mask_is_u32) static_cast<uint32_t*>(p.mask)[row] = mask;
@@ -358,57 +444,30 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
       }
     }
 
-    // fp64 re-evaluation of flagged rows, one row at a time by the whole warp (rare: ~1-2 % of rows)
-    unsigned int rows_flagged = 0;                        // bit i: row blk*16+i
-    {
-      const unsigned int ba = __ballot_sync(0xffffffffu, (flag_bits & 1u) && q == 0);
-      const unsigned int bb = __ballot_sync(0xffffffffu, (flag_bits & 2u) && q == 0);
+    // fp64 re-evaluation of flagged rows, one row at a time by the whole warp (rare: < 1 % of rows)
+    unsigned int rows_flagged = 0;                        // bit i: row blk*8+i
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if ((ba >> (4 * i)) & 1u) rows_flagged |= 1u << i;
-        if ((bb >> (4 * i)) & 1u) rows_flagged |= 1u << (i + 8);
-      }
+    for (int j = 0; j < 2; ++j) {
+      const unsigned int bal = __ballot_sync(0xffffffffu, ((flag_rows >> j) & 1u) && g == 0) & 0xFu;   // lanes 0..3 = t
+#pragma unroll
+      for (int tt = 0; tt < 4; ++tt)
+        if ((bal >> tt) & 1u) rows_flagged |= 1u << (2 * tt + j);
     }
     while (rows_flagged) {
       const int i = __ffs(rows_flagged) - 1;
       rows_flagged &= rows_flagged - 1;
-      const long long row = blk * 16 + i;
+      const long long row = blk * ZS_ROWS + i;
       if (row >= p.n) continue;
-      // lane owns k in [16*lane, 16*lane+16)
-      const uint4* px = reinterpret_cast<const uint4*>(p.x + row * p.ldx) + lane * 2;
-      const uint4 x0 = __ldg(px), x1 = __ldg(px + 1);
-      const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-      double xs[16];
-      double ss = 0.0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        xs[2 * j] = static_cast<double>(bf16_lo(xw[j]));
-        xs[2 * j + 1] = static_cast<double>(bf16_hi(xw[j]));
-        ss += xs[2 * j] * xs[2 * j] + xs[2 * j + 1] * xs[2 * j + 1];
+      if (p.fix_count != nullptr) {                       // deferred: list the row for zeroshot_fixup_kernel
+        unsigned int slot = 0;
+        if (lane == 0) slot = atomicAdd(p.fix_count, 1u);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot < p.fix_cap) {
+          if (lane == 0) p.fix_rows[slot] = static_cast<unsigned int>(row);
+          continue;
+        }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      const double kk = (p.normalize_x ? 1.0 / fmax(sqrt(ss), 1e-12) : 1.0) * static_cast<double>(p.inv_tau);
-      double l[ZS_MAXP];
-      for (int c = 0; c < p.np; ++c) {
-        // P[c][16*lane .. +16) from the fragment table: s = lane/2, 8-element groups 2*(lane&1) and 2*(lane&1)+1
-        const int fbase = ((lane >> 1) * 4 + (c >> 3)) * 32 + (c & 7) * 4 + (lane & 1) * 2;
-        const uint4 p0 = s_frag[fbase], p1 = s_frag[fbase + 1];
-        const uint32_t pw[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-        double d = 0.0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          d += xs[2 * j] * static_cast<double>(bf16_lo(pw[j])) + xs[2 * j + 1] * static_cast<double>(bf16_hi(pw[j]));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        l[c] = d * kk;
-      }
-      if (lane == 0) {
-        double sc[ZS_MAXP];
-        for (int lab = 0; lab < L; ++lab) sc[lab] = PAIR ? (l[2 * lab] - l[2 * lab + 1]) : l[lab];
-        emit_row_fp64(p, row, sc);
-        if (p.guard_count) atomicAdd(p.guard_count, 1ull);
-      }
+      reevaluate_row<PAIR>(p, row, lane);                 // no list (or list full): re-evaluate in place
     }
   }
 }
@@ -417,11 +476,17 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
 
 using namespace b200;
 
+extern "C" size_t b200clip_zeroshot_workspace_bytes(long long n) {
+  // room for every row (a pathological batch where all margins are inside the guard band); 4 bytes per row
+  return n <= 0 ? 0 : 256 + static_cast<size_t>(n) * 4;
+}
+
 extern "C" int b200clip_zeroshot_score(const void* x_bf16, long long ldx, long long n, const void* prompts_bf16, int np,
                                        int D, int pair_mode, int normalize_x, float temperature,
                                        const float* thr_logit_host, int thr_inclusive, float guard, int topk,
                                        int value_mode, uint8_t* argmax, void* mask, int mask_is_u32, uint8_t* topk_idx,
-                                       float* topk_val, float* scores, unsigned long long* guard_count, void* stream) {
+                                       float* topk_val, float* scores, unsigned long long* guard_count, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
   B200_REQUIRE(D == ZS_D, "zeroshot: D=%d unsupported (kernel is built for D=%d)", D, ZS_D);
   B200_REQUIRE(n >= 0 && np > 0 && np <= ZS_MAXP, "zeroshot: need 0 < np <= %d", ZS_MAXP);
   B200_REQUIRE(!pair_mode || np % 2 == 0, "zeroshot: pair mode needs an even number of prompts");
@@ -439,10 +504,17 @@ extern "C" int b200clip_zeroshot_score(const void* x_bf16, long long ldx, long l
   p.thr_inclusive = thr_inclusive; p.guard = guard; p.topk = topk; p.value_mode = value_mode;
   p.argmax = argmax; p.mask = mask; p.mask_is_u32 = mask_is_u32; p.topk_idx = topk_idx; p.topk_val = topk_val;
   p.scores = scores; p.guard_count = guard_count;
-  const long long nblk16 = (n + 15) / 16;
-  const int grid = static_cast<int>(std::min<long long>(nblk16, static_cast<long long>(num_sms())));
-  static SmemAttrOnce attr[4];
+  // optional workspace: [count u32 | pad | row indices u32 ...] -> flagged rows are re-evaluated by a second kernel
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (workspace != nullptr && workspace_bytes >= 256 + 4 && n < (1ll << 32)) {
+    p.fix_count = static_cast<unsigned int*>(workspace);
+    p.fix_rows = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(workspace) + 256);
+    p.fix_cap = static_cast<unsigned int>(std::min<size_t>((workspace_bytes - 256) / 4, 0xFFFFFFFFull));
+    B200_CHECK_CUDA(cudaMemsetAsync(p.fix_count, 0, 4, s));
+  }
+  const long long nblk = (n + ZS_ROWS - 1) / ZS_ROWS;
+  const int grid = static_cast<int>(std::min<long long>(nblk, static_cast<long long>(num_sms())));
+  static SmemAttrOnce attr[4];
 #define B200_ZS_CASE(PAIR, TOPK, IDX)                                                         \
   if ((pair_mode != 0) == PAIR && (topk > 0) == TOPK) {                                       \
     B200_CHECK_CUDA(attr[IDX].ensure(zeroshot_kernel<PAIR, TOPK>, ZS_SMEM_BYTES));            \
@@ -454,5 +526,11 @@ extern "C" int b200clip_zeroshot_score(const void* x_bf16, long long ldx, long l
   B200_ZS_CASE(true, true, 3)
 #undef B200_ZS_CASE
   B200_LAUNCH_CHECK();
+  if (p.fix_count != nullptr) {
+    const int fgrid = 2 * num_sms();
+    if (pair_mode) zeroshot_fixup_kernel<true><<<fgrid, 256, 0, s>>>(p);
+    else zeroshot_fixup_kernel<false><<<fgrid, 256, 0, s>>>(p);
+    B200_LAUNCH_CHECK();
+  }
   return B200_OK;
 }

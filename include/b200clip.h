@@ -243,11 +243,14 @@ int b200clip_predict_multilabel(const float* image_features, long long ldx, cons
  * multimodal_attention/disease_analysis.py:345-413 (sigmoid(cos/0.5) >= thr), NB02 c41:27-32, c44:24-36, and the
  * 14 x (pos,neg) prompt shape.  thr_logit_host: HOST array of nlabels floats, a label passes when its score
  * (cos/tau, or l+ - l- in pair mode) is > (or >= if thr_inclusive) the value, i.e. logit(threshold). */
+size_t b200clip_zeroshot_workspace_bytes(long long n);
+/* workspace (optional, b200clip_zeroshot_workspace_bytes): rows whose decision margin is inside the guard band are listed
+ * there and re-evaluated exactly by a second kernel; without it they are re-evaluated in place (same results, slower). */
 int b200clip_zeroshot_score(const void* x_bf16, long long ldx, long long n, const void* prompts_bf16, int np, int D,
                             int pair_mode, int normalize_x, float temperature, const float* thr_logit_host,
                             int thr_inclusive, float guard, int topk, int value_mode, uint8_t* argmax, void* mask,
                             int mask_is_u32, uint8_t* topk_idx, float* topk_val, float* scores,
-                            unsigned long long* guard_count, void* stream);
+                            unsigned long long* guard_count, void* workspace, size_t workspace_bytes, void* stream);
 
 /* contrastive_loss(image_features, text_features, temperature) -- 0426/train.py:154-176 -- for inputs that are NOT unit
  * vectors: fp32 logits, true row/column maxima, n <= 8192 (workspace: b200clip_softclip_workspace_bytes(n)).  The flash path
