@@ -125,7 +125,7 @@ def test_rank_partitioned_equals_monolithic(W, D):
         total += sums
         # allow_splits: with b_loc << b_glob the kernel cuts direction 0's columns into ranges (partial d_i sums)
         d_i, d_t = ops.infonce_backward(blk, tb, tau, rinvh, cinvh, None, row0=k * n, allow_splits=True)
-        assert (d_i.dim() == 3) == (W >= 2) and (d_i.dim() == 2 or d_i.shape[0] == W), d_i.shape
+        assert (d_i.dim() == 3) == (W >= 2) and (d_i.dim() == 2 or d_i.shape[0] == min(W, 4)), d_i.shape
         # the two directions launched separately (the data-parallel step does that to overlap the reduce-scatter of d_t with
         # direction 0) are bit-identical to the combined launch
         d_i1, none_t = ops.infonce_backward(blk, tb, tau, rinvh, cinvh, None, row0=k * n, allow_splits=True, directions=1)
