@@ -41,8 +41,12 @@ struct GemmParams {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 384;          // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
-constexpr int GEMM_EPI_WARPS = 8;
+#ifndef B200CLIP_GEMM_EPI_WARPS
+#define B200CLIP_GEMM_EPI_WARPS 8
+#endif
+constexpr int GEMM_EPI_WARPS = B200CLIP_GEMM_EPI_WARPS;     // 8 or 16: lane quadrant x column half / quarter of the tile
+constexpr int GEMM_THREADS = 128 + GEMM_EPI_WARPS * 32;     // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
+static_assert(GEMM_EPI_WARPS == 8 || GEMM_EPI_WARPS == 16, "epilogue warpgroups");
 
 template <int BN>
 constexpr int gemm_stage_bytes() { return GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2; }
@@ -195,7 +199,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   constexpr int B_BYTES = BN * GEMM_BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int EPI_COLS = BN / 2;                  // columns per epilogue warpgroup
+  constexpr int EPI_COLS = BN / (GEMM_EPI_WARPS / 4);   // columns per epilogue warpgroup
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;          // 2

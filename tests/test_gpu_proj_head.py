@@ -127,10 +127,13 @@ def _ste_bf16(x):
 
 # (256, 2048), (1024, 768): small cases; 200: ragged (not a multiple of 16 / 128); (4096, 2048) = BASELINE.json configs[1]
 # (cfg 2) at its full size; (8192, 768) = the bench shape's widths at the largest batch the CPU oracle finishes in seconds
-@pytest.mark.parametrize("B,E_img", [(256, 2048), (1024, 768), (200, 768), (4096, 2048), (8192, 768)])
-def test_fused_head_step(B, E_img):
+# D = 768: BASELINE.json configs[4] sweeps the shared width (0426/config.py:30); 3-CTA clusters in the InfoNCE backward, the
+# fp32 row kernels for the two BCE heads (the tensor-core heads kernel is built for D = 512)
+@pytest.mark.parametrize("B,E_img,D", [(256, 2048, 512), (1024, 768, 512), (200, 768, 512), (4096, 2048, 512), (8192, 768, 512),
+                                       (512, 2048, 768), (200, 768, 768)])
+def test_fused_head_step(B, E_img, D):
     import b200clip
-    D, E_txt, C = 512, 768, 16
+    E_txt, C = 768, 16
     ip = _round_params(synth.projection_params(100, E_img, D))
     tp = _round_params(synth.projection_params(200, E_txt, D))
     fw, fb = synth.uniform(31, -0.04, 0.04, C, D), synth.uniform(32, -0.04, 0.04, C)
