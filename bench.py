@@ -33,9 +33,9 @@ CFG = {
 }
 TAU_NCE, TAU_BCE = 0.07, 1.0
 # DRAM bytes of ONE launch from the ncu --set full captures under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum)
-NCE_BWD_KERNEL = "nce_bwd4_kernel"
-NCE_BWD_TRAFFIC_BYTES = 236.41e6          # profiles/r1_v6_ncu_nce_B32768.txt (B = 32768, D = 512, one GPU)
-ZS_TRAFFIC_BYTES = None                   # profiles/r2_ncu_zeroshot.txt once captured
+NCE_BWD_KERNEL = "nce_bwdc_kernel<2>"
+NCE_BWD_TRAFFIC_BYTES = 264.24e6          # profiles/r2_ncu_nce_B32768.txt: 156.66 MB read + 107.58 MB written (B = 32768, D = 512, one GPU)
+ZS_TRAFFIC_BYTES = 1.0649e9               # profiles/r2_ncu_zeroshot_16row.txt: 1.0313 GB read + 33.6 MB written (N = 1M, 28 prompts)
 DROPOUT = 0.1            # nn.Dropout(0.1) of the projections (0426/config.py:27), ON in the timed step as in training
 
 
