@@ -14,9 +14,14 @@
 
 #include "common.cuh"
 #include "host.cuh"
+#include "gemm.cuh"
 #include "../../include/b200clip.h"
 
 namespace b200 {
+int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, int K, long long lda, long long ldb,
+              int epi, float alpha, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
+              const void* resid, long long ld_res, const float* aux, long long ld_aux, int split_k, cudaStream_t stream,
+              float drop_p = 0.f, unsigned int drop_seed = 0u, int aux_is_bf16 = 0, const unsigned int* drop_seed_dev = nullptr);
 
 constexpr int SG_TILE = 64, SG_K = 16;
 
@@ -207,13 +212,61 @@ __global__ void __launch_bounds__(256) hard_grad_kernel(float* __restrict__ L, c
 
 constexpr long long SOFT_MAX_N = 8192;
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core Gram products at fp32-equivalent accuracy (round 2).  x = hi + lo with hi = bf16(x), lo = bf16(x - hi) carries
+// 16 significand bits; x.y ~ hi.hi' + hi.lo' + lo.hi' (the dropped lo.lo' term is 2^-18 relative).  The three products are
+// ONE tcgen05 GEMM over a K-concatenated pair of operands:  [hi | hi | lo] . [hi' | lo' | hi']^T, and sums of products
+// (I I^T + T T^T, dL I / tau + S T) concatenate further along K.  The n x n matrices still live in the workspace (n <= 8192);
+// what moves to the tensor cores is every contraction (7 SGEMMs of 2 n^2 D flops became 5 GEMM launches).
+// Error of a logit: sqrt(D) 2^-17 |x||y| / tau ~ 2.5e-3 at tau = 0.07, D = 512 -- below the fp32 reference's own accumulation
+// error (~1e-2) in that regime.
+// ---------------------------------------------------------------------------------------------------------------------
+// in [rows, cols] fp32 (pitch ld_in) * scale -> hi written to hi_a (and hi_b), lo to lo_out; all outputs bf16 with pitch ld_out
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ in, long long ld_in, long long rows, int cols,
+                                                         float scale, __nv_bfloat16* __restrict__ hi_a,
+                                                         __nv_bfloat16* __restrict__ hi_b, __nv_bfloat16* __restrict__ lo_out,
+                                                         long long ld_out) {
+  const long long total = rows * (cols / 4);
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    const long long r = i / (cols / 4);
+    const int c = static_cast<int>(i - r * (cols / 4)) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(in + r * ld_in + c);
+    const float x[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      h[k] = __float2bfloat16_rn(x[k]);
+      l[k] = __float2bfloat16_rn(x[k] - __bfloat162float(h[k]));
+    }
+    const uint2 hv = *reinterpret_cast<const uint2*>(h), lv = *reinterpret_cast<const uint2*>(l);
+    *reinterpret_cast<uint2*>(hi_a + r * ld_out + c) = hv;
+    if (hi_b) *reinterpret_cast<uint2*>(hi_b + r * ld_out + c) = hv;
+    *reinterpret_cast<uint2*>(lo_out + r * ld_out + c) = lv;
+  }
+}
+
+static int split3(const float* in, long long ld_in, long long rows, int cols, float scale, __nv_bfloat16* hi_a, __nv_bfloat16* hi_b,
+                  __nv_bfloat16* lo, long long ld_out, cudaStream_t s) {
+  const long long total = rows * (cols / 4);
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 8ll * num_sms()));
+  split_bf16_kernel<<<grid, 256, 0, s>>>(in, ld_in, rows, cols, scale, hi_a, hi_b, lo, ld_out);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+static bool soft_tc_eligible(long long n, int D) { return n >= 128 && n % 32 == 0 && D % 32 == 0 && D <= 1024; }
+static size_t soft_tc_bytes(long long n) {            // bf16 operand buffers of the tensor-core path, sized for D <= 1024
+  const size_t nn = static_cast<size_t>(n) * n, nd = static_cast<size_t>(n) * 1024;
+  return (2 * 6 * nd + 2 * 6 * nn + 2 * 6 * nd) * 2 + 4096;
+}
+
 }  // namespace b200
 
 using namespace b200;
 
 extern "C" size_t b200clip_softclip_workspace_bytes(long long n) {
   if (n <= 0) return 0;
-  return static_cast<size_t>(4 * n * n + 4 * n) * sizeof(float) + 1024;
+  return static_cast<size_t>(4 * n * n + 4 * n) * sizeof(float) + 1024 + (soft_tc_eligible(n, 32) ? soft_tc_bytes(n) : 0);
 }
 
 // mode == "eval" (0426/train.py:149-150): logits[n, n] = text image^T / tau
@@ -242,10 +295,35 @@ extern "C" int b200clip_softclip_fwd_bwd(const float* text, const float* image, 
   float* lse_r = vec; float* lse_c = vec + n; float* colsum_p = vec + 2 * n; float* rowloss = vec + 3 * n;
   const float inv_tau = 1.0f / temperature;
   int rc;
-  if ((rc = sgemm(text, D, 1, image, 1, D, L, n, N, N, D, inv_tau, 0, s))) return rc;            // :139  L = T I^T / tau
-  if ((rc = sgemm(image, D, 1, text, 1, D, Lt, n, N, N, D, inv_tau, 0, s))) return rc;           //       L^T (column statistics as rows)
-  if ((rc = sgemm(image, D, 1, image, 1, D, P, n, N, N, D, 1.0f, 0, s))) return rc;              // :141
-  if ((rc = sgemm(text, D, 1, text, 1, D, P, n, N, N, D, 1.0f, 1, s))) return rc;                // :142 (+=)
+  // tensor-core path: K-concatenated 3 x bf16 split operands (see above); fp32 SGEMM otherwise (small / ragged n)
+  const bool tc = soft_tc_eligible(n, D) && getenv("B200CLIP_SOFTCLIP_FP32") == nullptr;
+  __nv_bfloat16 *XA = nullptr, *XB = nullptr, *R1 = nullptr, *R2 = nullptr, *C1 = nullptr, *C2 = nullptr;
+  const long long D3 = 3ll * D, D6 = 6ll * D, n6 = 6 * n;
+  if (tc) {
+    uint8_t* tb = reinterpret_cast<uint8_t*>(vec + 4 * n);
+    tb = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tb) + 1023) & ~uintptr_t(1023));
+    const size_t nd = static_cast<size_t>(n) * 1024, nn2 = static_cast<size_t>(nn);
+    XA = reinterpret_cast<__nv_bfloat16*>(tb);           // [n, 6D] = [I_hi | I_hi | I_lo | T_hi | T_hi | T_lo]
+    XB = XA + 6 * nd;                                    // [n, 6D] = [I_hi | I_lo | I_hi | T_hi | T_lo | T_hi]
+    R1 = XB + 6 * nd;                                    // [n, 6n] = [dL_hi | dL_hi | dL_lo | S_hi | S_hi | S_lo]      (dL already / tau)
+    R2 = R1 + 6 * nn2;                                   // [6n, n] = the same six blocks stacked along rows
+    C1 = R2 + 6 * nn2;                                   // [6n, D] = [I_hi; I_lo; I_hi; T_hi; T_lo; T_hi]
+    C2 = C1 + 6 * nd;                                    // [6n, D] = [T_hi; T_lo; T_hi; I_hi; I_lo; I_hi]
+    // A-type (hi, hi, lo) and B-type (hi, lo, hi) concatenations of the two inputs
+    if ((rc = split3(image, D, n, D, 1.0f, XA, XA + D, XA + 2 * D, D6, s))) return rc;
+    if ((rc = split3(text, D, n, D, 1.0f, XA + D3, XA + D3 + D, XA + D3 + 2 * D, D6, s))) return rc;
+    if ((rc = split3(image, D, n, D, 1.0f, XB, XB + 2 * D, XB + D, D6, s))) return rc;
+    if ((rc = split3(text, D, n, D, 1.0f, XB + D3, XB + D3 + 2 * D, XB + D3 + D, D6, s))) return rc;
+    // :139  L = T I^T / tau ; L^T ; :141-142  I I^T + T T^T (one GEMM over K = 6D)
+    if ((rc = gemm_bf16(XA + D3, XB, 0, 0, N, N, (int)D3, D6, D6, EPI_STORE_F32, inv_tau, L, n, nullptr, 0, nullptr, nullptr, 0, nullptr, 0, 1, s))) return rc;
+    if ((rc = gemm_bf16(XA, XB + D3, 0, 0, N, N, (int)D3, D6, D6, EPI_STORE_F32, inv_tau, Lt, n, nullptr, 0, nullptr, nullptr, 0, nullptr, 0, 1, s))) return rc;
+    if ((rc = gemm_bf16(XA, XB, 0, 0, N, N, (int)D6, D6, D6, EPI_STORE_F32, 1.0f, P, n, nullptr, 0, nullptr, nullptr, 0, nullptr, 0, 1, s))) return rc;
+  } else {
+    if ((rc = sgemm(text, D, 1, image, 1, D, L, n, N, N, D, inv_tau, 0, s))) return rc;            // :139  L = T I^T / tau
+    if ((rc = sgemm(image, D, 1, text, 1, D, Lt, n, N, N, D, inv_tau, 0, s))) return rc;           //       L^T (column statistics as rows)
+    if ((rc = sgemm(image, D, 1, image, 1, D, P, n, N, N, D, 1.0f, 0, s))) return rc;              // :141
+    if ((rc = sgemm(text, D, 1, text, 1, D, P, n, N, N, D, 1.0f, 1, s))) return rc;                // :142 (+=)
+  }
   row_softmax_kernel<<<N, 256, 0, s>>>(P, N, 0.5f * temperature);                                // :143
   B200_LAUNCH_CHECK();
   row_lse_kernel<<<N, 256, 0, s>>>(L, N, lse_r);
@@ -264,6 +342,22 @@ extern "C" int b200clip_softclip_fwd_bwd(const float* text, const float* image, 
   B200_LAUNCH_CHECK();
   soft_sym_kernel<<<eg, 256, 0, s>>>(P, N, 0.5f * temperature, Lt);                              // Lt <- S
   B200_LAUNCH_CHECK();
+  if (tc) {
+    // row-concatenated [n, 6n] and row-stacked [6n, n] splits of dL / tau and S; K-stacked B operands [6n, D]
+    if ((rc = split3(L, n, n, N, inv_tau, R1, R1 + n, R1 + 2 * n, n6, s))) return rc;
+    if ((rc = split3(Lt, n, n, N, 1.0f, R1 + 3 * n, R1 + 4 * n, R1 + 5 * n, n6, s))) return rc;
+    if ((rc = split3(L, n, n, N, inv_tau, R2, R2 + nn, R2 + 2 * nn, n, s))) return rc;
+    if ((rc = split3(Lt, n, n, N, 1.0f, R2 + 3 * nn, R2 + 4 * nn, R2 + 5 * nn, n, s))) return rc;
+    const long long nD = n * static_cast<long long>(D);
+    if ((rc = split3(image, D, n, D, 1.0f, C1, C1 + 2 * nD, C1 + nD, D, s))) return rc;           // [I_hi; I_lo; I_hi]
+    if ((rc = split3(text, D, n, D, 1.0f, C1 + 3 * nD, C1 + 5 * nD, C1 + 4 * nD, D, s))) return rc;   // [T_hi; T_lo; T_hi]
+    if ((rc = split3(text, D, n, D, 1.0f, C2, C2 + 2 * nD, C2 + nD, D, s))) return rc;
+    if ((rc = split3(image, D, n, D, 1.0f, C2 + 3 * nD, C2 + 5 * nD, C2 + 4 * nD, D, s))) return rc;
+    // dT = dL I / tau + S T   ([n, 6n] x [6n, D]);   dI = dL^T T / tau + S I   (A read as [K][M] from the stacked copy)
+    if ((rc = gemm_bf16(R1, C1, 0, 1, N, D, (int)n6, n6, D, EPI_STORE_F32, 1.0f, d_text, D, nullptr, 0, nullptr, nullptr, 0, nullptr, 0, 1, s))) return rc;
+    if ((rc = gemm_bf16(R2, C2, 1, 1, N, D, (int)n6, n, D, EPI_STORE_F32, 1.0f, d_image, D, nullptr, 0, nullptr, nullptr, 0, nullptr, 0, 1, s))) return rc;
+    return B200_OK;
+  }
   if ((rc = sgemm(L, n, 1, image, D, 1, d_text, D, N, D, N, inv_tau, 0, s))) return rc;          // dT  = dL I / tau
   if ((rc = sgemm(Lt, n, 1, text, D, 1, d_text, D, N, D, N, 1.0f, 1, s))) return rc;             //     += S T
   if ((rc = sgemm(L, 1, n, text, D, 1, d_image, D, N, D, N, inv_tau, 0, s))) return rc;          // dI  = dL^T T / tau

@@ -27,8 +27,11 @@ def test_soft_target_loss_matches_reference_golden(golden):
     assert b200clip.contrastive_clip_loss_function(Tt, Ii, 2.0, mode="bogus") is None
 
 
+# n >= 128 with n % 32 == 0 takes the tensor-core path (K-concatenated 3 x bf16 split operands on the tcgen05 GEMM); the other
+# sizes the fp32 SGEMM path
 @pytest.mark.parametrize("B,D,tau,scale", [(16, 512, 2.0, 1.0), (32, 512, 0.07, 1.0), (64, 512, 0.07, 0.2), (300, 512, 2.0, 1.0),
-                                            (1000, 128, 0.5, 0.5)])
+                                            (1000, 128, 0.5, 0.5), (128, 512, 0.07, 1.0), (256, 512, 2.0, 1.0), (1024, 512, 0.07, 0.3),
+                                            (2048, 768, 0.5, 0.5), (4096, 512, 0.5, 0.05)])
 def test_soft_target_loss_and_grads(B, D, tau, scale):
     """LayerNorm-like rows (norm ~ sqrt(D) * scale): at tau = 0.07 the logits reach +-10^3, the regime that needs the true row
     maxima and fp32 Gram products.  The oracle runs in fp64 on the same fp32 inputs."""
@@ -64,3 +67,27 @@ def test_soft_target_loss_rejects_bad_input():
         b200clip.contrastive_clip_loss_function(torch.zeros(4, 32, device=d), torch.zeros(5, 32, device=d), 0.07, mode="train")
     with pytest.raises(RuntimeError):
         b200clip.contrastive_clip_loss_function(torch.zeros(4, 32), torch.zeros(4, 32), 0.07, mode="train")
+
+
+def test_tensor_core_path_agrees_with_fp32_path():
+    """Same call, the two contraction engines: tcgen05 GEMMs over 3 x bf16 split operands vs the fp32 CUDA-core SGEMM
+    (B200CLIP_SOFTCLIP_FP32=1 forces the latter)."""
+    import os
+    import b200clip
+    d = dev()
+    T = synth.randn(1, 512, 512).to(d)                          # tau = 2 on LayerNorm-scale rows: the notebooks' regime, loss O(1)
+    I = (0.5 * T.cpu() + 0.5 * synth.randn(2, 512, 512)).to(d)
+    res = {}
+    for mode in ("tc", "fp32"):
+        if mode == "fp32":
+            os.environ["B200CLIP_SOFTCLIP_FP32"] = "1"
+        try:
+            Tg, Ig = T.clone().requires_grad_(True), I.clone().requires_grad_(True)
+            loss = b200clip.contrastive_clip_loss_function(Tg, Ig, temperature=2.0, mode="train")
+            loss.backward()
+            torch.cuda.synchronize()
+            res[mode] = (loss.item(), Tg.grad.clone(), Ig.grad.clone())
+        finally:
+            os.environ.pop("B200CLIP_SOFTCLIP_FP32", None)
+    assert abs(res["tc"][0] - res["fp32"][0]) <= 1e-4 * abs(res["fp32"][0])
+    assert rel_l2(res["tc"][1], res["fp32"][1]) < 2e-3 and rel_l2(res["tc"][2], res["fp32"][2]) < 2e-3
