@@ -18,7 +18,8 @@ namespace b200 {
 int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, int K, long long lda, long long ldb,
               int epi, float alpha, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
               const void* resid, long long ld_res, const float* aux, long long ld_aux, int split_k, cudaStream_t stream,
-              float drop_p = 0.f, unsigned int drop_seed = 0u, int aux_is_bf16 = 0, const unsigned int* drop_seed_dev = nullptr);
+              float drop_p = 0.f, unsigned int drop_seed = 0u, int aux_is_bf16 = 0, const unsigned int* drop_seed_dev = nullptr,
+              float* splitk_ws = nullptr, size_t splitk_ws_bytes = 0);
 
 constexpr int AT_MAXC = 16;
 constexpr int AT_MAXD = 512;
@@ -298,6 +299,7 @@ extern "C" size_t b200clip_attention_bwd_workspace_bytes(long long B, int C, int
   n += ((static_cast<size_t>(at_bwd_grid(B)) * (C + 2) * D * 4) + 255) & ~size_t(255);   // block partials
   n += ((static_cast<size_t>(C + 2) * D * 4) + 255) & ~size_t(255);             // reduced d tp | d wa | colsum(d ip)
   n += (b200clip_colsum_workspace_bytes(B, D) + 255) & ~size_t(255);
+  n += (static_cast<size_t>(num_sms()) * 128 * 256 * sizeof(float) + 255) & ~size_t(255);   // deterministic split-K partial tiles
   return n + 1024;
 }
 
@@ -323,12 +325,13 @@ extern "C" int b200clip_attention_bwd(const float* d_out, const float* d_w, cons
   float* red = reinterpret_cast<float*>(carve(static_cast<size_t>(C + 2) * D * 4));
   const size_t cs_ws = b200clip_colsum_workspace_bytes(B, D);
   void* cs = carve(cs_ws);
+  const size_t sk_ws = static_cast<size_t>(num_sms()) * 128 * 256 * sizeof(float);
+  float* sk_work = reinterpret_cast<float*>(carve(sk_ws));
 
   if ((rc = b200clip_cast_f32_bf16(d_out, dout_bf, B * D, stream))) return rc;
   if ((rc = b200clip_colsum(d_out, 0, D, B, D, dbo, 0, cs, cs_ws, stream))) return rc;          // output_proj.bias
-  B200_CHECK_CUDA(cudaMemsetAsync(dwo, 0, static_cast<size_t>(D) * D * 4, s));
   if ((rc = gemm_bf16(dout_bf, e_bf16, 1, 1, D, D, (int)B, D, D, EPI_ATOMIC_F32, 1.0f, dwo, D, nullptr, 0, nullptr, nullptr, 0, nullptr,
-                      0, at_split_for(D, D, (int)B), s)))
+                      0, at_split_for(D, D, (int)B), s, 0.f, 0u, 0, nullptr, sk_work, sk_ws)))
     return rc;                                                                  // dWo = d_out^T e
   if ((rc = gemm_bf16(dout_bf, wo_bf16, 0, 1, (int)B, D, D, D, D, EPI_STORE_F32, 1.0f, de, D, nullptr, 0, nullptr, nullptr, 0, nullptr, 0,
                       1, s)))
@@ -348,9 +351,8 @@ extern "C" int b200clip_attention_bwd(const float* d_out, const float* d_w, cons
   B200_CHECK_CUDA(cudaMemcpyAsync(dbi, red + static_cast<size_t>(C + 1) * D, static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice, s));
   B200_CHECK_CUDA(cudaMemsetAsync(dba, 0, sizeof(float), s));    // a constant added to every score leaves the softmax unchanged
   // image side
-  B200_CHECK_CUDA(cudaMemsetAsync(dwi, 0, static_cast<size_t>(D) * D * 4, s));
   if ((rc = gemm_bf16(dip_bf, x_bf16, 1, 1, D, D, (int)B, D, D, EPI_ATOMIC_F32, 1.0f, dwi, D, nullptr, 0, nullptr, nullptr, 0, nullptr, 0,
-                      at_split_for(D, D, (int)B), s)))
+                      at_split_for(D, D, (int)B), s, 0.f, 0u, 0, nullptr, sk_work, sk_ws)))
     return rc;
   if (dx) {
     if ((rc = gemm_bf16(dip_bf, wi_bf16, 0, 1, (int)B, D, D, D, D, EPI_STORE_F32, 1.0f, dx, D, nullptr, 0, nullptr, nullptr, 0, nullptr, 0,

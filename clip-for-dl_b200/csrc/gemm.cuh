@@ -37,6 +37,7 @@ struct GemmParams {
   float drop_p;             // EPI_BIAS_RESID_F32: dropout on (acc + bias) before the residual add (0 = off)
   unsigned int drop_seed;
   const unsigned int* drop_seed_dev;   // optional device word added to drop_seed (a captured CUDA graph draws a fresh mask per replay)
+  int split_rows;           // deterministic split-K: split z stores its partial tile at row offset z * split_rows of out0 (0 = off)
 };
 
 constexpr int GEMM_BM = 128;
@@ -331,7 +332,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         const int col = n0 + c;
         if (!row_ok || col >= p.N) continue;          // N is a multiple of 32 (host-checked)
-        gemm_epilogue_chunk<EPI>(p, v, row, col);
+        gemm_epilogue_chunk<EPI>(p, v, row + z * p.split_rows, col);
       }
     }
   }

@@ -14,7 +14,8 @@ namespace b200 {
 int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, int K, long long lda, long long ldb,
               int epi, float alpha, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
               const void* resid, long long ld_res, const float* aux, long long ld_aux, int split_k, cudaStream_t stream,
-              float drop_p = 0.f, unsigned int drop_seed = 0u, int aux_is_bf16 = 0, const unsigned int* drop_seed_dev = nullptr);
+              float drop_p = 0.f, unsigned int drop_seed = 0u, int aux_is_bf16 = 0, const unsigned int* drop_seed_dev = nullptr,
+              float* splitk_ws = nullptr, size_t splitk_ws_bytes = 0);
 }
 using namespace b200;
 
@@ -45,8 +46,13 @@ extern "C" int b200clip_proj_fwd(const void* x_bf16, long long B, int E, int D, 
   return b200clip_layernorm_fwd(z_f32, gamma, beta, y_f32, yhat_bf16, mean, rstd, inv_norm, B, D, ln_eps, 1e-12f, stream);
 }
 
+// fp32 partial tiles of the deterministic split-K weight-gradient GEMMs.  split_for keeps tiles * splits <= #SMs and a
+// tile is at most 128 x 256, so splits * M * N * 4 <= #SMs * 128 KB (19.4 MB) whatever the shape.
+static size_t splitk_ws_bytes() { return static_cast<size_t>(num_sms()) * 128 * 256 * sizeof(float); }
+
 extern "C" size_t b200clip_proj_bwd_workspace_bytes(long long B, int E, int D) {
   size_t n = 0;
+  n += (splitk_ws_bytes() + 255) & ~size_t(255);
   n += static_cast<size_t>(B) * D * 4;                      // dz f32
   n += static_cast<size_t>(B) * D * 2;                      // dz bf16
   n += static_cast<size_t>(B) * D * 2;                      // dp bf16
@@ -77,6 +83,8 @@ extern "C" int b200clip_proj_bwd(const float* dy, const float* dyhat, int dyhat_
   void* ln_work = carve(ln_ws);
   const size_t cs_ws = b200clip_colsum_workspace_bytes(B, D);
   void* cs_work = carve(cs_ws);
+  const size_t sk_ws = splitk_ws_bytes();
+  float* sk_work = reinterpret_cast<float*>(carve(sk_ws));
 
   // Without dropout the fc branch and the residual branch see the same dz: the f32 copy (67 MB written + read at B = 32768)
   // is skipped and the residual add in the GELU-backward epilogue reads the bf16 copy the GEMMs use anyway.
@@ -89,9 +97,8 @@ extern "C" int b200clip_proj_bwd(const float* dy, const float* dyhat, int dyhat_
                                           drop_seed, drop_seed_dev, ln_work, ln_ws, stream);
   if (rc) return rc;
   // dW2[o][j] = sum_b dz[b][o] h[b][j]
-  B200_CHECK_CUDA(cudaMemsetAsync(dw2, 0, static_cast<size_t>(D) * D * 4, s));
   if ((rc = gemm_bf16(dz_bf, h_bf16, 1, 1, D, D, (int)B, D, D, EPI_ATOMIC_F32, 1.0f, dw2, D, nullptr, 0, nullptr, nullptr, 0,
-                      nullptr, 0, split_for(D, D, (int)B), s)))
+                      nullptr, 0, split_for(D, D, (int)B), s, 0.f, 0u, 0, nullptr, sk_work, sk_ws)))
     return rc;
   // dp = (dz W2) * gelu'(p) + dz
   if ((rc = gemm_bf16(dz_bf, w2_bf16, 0, 1, (int)B, D, D, D, D, EPI_GELU_BWD, 1.0f, dp_bf, D, nullptr, 0, nullptr, p_bf16, D,
@@ -99,9 +106,8 @@ extern "C" int b200clip_proj_bwd(const float* dy, const float* dyhat, int dyhat_
     return rc;
   if ((rc = b200clip_colsum(dp_bf, 1, D, B, D, db1, 0, cs_work, cs_ws, stream))) return rc;
   // dW1[o][e] = sum_b dp[b][o] x[b][e]
-  B200_CHECK_CUDA(cudaMemsetAsync(dw1, 0, static_cast<size_t>(D) * E * 4, s));
   if ((rc = gemm_bf16(dp_bf, x_bf16, 1, 1, D, E, (int)B, D, E, EPI_ATOMIC_F32, 1.0f, dw1, E, nullptr, 0, nullptr, nullptr, 0,
-                      nullptr, 0, split_for(D, E, (int)B), s)))
+                      nullptr, 0, split_for(D, E, (int)B), s, 0.f, 0u, 0, nullptr, sk_work, sk_ws)))
     return rc;
   if (dx_f32 || dx_bf16) {                         // input gradient in the caller's dtype (bf16 inputs get bf16 grads directly)
     B200_REQUIRE(E % 32 == 0, "proj_bwd: dx needs E %% 32 == 0");
@@ -133,6 +139,7 @@ extern "C" size_t b200clip_fusion_bwd_workspace_bytes(long long B, int D) {
   size_t n = 0;
   n += 2 * (((static_cast<size_t>(B) * D * 2) + 255) & ~size_t(255));      // dy bf16, dh bf16
   n += 2 * ((b200clip_colsum_workspace_bytes(B, D) + 255) & ~size_t(255));
+  n += (splitk_ws_bytes() + 255) & ~size_t(255);
   return n + 1024;
 }
 
@@ -149,13 +156,14 @@ extern "C" int b200clip_fusion_bwd(const float* dy, const void* x_bf16, long lon
   const size_t cs_ws = b200clip_colsum_workspace_bytes(B, D);
   void* cs0 = carve(cs_ws);
   void* cs1 = carve(cs_ws);
+  const size_t sk_ws = splitk_ws_bytes();
+  float* sk_work = reinterpret_cast<float*>(carve(sk_ws));
   int rc;
   if ((rc = b200clip_cast_f32_bf16(dy, dy_bf, B * D, stream))) return rc;
   if ((rc = b200clip_colsum(dy, 0, D, B, D, db3, 0, cs0, cs_ws, stream))) return rc;           // db3 = column sums of dy
   // dW3[o][j] = sum_b dy[b][o] h[b][j]
-  B200_CHECK_CUDA(cudaMemsetAsync(dw3, 0, static_cast<size_t>(D) * D * 4, s));
   if ((rc = gemm_bf16(dy_bf, h_bf16, 1, 1, D, D, (int)B, D, D, EPI_ATOMIC_F32, 1.0f, dw3, D, nullptr, 0, nullptr, nullptr, 0,
-                      nullptr, 0, split_for(D, D, (int)B), s)))
+                      nullptr, 0, split_for(D, D, (int)B), s, 0.f, 0u, 0, nullptr, sk_work, sk_ws)))
     return rc;
   // dh = (dy W3) / (1 - p) where the unit was positive and kept
   if ((rc = gemm_bf16(dy_bf, w3_bf16, 0, 1, (int)B, D, D, D, D, EPI_RELU_BWD, 1.0f / (1.0f - drop_p), dh_bf, D, nullptr, 0, nullptr,
@@ -163,9 +171,8 @@ extern "C" int b200clip_fusion_bwd(const float* dy, const void* x_bf16, long lon
     return rc;
   if ((rc = b200clip_colsum(dh_bf, 1, D, B, D, db0, 0, cs1, cs_ws, stream))) return rc;
   // dW0[o][e] = sum_b dh[b][o] x[b][e]
-  B200_CHECK_CUDA(cudaMemsetAsync(dw0, 0, static_cast<size_t>(D) * 2 * D * 4, s));
   if ((rc = gemm_bf16(dh_bf, x_bf16, 1, 1, D, 2 * D, (int)B, D, 2 * D, EPI_ATOMIC_F32, 1.0f, dw0, 2 * D, nullptr, 0, nullptr, nullptr, 0,
-                      nullptr, 0, split_for(D, 2 * D, (int)B), s)))
+                      nullptr, 0, split_for(D, 2 * D, (int)B), s, 0.f, 0u, 0, nullptr, sk_work, sk_ws)))
     return rc;
   if (dx_f32) {
     if ((rc = gemm_bf16(dh_bf, w0_bf16, 0, 1, (int)B, 2 * D, D, D, 2 * D, EPI_STORE_F32, 1.0f, dx_f32, 2 * D, nullptr, 0, nullptr,

@@ -21,7 +21,8 @@ namespace b200 {
 int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, int K, long long lda, long long ldb,
               int epi, float alpha, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
               const void* resid, long long ld_res, const float* aux, long long ld_aux, int split_k, cudaStream_t stream,
-              float drop_p = 0.f, unsigned int drop_seed = 0u, int aux_is_bf16 = 0, const unsigned int* drop_seed_dev = nullptr);
+              float drop_p = 0.f, unsigned int drop_seed = 0u, int aux_is_bf16 = 0, const unsigned int* drop_seed_dev = nullptr,
+              float* splitk_ws = nullptr, size_t splitk_ws_bytes = 0);
 
 constexpr int SG_TILE = 64, SG_K = 16;
 
