@@ -4,9 +4,12 @@ rank 3: dynamic per-label thresholds from a validation slice and the weighted tw
 per-view prediction lists of multimodal_attention/disease_analysis.py:361-413, with label INDICES instead of disease-name
 strings (the reference maps names back through disease_list.index, :218-221).
 
-Parity status: the reference code lives inside `main()` between data loaders and a checkpoint load, so it cannot be imported
-and run here -> "parity unpinned" by reference outputs; the F1 it calls (sklearn.metrics.f1_score, zero_division=0) is pinned
-against scikit-learn itself in tests/test_oracle_zs_post.py.  The CUDA path (csrc/zs_post.cu) is checked against this file in
+Parity status: PINNED.  The reference code lives inside `main()` between data loaders and a checkpoint load; round 2 runs
+that function unmodified with the data side stubbed (oracle/make_golden_zs_main.py: synthetic loader, stub encoders, the
+reference's own projectors / predict_zero_shot / f1_score / evaluate_predictions) and records the thresholds dict it passes to
+its second pass and the prediction matrix it hands to evaluate_predictions -> tests/golden/zs_main_golden.npz.
+tests/test_oracle_zs_post.py checks this file against that run BIT-EXACTLY (float64 thresholds, {0,1} matrix), and the F1
+against scikit-learn.  The CUDA path (csrc/zs_post.cu) is checked against this file and against the same golden in
 tests/test_gpu_zs_post.py.
 """
 from __future__ import annotations

@@ -69,3 +69,19 @@ def test_thresholds_then_merge_pipeline_matches_oracle():
     got = b200clip.merge_two_views(torch.from_numpy(pv).to(d), thr)
     ref = Z.merged_prediction_matrix(pv, thr.cpu().numpy())
     assert np.array_equal(got.cpu().numpy().astype(np.float64), ref)
+
+
+def test_device_path_equals_reference_main_run():
+    """Golden minted by the reference's unmodified main() (oracle/make_golden_zs_main.py): thresholds from the first 25 % of
+    the validation studies, merged prediction matrix over all of them."""
+    import b200clip
+    d = dev()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "zs_main_golden.npz"))
+    pv, labels, n_thr = g["prob_views"], g["labels"], int(g["n_threshold_studies"])
+    mx = torch.from_numpy(pv[:n_thr]).to(d).amax(dim=1)
+    thr = b200clip.dynamic_thresholds(mx, torch.from_numpy(labels[:n_thr]).to(d))
+    np.testing.assert_allclose(thr.cpu().numpy(), g["thresholds"], rtol=0, atol=1e-12)
+    got = b200clip.merge_two_views(torch.from_numpy(pv).to(d), thr)
+    assert np.array_equal(got.cpu().numpy().astype(np.float64), g["pred_matrix"])
+    got = b200clip.merge_two_views(torch.from_numpy(pv).to(d), torch.from_numpy(g["thresholds"]).to(d))
+    assert np.array_equal(got.cpu().numpy().astype(np.float64), g["pred_matrix"])

@@ -82,3 +82,19 @@ def test_merged_prediction_matrix_shape_and_fallback():
     thr = np.full(14, 0.97)
     m = Z.merged_prediction_matrix(pv, thr)
     assert m.shape == (50, 14) and np.all(m.sum(1) >= 1)                        # every sample gets at least one label
+
+
+def _main_golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "zs_main_golden.npz"))
+
+
+def test_oracle_equals_reference_main_run():
+    """The reference's own main() (multimodal_attention/zero_shot_predict.py:14-261) was executed unmodified by
+    oracle/make_golden_zs_main.py with the data side stubbed; its thresholds dict and final prediction matrix are the golden."""
+    g = _main_golden()
+    pv, labels, n_thr = g["prob_views"], g["labels"], int(g["n_threshold_studies"])
+    thr = Z.dynamic_thresholds(pv[:n_thr].astype(np.float64).max(axis=1), labels[:n_thr])
+    assert np.array_equal(thr, g["thresholds"])                                  # bit-exact float64
+    assert thr[3] == 0.8 and thr[9] == 0.2
+    assert np.array_equal(Z.merged_prediction_matrix(pv, g["thresholds"]), g["pred_matrix"])
+    assert g["pred_matrix"].sum() > 0 and (g["pred_matrix"].sum(axis=1) >= 1).all()   # the fallback keeps one label per study
