@@ -63,6 +63,7 @@ SIGNATURES = {
     "b200clip_infonce_workspace_bytes": (sz, [ll, ll]),
     "b200clip_infonce_fwd_stats": (i32, [vp, vp, i32, ll, ll, f32, vp, vp, vp, sz, vp]),
     "b200clip_infonce_loss": (i32, [vp, vp, i32, ll, ll, ll, f32, vp, vp, ll, ll, vp, vp, vp, vp, vp, sz, vp]),
+    "b200clip_infonce_inv_stats": (i32, [vp, ll, vp, ll, vp, vp, vp]),
     "b200clip_infonce_bwd_splits": (i32, [ll, ll]),
     "b200clip_infonce_bwd": (i32, [vp, vp, i32, ll, ll, ll, f32, vp, vp, vp, vp, i32, vp, i32, vp]),
     "b200clip_smallc_workspace_bytes": (sz, [ll, i32, i32]),

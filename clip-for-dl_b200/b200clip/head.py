@@ -54,27 +54,37 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
     b_loc = x_img.shape[0]
     b_glob = b_loc * W
     row0 = rank * b_loc
-    xi, xt = ops.cast_bf16(x_img), ops.cast_bf16(x_txt)
-    iw1b, iw2b, tw1b, tw2b = (ops.cast_bf16(w) for w in (iw1, iw2, tw1, tw2))
     f = ops._f32c
     labels_f = f(labels)
-    lsum = ops._label_sum(labels_f)
-    lsum_work = dp.sum_across_async(lsum, group)          # global label count, needed only by the BCE heads
     # The text side (projection, then the all-gather of T_hat) and the image side (projection; the BCE heads below) are
     # independent until the logits.  With small per-rank batches every kernel of the two chains is a fraction of a wave
     # (a [4096 x 512] GEMM is 64-128 tiles for 148 SMs), so they run on two streams; at large batches each kernel fills the GPU
     # and one stream is used.  Independent dropout streams for the two projections (seed, seed + 1).
-    side = _side_stream(x_img.device) if b_loc <= TWO_STREAM_MAX_ROWS else None
+    # Two more branches at those sizes: the BCE heads (they need only the image projection) run beside the InfoNCE forward
+    # kernel, and the loss VALUE (diagonal + log-sum numerators, their all-reduce) is computed beside the backward pass, which
+    # needs only the half-inverse statistics.
+    small = b_loc <= TWO_STREAM_MAX_ROWS
+    side = _side_stream(x_img.device) if small else None
+    heads_side = _side_stream(x_img.device, 2) if small else None
+    loss_side = _side_stream(x_img.device, 3)
     main = torch.cuda.current_stream()
     if side is not None:
         side.wait_stream(main)
+        heads_side.wait_stream(main)
+    with torch.cuda.stream(heads_side if small else main):
+        lsum = ops._label_sum(labels_f)
+        lsum_work = dp.sum_across_async(lsum, group)      # global label count, needed only by the BCE heads
     with torch.cuda.stream(side if side is not None else main):
+        xt = ops.cast_bf16(x_txt)
+        tw1b, tw2b = ops.cast_bf16(tw1), ops.cast_bf16(tw2)
         y_txt, that_loc, inv_txt, saved_t = ops.proj_fwd(xt, tw1b, f(tb1), tw2b, f(tb2), f(tg), f(tbeta), want_yhat=True,
                                                          drop_p=drop_p, drop_seed=drop_seed + 1, drop_seed_dev=drop_seed_dev)
         that_all, work = dp.gather_rows(that_loc, group, async_op=True)
         if side is not None:
             dp.wait(work)                         # the side stream waits for NCCL; the main stream joins the side stream below
             work = None
+    xi = ops.cast_bf16(x_img)
+    iw1b, iw2b = ops.cast_bf16(iw1), ops.cast_bf16(iw2)
     y_img, ihat, inv_img, saved_i = ops.proj_fwd(xi, iw1b, f(ib1), iw2b, f(ib2), f(ig), f(ibeta), want_yhat=True,
                                                  drop_p=drop_p, drop_seed=drop_seed, drop_seed_dev=drop_seed_dev)
     C = class_text.shape[0]
@@ -83,29 +93,40 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
     # one pass over y_img serves both BCE heads, forward AND backward: the input gradient d_bce (for upstream grad 1)
     # and the FC coefficients are produced here; backward only scales them by the incoming gradient.  The heads do not
     # depend on the gathered texts, so they run while the all-gather is still in flight.
-    dp.wait(lsum_work)
-    fast_heads = ops.heads_mma_supported(y_img.shape[1], C, Cf)
-    if fast_heads:        # tensor-core path: reads the bf16 normalised features LayerNorm wrote for InfoNCE
-        d_bce, coef, db_raw = ops.bce_heads_mma(ihat, inv_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
-                                                total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
-                                                sums_out=sums6[3:], want_grad=need_grad)
-    else:
-        db_raw = None
-        d_bce = torch.empty_like(y_img) if need_grad else None
-        *_, coef = ops.bce_heads(y_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
-                                 total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
-                                 dx_out=d_bce, want_coef=need_grad, finalize=False, sums_out=sums6[3:])
+    if small:
+        heads_side.wait_stream(main)                       # the heads branch: label count (above), then the image features
+    with torch.cuda.stream(heads_side if small else main):
+        dp.wait(lsum_work)
+        fast_heads = ops.heads_mma_supported(y_img.shape[1], C, Cf)
+        if fast_heads:        # tensor-core path: reads the bf16 normalised features LayerNorm wrote for InfoNCE
+            d_bce, coef, db_raw = ops.bce_heads_mma(ihat, inv_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
+                                                    total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
+                                                    sums_out=sums6[3:], want_grad=need_grad)
+        else:
+            db_raw = None
+            d_bce = torch.empty_like(y_img) if need_grad else None
+            *_, coef = ops.bce_heads(y_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
+                                     total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
+                                     dx_out=d_bce, want_coef=need_grad, finalize=False, sums_out=sums6[3:])
     dp.wait(work)
     if side is not None:
         main.wait_stream(side)
+    keep = []
     _, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, group=group if W > 1 else None,
-                                          sums_out=sums6[:3])
+                                          sums_out=sums6[:3], loss_stream=loss_side, keep=keep)
+    if small:
+        main.wait_stream(heads_side)                       # backward needs d_bce / coef
+        loss_side.wait_stream(heads_side)                  # the BCE numerators in sums6[3:]
     # The loss VALUE needs the six numerators summed over ranks; nothing in the backward pass does.  One small
-    # all-reduce, off the critical path: `finish` waits for it and runs the one-thread finalisation kernel.
-    sums_work = dp.sum_across_async(sums6, group)
+    # all-reduce on the loss branch, off the critical path: `finish` joins the branch and runs the one-thread finalisation.
+    with torch.cuda.stream(loss_side):
+        sums_work = dp.sum_across_async(sums6, group)
+        dp.wait(sums_work)
+    keep.extend((sums6, lsum))
 
     def finish():
-        dp.wait(sums_work)
+        torch.cuda.current_stream().wait_stream(loss_side)
+        keep.clear()
         return ops.head_loss_finalize(sums6, lsum, tau_nce, b_glob, float(b_glob) * C, float(b_glob) * Cf)
 
     if defer_loss:

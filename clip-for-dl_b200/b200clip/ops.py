@@ -342,10 +342,14 @@ class AttentionFn(torch.autograd.Function):
 # a-N symmetric InfoNCE
 # --------------------------------------------------------------------------------------------------------------
 def infonce_forward(i_hat: torch.Tensor, t_hat: torch.Tensor, temperature: float, row0: int = 0, group=None,
-                    sums_out: Optional[torch.Tensor] = None):
+                    sums_out: Optional[torch.Tensor] = None, loss_stream: Optional[torch.cuda.Stream] = None,
+                    keep: Optional[list] = None):
     """i_hat: local rows [b_loc, D] bf16; t_hat: all rows [b_glob, D] bf16.  Returns (loss, rinvh, cinvh).
     With sums_out (3 doubles) the rank-local loss numerators are written there and loss is None (the fused head sums
-    them over ranks together with the BCE numerators and finalises once)."""
+    them over ranks together with the BCE numerators and finalises once).  With loss_stream (needs sums_out and `keep`) the
+    loss numerators are computed on that stream, off the critical path: the current stream only runs the half-inverse
+    statistics the backward pass needs; the caller joins loss_stream and must hold `keep` (the tensors that stream reads)
+    until then."""
     lib = load()
     b_loc, D = i_hat.shape
     b_glob = t_hat.shape[0]
@@ -372,6 +376,15 @@ def infonce_forward(i_hat: torch.Tensor, t_hat: torch.Tensor, temperature: float
     sums = sums_out if deferred else torch.empty((3,), dtype=torch.float64, device=dev)
     loss = None if deferred else torch.empty((), dtype=torch.float32, device=dev)
     c_lo, c_hi = (row0, row0 + b_loc) if world > 1 else (0, b_glob)
+    if loss_stream is not None:
+        assert deferred and keep is not None
+        check(lib.b200clip_infonce_inv_stats(ptr(r), b_loc, ptr(c), b_glob, ptr(rinvh), ptr(cinvh), stream_ptr()), "infonce_inv_stats")
+        loss_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(loss_stream):
+            check(lib.b200clip_infonce_loss(ptr(i_hat), ptr(t_hat), D, b_loc, b_glob, row0, temperature, ptr(r), ptr(c), c_lo, c_hi,
+                                            None, None, ptr(sums), None, ptr(ws), ws.numel(), stream_ptr()), "infonce_loss")
+        keep.extend((ws, r, c, sums, i_hat, t_hat))
+        return None, rinvh, cinvh
     check(lib.b200clip_infonce_loss(ptr(i_hat), ptr(t_hat), D, b_loc, b_glob, row0, temperature, ptr(r), ptr(c), c_lo, c_hi,
                                     ptr(rinvh), ptr(cinvh), ptr(sums), ptr(loss) if (world == 1 and not deferred) else None,
                                     ptr(ws), ws.numel(), stream_ptr()), "infonce_loss")

@@ -151,4 +151,38 @@ struct SmemAttrOnce {
   }
 };
 
+
+// A fork lane = one auxiliary stream + events, for entry points that run two independent kernel chains concurrently
+// (b200clip_proj_bwd: weight-gradient GEMMs beside the dz -> dp -> dx chain).  fork(): aux waits for everything enqueued on
+// the caller's stream so far; join(): the caller's stream waits for aux.  Event record / wait are capturable, so inside a
+// CUDA-graph capture the lane's work becomes a parallel branch of the same graph.  Lanes are created once per device (all of
+// them at the first use, i.e. in the un-captured warm-up call) and handed out round-robin, so two concurrent callers (the
+// text-side and image-side chains run on two streams) get different lanes.
+struct ForkLane {
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev[4] = {};
+  cudaError_t link(cudaStream_t from, cudaStream_t to, int e) {       // `to` waits for what `from` holds now
+    cudaError_t rc = cudaEventRecord(ev[e], from);
+    return rc != cudaSuccess ? rc : cudaStreamWaitEvent(to, ev[e], 0);
+  }
+};
+inline ForkLane* acquire_fork_lane() {
+  constexpr int kLanes = 8;
+  static ForkLane lanes[kMaxDevices][kLanes];
+  static std::once_flag once[kMaxDevices];
+  static bool ok[kMaxDevices] = {};
+  static std::atomic<unsigned> next[kMaxDevices];
+  const int dev = current_device();
+  std::call_once(once[dev], [&] {
+    bool good = true;
+    for (auto& l : lanes[dev]) {
+      good = good && cudaStreamCreateWithFlags(&l.aux, cudaStreamNonBlocking) == cudaSuccess;
+      for (auto& e : l.ev) good = good && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok[dev] = good;
+  });
+  if (!ok[dev]) return nullptr;
+  return &lanes[dev][next[dev].fetch_add(1u, std::memory_order_relaxed) % kLanes];
+}
+
 }  // namespace b200

@@ -1050,6 +1050,15 @@ __global__ void __launch_bounds__(256) nce_reduce_stats_kernel(const float* __re
   }
 }
 
+// rinvh = 0.5 / r, cinvh = 0.5 / c: all the backward pass needs from the statistics.  Launched alone when the loss VALUE is
+// computed off the critical path (b200clip_infonce_inv_stats; nce_loss_kernel then gets null rinvh / cinvh).
+__global__ void __launch_bounds__(256) nce_inv_stats_kernel(const float* __restrict__ r, int b_loc, const float* __restrict__ c,
+                                                            int b_glob, float* __restrict__ rinvh, float* __restrict__ cinvh) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < b_loc) rinvh[i] = 0.5f / r[i];
+  if (i < b_glob) cinvh[i] = 0.5f / c[i];
+}
+
 // sums[0] = sum_i log r_i (local rows), sums[1] = sum_{j in [c_lo,c_hi)} log c_j, sums[2] = sum_i S_ii  (S_ii = I_i.T_{row0+i}/tau)
 // also writes rinvh = 0.5 / r, cinvh = 0.5 / c.  Deterministic: per-block partials, last block folds them in order.
 __global__ void __launch_bounds__(256) nce_loss_kernel(const __nv_bfloat16* __restrict__ I, const __nv_bfloat16* __restrict__ T,
@@ -1068,11 +1077,11 @@ __global__ void __launch_bounds__(256) nce_loss_kernel(const __nv_bfloat16* __re
   for (int i = gtid; i < b_loc; i += gsz) {
     const float ri = r[i];
     a_logr += static_cast<double>(logf(ri));
-    rinvh[i] = 0.5f / ri;
+    if (rinvh) rinvh[i] = 0.5f / ri;
   }
   for (int j = gtid; j < b_glob; j += gsz) {
     const float cj = c[j];
-    cinvh[j] = 0.5f / cj;
+    if (cinvh) cinvh[j] = 0.5f / cj;
     if (j >= c_lo && j < c_hi) a_logc += static_cast<double>(logf(cj));
   }
   // diagonal: one warp per row, D bf16 = D/8 16-byte pieces dealt round-robin to the lanes
@@ -1266,6 +1275,15 @@ extern "C" int b200clip_infonce_loss(const void* i_hat, const void* t_hat, int D
   nce_loss_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(i_hat), static_cast<const __nv_bfloat16*>(t_hat),
                                        D, (int)b_loc, (int)b_glob, (int)row0, 1.0f / temperature, r, c, (int)c_lo, (int)c_hi,
                                        rinvh, cinvh, partial, counter, sums, loss, static_cast<float>(nce_shift(temperature)));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200clip_infonce_inv_stats(const float* r, long long b_loc, const float* c, long long b_glob, float* rinvh,
+                                          float* cinvh, void* stream) {
+  B200_REQUIRE(b_loc > 0 && b_glob >= b_loc && r && c && rinvh && cinvh, "infonce_inv_stats: bad arguments");
+  nce_inv_stats_kernel<<<static_cast<unsigned>((b_glob + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      r, (int)b_loc, c, (int)b_glob, rinvh, cinvh);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

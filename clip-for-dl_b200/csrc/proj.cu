@@ -96,18 +96,26 @@ extern "C" int b200clip_proj_bwd(const float* dy, const float* dyhat, int dyhat_
                                           rstd, gamma, need_f32_dz ? dz : nullptr, dz_bf, dgamma, dbeta, db2, 0, B, D, drop_p,
                                           drop_seed, drop_seed_dev, ln_work, ln_ws, stream);
   if (rc) return rc;
+  // Two chains from here: the data chain dz -> dp -> dx on the caller's stream, the parameter-gradient chain (dW2, db1, dW1)
+  // on a fork lane.  At per-rank batches of a few thousand rows every kernel here is a fraction of a wave, so the chains run
+  // side by side (B = 4096: 105 -> 65 us per side); at large batches they simply queue.  B200CLIP_PROJ_BWD_FORK=0 disables.
+  static const bool fork_enabled = [] { const char* e = getenv("B200CLIP_PROJ_BWD_FORK"); return !(e && atoi(e) == 0); }();
+  ForkLane* lane = fork_enabled ? acquire_fork_lane() : nullptr;
+  cudaStream_t sa = lane ? lane->aux : s;
+  if (lane) B200_CHECK_CUDA(lane->link(s, sa, 0));                                   // aux sees dz
   // dW2[o][j] = sum_b dz[b][o] h[b][j]
   if ((rc = gemm_bf16(dz_bf, h_bf16, 1, 1, D, D, (int)B, D, D, EPI_ATOMIC_F32, 1.0f, dw2, D, nullptr, 0, nullptr, nullptr, 0,
-                      nullptr, 0, split_for(D, D, (int)B), s, 0.f, 0u, 0, nullptr, sk_work, sk_ws)))
+                      nullptr, 0, split_for(D, D, (int)B), sa, 0.f, 0u, 0, nullptr, sk_work, sk_ws)))
     return rc;
   // dp = (dz W2) * gelu'(p) + dz
   if ((rc = gemm_bf16(dz_bf, w2_bf16, 0, 1, (int)B, D, D, D, D, EPI_GELU_BWD, 1.0f, dp_bf, D, nullptr, 0, nullptr, p_bf16, D,
                       need_f32_dz ? dz : reinterpret_cast<const float*>(dz_bf), D, 1, s, 0.f, 0u, need_f32_dz ? 0 : 1)))
     return rc;
-  if ((rc = b200clip_colsum(dp_bf, 1, D, B, D, db1, 0, cs_work, cs_ws, stream))) return rc;
+  if (lane) B200_CHECK_CUDA(lane->link(s, sa, 1));                                   // aux sees dp
+  if ((rc = b200clip_colsum(dp_bf, 1, D, B, D, db1, 0, cs_work, cs_ws, sa))) return rc;
   // dW1[o][e] = sum_b dp[b][o] x[b][e]
   if ((rc = gemm_bf16(dp_bf, x_bf16, 1, 1, D, E, (int)B, D, E, EPI_ATOMIC_F32, 1.0f, dw1, E, nullptr, 0, nullptr, nullptr, 0,
-                      nullptr, 0, split_for(D, E, (int)B), s, 0.f, 0u, 0, nullptr, sk_work, sk_ws)))
+                      nullptr, 0, split_for(D, E, (int)B), sa, 0.f, 0u, 0, nullptr, sk_work, sk_ws)))
     return rc;
   if (dx_f32 || dx_bf16) {                         // input gradient in the caller's dtype (bf16 inputs get bf16 grads directly)
     B200_REQUIRE(E % 32 == 0, "proj_bwd: dx needs E %% 32 == 0");
@@ -115,6 +123,7 @@ extern "C" int b200clip_proj_bwd(const float* dy, const float* dyhat, int dyhat_
                         dx_f32 ? static_cast<void*>(dx_f32) : dx_bf16, E, nullptr, 0, nullptr, nullptr, 0, nullptr, 0, 1, s)))
       return rc;
   }
+  if (lane) B200_CHECK_CUDA(lane->link(sa, s, 2));                                   // join
   return B200_OK;
 }
 

@@ -140,6 +140,10 @@ int b200clip_infonce_fwd_stats(const void* i_hat, const void* t_hat, int D, long
 int b200clip_infonce_loss(const void* i_hat, const void* t_hat, int D, long long b_loc, long long b_glob, long long row0,
                           float temperature, const float* r, const float* c, long long c_lo, long long c_hi, float* rinvh,
                           float* cinvh, double* sums, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+/* rinvh = 0.5 / r, cinvh = 0.5 / c alone (one tiny kernel): everything the backward pass needs from the statistics, so that
+ * b200clip_infonce_loss (then called with rinvh = cinvh = NULL) can run on another stream beside the backward kernel. */
+int b200clip_infonce_inv_stats(const float* r, long long b_loc, const float* c, long long b_glob, float* rinvh, float* cinvh,
+                               void* stream);
 /* d_i is [d_i_splits][b_loc][D]: partial sums over column ranges (1 <= splits <= 8; b200clip_infonce_bwd_splits suggests
  * a count that balances the grid when b_loc << b_glob); their sum is the gradient.  D = 512 or 768.  directions: 1 = d_i only,
  * 2 = d_t_partial only, 3 = both in one launch (the data-parallel step launches 2 first so that the reduce-scatter of
