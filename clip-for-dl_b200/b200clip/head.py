@@ -79,12 +79,19 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
         tw1b, tw2b = ops.cast_bf16(tw1), ops.cast_bf16(tw2)
         y_txt, that_loc, inv_txt, saved_t = ops.proj_fwd(xt, tw1b, f(tb1), tw2b, f(tb2), f(tg), f(tbeta), want_yhat=True,
                                                          drop_p=drop_p, drop_seed=drop_seed + 1, drop_seed_dev=drop_seed_dev)
+        if W > 1 and side is not None:
+            # data parallel: the image chain starts when the text chain has finished, so the text chain gets the whole GPU and
+            # the all-gather of T_hat (81 us at 8 ranks, RING_LL) starts ~25 us earlier, hidden behind the image chain + heads
+            text_done = torch.cuda.Event()
+            text_done.record(side)
         that_all, work = dp.gather_rows(that_loc, group, async_op=True)
         if side is not None:
             dp.wait(work)                         # the side stream waits for NCCL; the main stream joins the side stream below
             work = None
     xi = ops.cast_bf16(x_img)
     iw1b, iw2b = ops.cast_bf16(iw1), ops.cast_bf16(iw2)
+    if W > 1 and side is not None:
+        main.wait_event(text_done)
     y_img, ihat, inv_img, saved_i = ops.proj_fwd(xi, iw1b, f(ib1), iw2b, f(ib2), f(ig), f(ibeta), want_yhat=True,
                                                  drop_p=drop_p, drop_seed=drop_seed, drop_seed_dev=drop_seed_dev)
     C = class_text.shape[0]
@@ -112,21 +119,33 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
     if side is not None:
         main.wait_stream(side)
     keep = []
-    _, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, group=group if W > 1 else None,
-                                          sums_out=sums6[:3], loss_stream=loss_side, keep=keep)
-    if small:
-        main.wait_stream(heads_side)                       # backward needs d_bce / coef
-        loss_side.wait_stream(heads_side)                  # the BCE numerators in sums6[3:]
-    # The loss VALUE needs the six numerators summed over ranks; nothing in the backward pass does.  One small
-    # all-reduce on the loss branch, off the critical path: `finish` joins the branch and runs the one-thread finalisation.
-    with torch.cuda.stream(loss_side):
+    if W == 1:
+        # The loss VALUE (diagonal + log-sum numerators) is needed by nothing in the backward pass: it is computed on its own
+        # branch beside the backward kernels; `finish` joins the branch and runs the one-thread finalisation.  The MAIN stream
+        # joins the heads branch only in head_backward, after the InfoNCE backward launch (d_bce / coef are first read by the
+        # image-side chain behind it).
+        _, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, sums_out=sums6[:3], loss_stream=loss_side,
+                                              keep=keep)
+        if small:
+            loss_side.wait_stream(heads_side)              # the BCE numerators in sums6[3:]
+        sums_work = None
+        keep.extend((sums6, lsum))
+    else:
+        # Data parallel: the numerators are summed over ranks, and NCCL runs a communicator's collectives in issue order -- a
+        # loss kernel queued behind the backward kernels' CTAs would hold this all-reduce, and with it the reduce-scatter of
+        # dT issued after it (measured at 2 ranks: reduce-scatter start 570 us late).  So the loss kernel stays on the main
+        # stream in front of the backward pass (6-17 us) and only the all-reduce is asynchronous.
+        if small:
+            main.wait_stream(heads_side)
+            heads_side = None
+        _, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, group=group, sums_out=sums6[:3])
         sums_work = dp.sum_across_async(sums6, group)
-        dp.wait(sums_work)
-    keep.extend((sums6, lsum))
 
     def finish():
-        torch.cuda.current_stream().wait_stream(loss_side)
-        keep.clear()
+        if sums_work is None:
+            torch.cuda.current_stream().wait_stream(loss_side)
+            keep.clear()
+        dp.wait(sums_work)
         return ops.head_loss_finalize(sums6, lsum, tau_nce, b_glob, float(b_glob) * C, float(b_glob) * Cf)
 
     if defer_loss:
@@ -138,7 +157,8 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
     tensors = (xi, xt, iw1b, iw2b, tw1b, tw2b, f(ig), f(tg), y_img, y_txt, ihat, that_all, inv_img, inv_txt, rinvh, cinvh,
                d_bce, coef, db_raw, *saved_i, *saved_t)
     meta = dict(tau_nce=tau_nce, group=group, W=W, row0=row0, need_dx=tuple(need_dx), in_dtypes=(x_img.dtype, x_txt.dtype),
-                drop=(float(drop_p), int(drop_seed)), drop_seed_dev=drop_seed_dev, has_fc_bias=fb is not None)
+                drop=(float(drop_p), int(drop_seed)), drop_seed_dev=drop_seed_dev, has_fc_bias=fb is not None,
+                heads_side=heads_side)
     return loss, parts, (tensors, meta)
 
 
@@ -173,6 +193,8 @@ def head_backward(tensors, meta, g):
         d_ihat, d_that = ops.infonce_backward(ihat, that_all, meta["tau_nce"], rinvh, cinvh, g, row0=row0, allow_splits=True)
         d_that_loc, work = d_that, None
     that_loc = that_all[row0:row0 + b_loc]                           # this rank's normalised text rows (bf16)
+    if meta.get("heads_side") is not None:
+        main.wait_stream(meta["heads_side"])         # the BCE-heads branch of the forward pass (d_bce, coef, db_raw)
     # text side (needs only the reduce-scattered dT) on the side stream, image side (needs dI) on the main stream: two chains of
     # ~12 kernels that are each a fraction of a wave at per-rank batch sizes
     if side is not None:
@@ -182,6 +204,10 @@ def head_backward(tensors, meta, g):
             dp.wait(work)
             gt = ops.proj_bwd(None, xt, tw1b, tw2b, tg, saved_t, need_dxt, meta["in_dtypes"][1], drop_p=drop_p, drop_seed=drop_seed + 1,
                               l2=(d_that_loc, that_loc, inv_txt, None, None), drop_seed_dev=seed_dev)
+            if W > 1:
+                # The text chain starts when the reduce-scatter lands, i.e. while dI is still running, and ends ~60 us before
+                # the image chain: its gradient bucket travels behind the image chain, only the image bucket is exposed.
+                txt_grads = dp.allreduce_flat([gt[1], gt[2], gt[3], gt[4], gt[5], gt[6]], group)
     if nce_side is not None:
         main.wait_stream(nce_side)
     # image side: the L2-normalisation backward (+ g * the two BCE heads' input gradient from the forward pass) runs inside
@@ -202,10 +228,10 @@ def head_backward(tensors, meta, g):
         txt_grads = dp.allreduce_flat([gt[1], gt[2], gt[3], gt[4], gt[5], gt[6]], group)
         dp.wait(img_work)
     else:
-        # two streams: the chains end together, so ONE bucket (7.9 MB: 70 us at 8 ranks) beats two latency-bound ones (2 x 55 us)
+        img_grads = dp.allreduce_flat([gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], dfw, dfb], group)
         main.wait_stream(side)
-        allg = dp.allreduce_flat([gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], dfw, dfb, gt[1], gt[2], gt[3], gt[4], gt[5], gt[6]], group)
-        img_grads, txt_grads = allg[:8], allg[8:]
+        if W == 1:
+            txt_grads = [gt[1], gt[2], gt[3], gt[4], gt[5], gt[6]]
     grads = [*img_grads[:6], *txt_grads, img_grads[6], img_grads[7]]
     if not meta["has_fc_bias"]:
         grads[-1] = None
