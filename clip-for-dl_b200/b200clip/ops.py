@@ -268,7 +268,7 @@ class FusionFn(torch.autograd.Function):
         D = D2 // 2
         dev = x.device
         dy = _f32c(dy)
-        dx = torch.empty((B, D2), dtype=torch.float32, device=dev) if ctx.need_dx else None
+        dx = torch.empty((2, B, D), dtype=torch.float32, device=dev) if ctx.need_dx else None      # d frontal | d lateral
         dw0 = torch.empty((D, D2), dtype=torch.float32, device=dev)
         dw3 = torch.empty((D, D), dtype=torch.float32, device=dev)
         db0, db3 = torch.empty((D,), dtype=torch.float32, device=dev), torch.empty((D,), dtype=torch.float32, device=dev)
@@ -277,7 +277,7 @@ class FusionFn(torch.autograd.Function):
                                       ptr(dw3), ptr(db3), ptr(ws), ws.numel(), stream_ptr()), "fusion_bwd")
         df = dl = None
         if dx is not None:
-            df, dl = dx[:, :D].to(ctx.dtypes[0]), dx[:, D:].to(ctx.dtypes[1])
+            df, dl = dx[0].to(ctx.dtypes[0]), dx[1].to(ctx.dtypes[1])
         return df, dl, dw0, db0, dw3, db3, None, None
 
 

@@ -3,9 +3,9 @@
 //   ip = x Wi^T + bi  [B, D]      tp = t Wt^T + bt  [C, D]
 //   s_bc = sum_d tanh(ip_bd + tp_cd) wa_d + ba        w = softmax_c(s)        e = ip + w tp        out = e Wo^T + bo
 // The three [B, D] x [D, D] products run on the tcgen05 GEMM (gemm.cuh); the attention core is one row kernel per pass
-// (one warp per image, tp and wa resident in shared memory, MUFU tanh, scores reduced so that lane c owns class c).
-// Backward recomputes tanh and accumulates the cross-row gradients (d tp [C, D], d wa [D], column sum of d ip) in per-warp
-// shared-memory accumulators (each lane owns its columns: no atomics), block partials, deterministic final reduction.
+// (D/128 warps per image, each owning 128 columns with its slice of tp and wa in registers, MUFU tanh, scores reduced so that
+// lane c owns class c).  Backward recomputes tanh and accumulates the cross-row gradients (d tp [C, D], d wa [D], column sum
+// of d ip) in register accumulators (each lane owns its columns: no atomics), block partials, deterministic final reduction.
 // The text side (C rows) is tiny and stays in fp32 CUDA-core kernels.
 // Bytes per image: forward 2 KB (ip f32) in, 1 KB (e bf16) + 64 B (w) out; backward 2 KB + 2 KB (ip, d e) in, 1 KB (d ip) out.
 #include <algorithm>
@@ -23,9 +23,6 @@ int gemm_bf16(const void* a, const void* b, int a_mn, int b_mn, int M, int N, in
 
 constexpr int AT_MAXC = 16;
 constexpr int AT_MAXD = 512;
-constexpr int AT_V = AT_MAXD / 128;                      // float4 groups per lane
-constexpr int AT_FWD_THREADS = 256;
-constexpr int AT_BWD_THREADS = 128;                      // 4 warps: (C + 2) x D fp32 accumulators each in shared memory
 
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -76,142 +73,161 @@ struct AttnParams {
   float* partial;        // [grid][(C + 2) * D]: d tp rows, d wa, column sum of d ip
 };
 
-__global__ void __launch_bounds__(AT_FWD_THREADS) attn_fwd_kernel(const AttnParams p) {
-  extern __shared__ __align__(16) float at_smem[];          // tp [C][D] | wa [D]
-  float* s_tp = at_smem;
-  float* s_wa = at_smem + p.C * p.D;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int C = p.C, D = p.D, nv = D >> 7;
-  for (int i = threadIdx.x; i < C * D; i += AT_FWD_THREADS) s_tp[i] = p.tp[i];
-  for (int i = threadIdx.x; i < D; i += AT_FWD_THREADS) s_wa[i] = p.wa[i];
-  __syncthreads();
-  const float ba = *p.ba;
-  for (long long row = blockIdx.x * (AT_FWD_THREADS / 32) + warp; row < p.B; row += static_cast<long long>(gridDim.x) * (AT_FWD_THREADS / 32)) {
-    float4 x[AT_V];
+// Row kernels, round 2 layout: one CTA of D/128 warps walks PAIRS of rows; warp q owns columns [128q, 128q + 128) (lane l:
+// the float4 at 128q + 4l), so tp (C x 4 values per lane), wa and -- in the backward pass -- the d tp / d wa / column-sum
+// accumulators all live in REGISTERS: no shared-memory traffic in the inner loops (round 1 kept tp in shared memory and the
+// accumulators in per-warp shared arrays: 6 LDS/STS.128 per (class, float4), 484 us at B = 32768; the MUFU floor is 58 us).
+// Both kernels are ISSUE-bound (ncu: 69-76 % issue-active, profiles/r2_ncu_attention.txt), and a third of the instructions
+// were per-row bookkeeping: the 32-wide column-sum exchange carried 16 classes + 16 zeros and the softmax used 5-level warp
+// reductions.  Two rows per iteration fill the exchange (lanes 0-15: row A's classes, lanes 16-31: row B's) and run both
+// softmaxes in the two half-warps.  The only cross-warp step is the per-pair score (forward) / d w (backward) reduction: 32
+// floats per warp through shared memory and one __syncthreads per pair (double-buffered by parity).  The next pair's
+// operands are prefetched before the current pair's arithmetic.
+constexpr int AT_MAXW = AT_MAXD / 128;                   // warps per CTA at D = 512
+
+__device__ __forceinline__ void at_load_tp(const AttnParams& p, int col, float4 (&tp)[AT_MAXC], float4& wa) {
 #pragma unroll
-    for (int i = 0; i < AT_V; ++i)
-      if (i < nv) x[i] = ldf4(p.ip + row * D + i * 128 + lane * 4);
+  for (int c = 0; c < AT_MAXC; ++c) tp[c] = c < p.C ? ldf4(p.tp + c * p.D + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+  wa = ldf4(p.wa + col);
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float half_sum(float v) {      // sum over the 16 lanes of this half-warp
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float half_max(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// every warp returns, in lane l, the sum over the CTA's warps of `mine` (fixed order: deterministic)
+__device__ __forceinline__ float at_cross_warp(float mine, float (*s_x)[AT_MAXW][32], int buf, int warp, int lane, int nwarps) {
+  s_x[buf][warp][lane] = mine;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < nwarps; ++w) tot += s_x[buf][w][lane];
+  return tot;
+}
+
+__global__ void __launch_bounds__(128, 4) attn_fwd_kernel(const AttnParams p) {
+  __shared__ float s_x[2][AT_MAXW][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int C = p.C, D = p.D, col = warp * 128 + lane * 4;
+  float4 tp[AT_MAXC], wa;
+  at_load_tp(p, col, tp, wa);
+  const float ba = *p.ba;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long B = p.B;
+  long long ra = 2ll * blockIdx.x;
+  float4 xa = ra < B ? ldf4(p.ip + ra * D + col) : z4, xb = ra + 1 < B ? ldf4(p.ip + (ra + 1) * D + col) : z4;
+  for (int it = 0; ra < B; ra += 2ll * gridDim.x, ++it) {
+    const long long na = ra + 2ll * gridDim.x;
+    const float4 xan = na < B ? ldf4(p.ip + na * D + col) : z4, xbn = na + 1 < B ? ldf4(p.ip + (na + 1) * D + col) : z4;
     float part[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      part[c] = 0.f;
-      if (c < AT_MAXC && c < C) {
-        float a = 0.f;
-#pragma unroll
-        for (int i = 0; i < AT_V; ++i)
-          if (i < nv) {
-            const float4 t = ldf4(s_tp + c * D + i * 128 + lane * 4), wv = ldf4(s_wa + i * 128 + lane * 4);
-            a += tanh_fast(x[i].x + t.x) * wv.x + tanh_fast(x[i].y + t.y) * wv.y + tanh_fast(x[i].z + t.z) * wv.z +
-                 tanh_fast(x[i].w + t.w) * wv.w;                              // :1101
-          }
-        part[c] = a;
+    for (int c = 0; c < AT_MAXC; ++c) {
+      part[c] = 0.f; part[16 + c] = 0.f;
+      if (c < C) {                                                             // :1101
+        part[c] = tanh_fast(xa.x + tp[c].x) * wa.x + tanh_fast(xa.y + tp[c].y) * wa.y + tanh_fast(xa.z + tp[c].z) * wa.z +
+                  tanh_fast(xa.w + tp[c].w) * wa.w;
+        part[16 + c] = tanh_fast(xb.x + tp[c].x) * wa.x + tanh_fast(xb.y + tp[c].y) * wa.y + tanh_fast(xb.z + tp[c].z) * wa.z +
+                       tanh_fast(xb.w + tp[c].w) * wa.w;
       }
     }
-    const float score = colsum32_at(part, lane) + ba;                         // lane c: s_c
-    const bool act = lane < C;
-    const float m = warp_max(act ? score : -INFINITY);
+    // lane l: class (l & 15) of row ra + (l >> 4)
+    const float score = at_cross_warp(colsum32_at(part, lane), s_x, it & 1, warp, lane, nwarps) + ba;
+    const bool act = (lane & 15) < C;
+    const float m = half_max(act ? score : -INFINITY);
     const float ex = act ? expf(score - m) : 0.f;
-    const float wgt = ex / warp_sum(ex);                                      // :1102 softmax over the classes
-    if (act) p.w[row * C + lane] = wgt;
-    float4 att[AT_V];
+    const float wgt = ex / half_sum(ex);                                      // :1102 softmax over the classes
+    const long long my_row = ra + (lane >> 4);
+    if (act && warp == 0 && my_row < B) p.w[my_row * C + (lane & 15)] = wgt;
+    float4 atta = z4, attb = z4;
 #pragma unroll
-    for (int i = 0; i < AT_V; ++i) att[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = 0; c < C; ++c) {
-      const float wc = __shfl_sync(0xffffffffu, wgt, c);
-#pragma unroll
-      for (int i = 0; i < AT_V; ++i)
-        if (i < nv) {
-          const float4 t = ldf4(s_tp + c * D + i * 128 + lane * 4);
-          att[i].x += wc * t.x; att[i].y += wc * t.y; att[i].z += wc * t.z; att[i].w += wc * t.w;   // :1105
-        }
+    for (int c = 0; c < AT_MAXC; ++c) {
+      const float wca = __shfl_sync(0xffffffffu, wgt, c), wcb = __shfl_sync(0xffffffffu, wgt, 16 + c);   // 0 for c >= C
+      atta.x += wca * tp[c].x; atta.y += wca * tp[c].y; atta.z += wca * tp[c].z; atta.w += wca * tp[c].w;   // :1105
+      attb.x += wcb * tp[c].x; attb.y += wcb * tp[c].y; attb.z += wcb * tp[c].z; attb.w += wcb * tp[c].w;
     }
-#pragma unroll
-    for (int i = 0; i < AT_V; ++i)
-      if (i < nv)                                                             // :1108 image_proj + attended_features
-        *reinterpret_cast<uint2*>(p.e + row * D + i * 128 + lane * 4) =
-            make_uint2(pack_bf16x2(x[i].x + att[i].x, x[i].y + att[i].y), pack_bf16x2(x[i].z + att[i].z, x[i].w + att[i].w));
+    *reinterpret_cast<uint2*>(p.e + ra * D + col) =                           // :1108 image_proj + attended_features
+        make_uint2(pack_bf16x2(xa.x + atta.x, xa.y + atta.y), pack_bf16x2(xa.z + atta.z, xa.w + atta.w));
+    if (ra + 1 < B)
+      *reinterpret_cast<uint2*>(p.e + (ra + 1) * D + col) =
+          make_uint2(pack_bf16x2(xb.x + attb.x, xb.y + attb.y), pack_bf16x2(xb.z + attb.z, xb.w + attb.w));
+    xa = xan; xb = xbn;
   }
 }
 
-__global__ void __launch_bounds__(AT_BWD_THREADS, 1) attn_bwd_kernel(const AttnParams p) {
-  extern __shared__ __align__(16) float at_smem[];          // tp [C][D] | wa [D] | acc [4 warps][(C + 2)][D]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int C = p.C, D = p.D, nv = D >> 7;
-  float* s_tp = at_smem;
-  float* s_wa = at_smem + C * D;
-  float* s_acc = s_wa + D;
-  float* my = s_acc + static_cast<size_t>(warp) * (C + 2) * D;
-  for (int i = threadIdx.x; i < C * D; i += AT_BWD_THREADS) s_tp[i] = p.tp[i];
-  for (int i = threadIdx.x; i < D; i += AT_BWD_THREADS) s_wa[i] = p.wa[i];
-  for (int i = threadIdx.x; i < (AT_BWD_THREADS / 32) * (C + 2) * D; i += AT_BWD_THREADS) s_acc[i] = 0.f;
-  __syncthreads();
-  auto acc_add = [&](int r, int i, float4 v) {                 // lane-private columns: plain read-modify-write
-    float4* q = reinterpret_cast<float4*>(my + r * D + i * 128 + lane * 4);
-    float4 t = *q;
-    t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
-    *q = t;
-  };
-  for (long long row = blockIdx.x * (AT_BWD_THREADS / 32) + warp; row < p.B; row += static_cast<long long>(gridDim.x) * (AT_BWD_THREADS / 32)) {
-    float4 x[AT_V], g[AT_V], dip[AT_V];
+// one (class, row) term of the backward pass: du = kc wa (1 - tanh^2), accumulated into d ip, d tp_c and d wa
+__device__ __forceinline__ void at_bwd_term(const float4& x, const float4& g, const float4& t, const float4& wa, float kc, float wc,
+                                            float4& dip, float4& acc_tp, float4& acc_wa) {
+  const float4 th = make_float4(tanh_fast(x.x + t.x), tanh_fast(x.y + t.y), tanh_fast(x.z + t.z), tanh_fast(x.w + t.w));
+  const float4 du = make_float4(kc * wa.x * (1.f - th.x * th.x), kc * wa.y * (1.f - th.y * th.y),
+                                kc * wa.z * (1.f - th.z * th.z), kc * wa.w * (1.f - th.w * th.w));
+  dip.x += du.x; dip.y += du.y; dip.z += du.z; dip.w += du.w;
+  acc_tp.x += du.x + wc * g.x; acc_tp.y += du.y + wc * g.y; acc_tp.z += du.z + wc * g.z; acc_tp.w += du.w + wc * g.w;   // d tp_c
+  acc_wa.x += kc * th.x; acc_wa.y += kc * th.y; acc_wa.z += kc * th.z; acc_wa.w += kc * th.w;                           // d wa
+}
+
+__global__ void __launch_bounds__(128, 2) attn_bwd_kernel(const AttnParams p) {
+  __shared__ float s_x[2][AT_MAXW][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int C = p.C, D = p.D, col = warp * 128 + lane * 4;
+  float4 tp[AT_MAXC], wa;
+  at_load_tp(p, col, tp, wa);
+  float4 acc_tp[AT_MAXC];
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < AT_V; ++i)
-      if (i < nv) {
-        x[i] = ldf4(p.ip + row * D + i * 128 + lane * 4);
-        g[i] = ldf4(p.de + row * D + i * 128 + lane * 4);
-        dip[i] = g[i];                                         // e = ip + attended: direct path
-      }
-    const bool act = lane < C;
-    const float wgt = act ? p.w[row * C + lane] : 0.f;
+  for (int c = 0; c < AT_MAXC; ++c) acc_tp[c] = z4;
+  float4 acc_wa = z4, acc_cs = z4;
+  const long long B = p.B;
+  const bool act = (lane & 15) < C;
+  auto ldw = [&](const float* src, long long ra) {          // lane l: element (l & 15) of row ra + (l >> 4), 0 outside
+    const long long r = ra + (lane >> 4);
+    return (src != nullptr && act && r < B) ? src[r * C + (lane & 15)] : 0.f;
+  };
+  long long ra = 2ll * blockIdx.x;
+  float4 xa = ra < B ? ldf4(p.ip + ra * D + col) : z4, xb = ra + 1 < B ? ldf4(p.ip + (ra + 1) * D + col) : z4;
+  float4 ga = ra < B ? ldf4(p.de + ra * D + col) : z4, gb = ra + 1 < B ? ldf4(p.de + (ra + 1) * D + col) : z4;
+  float wgt = ldw(p.w, ra), up = ldw(p.dw_up, ra);
+  for (int it = 0; ra < B; ra += 2ll * gridDim.x, ++it) {
+    const long long na = ra + 2ll * gridDim.x;
+    const float4 xan = na < B ? ldf4(p.ip + na * D + col) : z4, xbn = na + 1 < B ? ldf4(p.ip + (na + 1) * D + col) : z4;
+    const float4 gan = na < B ? ldf4(p.de + na * D + col) : z4, gbn = na + 1 < B ? ldf4(p.de + (na + 1) * D + col) : z4;
+    const float wn = ldw(p.w, na), un = ldw(p.dw_up, na);
     // d w_c = d e . tp_c  (+ upstream gradient of the returned weights)
     float part[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      part[c] = 0.f;
-      if (c < AT_MAXC && c < C) {
-        float a = 0.f;
+    for (int c = 0; c < AT_MAXC; ++c) {
+      part[c] = 0.f; part[16 + c] = 0.f;
+      if (c < C) { part[c] = dot4(ga, tp[c]); part[16 + c] = dot4(gb, tp[c]); }
+    }
+    const float dwc = at_cross_warp(colsum32_at(part, lane), s_x, it & 1, warp, lane, nwarps) + up;
+    const float sw = half_sum(wgt * dwc);                      // wgt = 0 on inactive lanes / missing rows
+    const float ds = wgt * (dwc - sw);                         // softmax backward: lane l holds d s of (row l >> 4, class l & 15)
+    float4 dipa = ga, dipb = gb;                               // e = ip + attended: direct path
 #pragma unroll
-        for (int i = 0; i < AT_V; ++i)
-          if (i < nv) {
-            const float4 t = ldf4(s_tp + c * D + i * 128 + lane * 4);
-            a += g[i].x * t.x + g[i].y * t.y + g[i].z * t.z + g[i].w * t.w;
-          }
-        part[c] = a;
+    for (int c = 0; c < AT_MAXC; ++c) {
+      if (c < C) {
+        at_bwd_term(xa, ga, tp[c], wa, __shfl_sync(0xffffffffu, ds, c), __shfl_sync(0xffffffffu, wgt, c), dipa, acc_tp[c], acc_wa);
+        at_bwd_term(xb, gb, tp[c], wa, __shfl_sync(0xffffffffu, ds, 16 + c), __shfl_sync(0xffffffffu, wgt, 16 + c), dipb, acc_tp[c], acc_wa);
       }
     }
-    float dwc = colsum32_at(part, lane);
-    if (act && p.dw_up) dwc += p.dw_up[row * C + lane];
-    const float sw = warp_sum(act ? wgt * dwc : 0.f);
-    const float ds = act ? wgt * (dwc - sw) : 0.f;             // softmax backward: lane c holds d s_c
-    for (int c = 0; c < C; ++c) {
-      const float kc = __shfl_sync(0xffffffffu, ds, c), wc = __shfl_sync(0xffffffffu, wgt, c);
-#pragma unroll
-      for (int i = 0; i < AT_V; ++i)
-        if (i < nv) {
-          const float4 t = ldf4(s_tp + c * D + i * 128 + lane * 4), wv = ldf4(s_wa + i * 128 + lane * 4);
-          const float4 th = make_float4(tanh_fast(x[i].x + t.x), tanh_fast(x[i].y + t.y), tanh_fast(x[i].z + t.z), tanh_fast(x[i].w + t.w));
-          const float4 du = make_float4(kc * wv.x * (1.f - th.x * th.x), kc * wv.y * (1.f - th.y * th.y),
-                                        kc * wv.z * (1.f - th.z * th.z), kc * wv.w * (1.f - th.w * th.w));
-          dip[i].x += du.x; dip[i].y += du.y; dip[i].z += du.z; dip[i].w += du.w;
-          acc_add(c, i, make_float4(du.x + wc * g[i].x, du.y + wc * g[i].y, du.z + wc * g[i].z, du.w + wc * g[i].w));   // d tp_c
-          acc_add(C, i, make_float4(kc * th.x, kc * th.y, kc * th.z, kc * th.w));                                        // d wa
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < AT_V; ++i)
-      if (i < nv) {
-        acc_add(C + 1, i, dip[i]);                             // column sum of d ip = gradient of image_proj.bias
-        *reinterpret_cast<uint2*>(p.dip + row * D + i * 128 + lane * 4) =
-            make_uint2(pack_bf16x2(dip[i].x, dip[i].y), pack_bf16x2(dip[i].z, dip[i].w));
-      }
+    // column sum of d ip = d image_proj.bias (a missing row B has g = 0, wgt = 0: it contributes 0)
+    acc_cs.x += dipa.x + dipb.x; acc_cs.y += dipa.y + dipb.y; acc_cs.z += dipa.z + dipb.z; acc_cs.w += dipa.w + dipb.w;
+    *reinterpret_cast<uint2*>(p.dip + ra * D + col) = make_uint2(pack_bf16x2(dipa.x, dipa.y), pack_bf16x2(dipa.z, dipa.w));
+    if (ra + 1 < B)
+      *reinterpret_cast<uint2*>(p.dip + (ra + 1) * D + col) = make_uint2(pack_bf16x2(dipb.x, dipb.y), pack_bf16x2(dipb.z, dipb.w));
+    xa = xan; xb = xbn; ga = gan; gb = gbn; wgt = wn; up = un;
   }
-  __syncthreads();
-  float* out = p.partial + static_cast<long long>(blockIdx.x) * (C + 2) * D;
-  for (int i = threadIdx.x; i < (C + 2) * D; i += AT_BWD_THREADS) {
-    float a = 0.f;
+  float* out = p.partial + static_cast<long long>(blockIdx.x) * (C + 2) * D + col;
 #pragma unroll
-    for (int w = 0; w < AT_BWD_THREADS / 32; ++w) a += s_acc[static_cast<size_t>(w) * (C + 2) * D + i];
-    out[i] = a;
-  }
+  for (int c = 0; c < AT_MAXC; ++c)
+    if (c < C) *reinterpret_cast<float4*>(out + c * D) = acc_tp[c];
+  *reinterpret_cast<float4*>(out + C * D) = acc_wa;
+  *reinterpret_cast<float4*>(out + (C + 1) * D) = acc_cs;
 }
 
 // out[i] = sum_parts partial[part][i]   (fixed order: deterministic)
@@ -219,6 +235,7 @@ __global__ void __launch_bounds__(256) attn_reduce_kernel(const float* __restric
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   float a = 0.f;
+#pragma unroll 8
   for (int q = 0; q < nparts; ++q) a += partial[static_cast<long long>(q) * n + i];
   out[i] = a;
 }
@@ -238,14 +255,25 @@ __global__ void __launch_bounds__(256) attn_text_bwd_w_kernel(const float* __res
   dwt[idx] = a;
   if (j == 0) dbt[o] = b;
 }
+// dt[c][j] = sum_o dtp[c][o] Wt[o][j]: block (j-block of 32, class c); warp s of the 8 sums the o-slice [s D/8, (s+1) D/8)
+// (round 1: one thread per output walking all D rows of Wt -- 59 us of dependent loads for 16 x 512 outputs)
 __global__ void __launch_bounds__(256) attn_text_bwd_x_kernel(const float* __restrict__ dtp, const float* __restrict__ wt, int C, int D,
                                                               float* __restrict__ dt) {
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  if (idx >= C * D) return;
-  const int c = idx / D, j = idx - c * D;
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, s = threadIdx.x >> 5;
+  const int c = blockIdx.y, j = blockIdx.x * 32 + lane;
+  const int o0 = s * (D / 8), o1 = o0 + D / 8;
   float a = 0.f;
-  for (int o = 0; o < D; ++o) a += dtp[c * D + o] * wt[static_cast<long long>(o) * D + j];
-  dt[idx] = a;
+#pragma unroll 8
+  for (int o = o0; o < o1; ++o) a += dtp[c * D + o] * wt[static_cast<long long>(o) * D + j];
+  red[s][lane] = a;
+  __syncthreads();
+  if (s == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += red[k][lane];
+    dt[c * D + j] = tot;
+  }
 }
 
 static int at_split_for(int M, int N, int K) {
@@ -255,8 +283,8 @@ static int at_split_for(int M, int N, int K) {
   if (s > kchunks) s = kchunks;
   return s < 1 ? 1 : s;
 }
-static int at_bwd_grid(long long B) {
-  return static_cast<int>(std::max<long long>(1, std::min<long long>((B + 3) / 4, num_sms())));
+static int at_bwd_grid(long long B) {                      // 2 CTAs of D/128 warps per SM (register accumulators), row pairs
+  return static_cast<int>(std::max<long long>(1, std::min<long long>((B + 1) / 2, 2LL * num_sms())));
 }
 static int check_attn(const char* who, long long B, int C, int D) {
   B200_REQUIRE(B > 0 && C > 0 && C <= AT_MAXC, "%s: need B > 0 and 0 < C <= %d (got B=%lld C=%d)", who, AT_MAXC, B, C);
@@ -284,9 +312,8 @@ extern "C" int b200clip_attention_fwd(const void* x_bf16, const float* t, long l
   B200_LAUNCH_CHECK();
   AttnParams p{};
   p.ip = ip; p.tp = tp; p.wa = wa; p.ba = ba; p.B = (int)B; p.C = C; p.D = D; p.w = w; p.e = static_cast<__nv_bfloat16*>(e_bf16);
-  const size_t smem = static_cast<size_t>(C + 1) * D * sizeof(float);
-  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((B + 7) / 8, 4LL * num_sms())));
-  attn_fwd_kernel<<<grid, AT_FWD_THREADS, smem, s>>>(p);
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((B + 1) / 2, 4LL * num_sms())));
+  attn_fwd_kernel<<<grid, 32 * (D / 128), 0, s>>>(p);
   B200_LAUNCH_CHECK();
   return gemm_bf16(e_bf16, wo_bf16, 0, 0, (int)B, D, D, D, D, EPI_STORE_F32, 1.0f, out, D, nullptr, 0, bo, nullptr, 0, nullptr, 0, 1, s);   // :1108
 }
@@ -339,10 +366,7 @@ extern "C" int b200clip_attention_bwd(const float* d_out, const float* d_w, cons
   AttnParams p{};
   p.ip = ip; p.tp = tp; p.wa = wa; p.ba = ba; p.B = (int)B; p.C = C; p.D = D; p.w = const_cast<float*>(w); p.de = de; p.dw_up = d_w;
   p.dip = static_cast<__nv_bfloat16*>(dip_bf); p.partial = partial;
-  const size_t smem = (static_cast<size_t>(C + 1) * D + static_cast<size_t>(AT_BWD_THREADS / 32) * (C + 2) * D) * sizeof(float);
-  static SmemAttrOnce attr;
-  B200_CHECK_CUDA(attr.ensure(attn_bwd_kernel, static_cast<int>((static_cast<size_t>(AT_MAXC + 1) * AT_MAXD + 4ull * (AT_MAXC + 2) * AT_MAXD) * 4)));
-  attn_bwd_kernel<<<grid, AT_BWD_THREADS, smem, s>>>(p);
+  attn_bwd_kernel<<<grid, 32 * (D / 128), 0, s>>>(p);
   B200_LAUNCH_CHECK();
   attn_reduce_kernel<<<((C + 2) * D + 255) / 256, 256, 0, s>>>(partial, grid, (C + 2) * D, red);
   B200_LAUNCH_CHECK();
@@ -363,7 +387,7 @@ extern "C" int b200clip_attention_bwd(const float* d_out, const float* d_w, cons
   attn_text_bwd_w_kernel<<<static_cast<int>((static_cast<long long>(D) * D + 255) / 256), 256, 0, s>>>(dtp, t, C, D, dwt, dbt);
   B200_LAUNCH_CHECK();
   if (dt) {
-    attn_text_bwd_x_kernel<<<(C * D + 255) / 256, 256, 0, s>>>(dtp, wt, C, D, dt);
+    attn_text_bwd_x_kernel<<<dim3(D / 32, C), 256, 0, s>>>(dtp, wt, C, D, dt);
     B200_LAUNCH_CHECK();
   }
   return B200_OK;

@@ -184,9 +184,12 @@ extern "C" int b200clip_fusion_bwd(const float* dy, const void* x_bf16, long lon
                       nullptr, 0, split_for(D, 2 * D, (int)B), s, 0.f, 0u, 0, nullptr, sk_work, sk_ws)))
     return rc;
   if (dx_f32) {
-    if ((rc = gemm_bf16(dh_bf, w0_bf16, 0, 1, (int)B, 2 * D, D, D, 2 * D, EPI_STORE_F32, 1.0f, dx_f32, 2 * D, nullptr, 0, nullptr,
-                        nullptr, 0, nullptr, 0, 1, s)))
-      return rc;
+    // d frontal | d lateral as two contiguous [B, D] halves (dx_f32 is [2][B][D]): the callers hand them to autograd as they
+    // are -- a [B, 2D] result would cost two strided 64 MB copies at B = 32768 to split
+    for (int v = 0; v < 2; ++v)
+      if ((rc = gemm_bf16(dh_bf, static_cast<const __nv_bfloat16*>(w0_bf16) + static_cast<size_t>(v) * D, 0, 1, (int)B, D, D, D, 2 * D,
+                          EPI_STORE_F32, 1.0f, dx_f32 + static_cast<size_t>(v) * B * D, D, nullptr, 0, nullptr, nullptr, 0, nullptr, 0, 1, s)))
+        return rc;
   }
   return B200_OK;
 }

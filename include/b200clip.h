@@ -107,6 +107,7 @@ int b200clip_cast_f32_bf16_2d(const float* in, long long ld_in, void* out_bf16, 
                               void* stream);
 int b200clip_fusion_fwd(const void* x_bf16, long long B, int D, const void* w0_bf16, const float* b0, const void* w3_bf16,
                         const float* b3, float drop_p, unsigned int drop_seed, void* h_bf16, float* y_f32, void* stream);
+/* dx_f32 (or NULL) is [2][B][D]: d frontal, then d lateral, each contiguous (what autograd wants: no split copies). */
 size_t b200clip_fusion_bwd_workspace_bytes(long long B, int D);
 int b200clip_fusion_bwd(const float* dy, const void* x_bf16, long long B, int D, const void* w0_bf16, const void* w3_bf16,
                         const void* h_bf16, float drop_p, float* dx_f32, float* dw0, float* db0, float* dw3, float* db3,

@@ -32,6 +32,42 @@ def timed(fn, n=20, warm=5):
     return e0.elapsed_time(e1) / n
 
 
+def timed_graph(fn, n=20, warm=3):
+    """the same step captured once into a CUDA graph and replayed: kernel time without the ~25 Python launches"""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(warm):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def kernels(fn, title):
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    print(f"# kernels of one {title} step (eager): {len(evs)} launches, {sum(e.time_range.end - e.time_range.start for e in evs):.0f} us busy")
+    for e in evs:
+        print(f"#   {e.time_range.end - e.time_range.start:7.1f} us  {e.name[:100]}")
+
+
 def line(name, ms, flops, bytes_):
     tf, gbs = flops / (ms / 1e3) / 1e12, bytes_ / (ms / 1e3) / 1e9
     print(json.dumps({"op": name, "B": B, "ms": round(ms, 4), "rows_per_s": round(B / (ms / 1e3)), "algorithmic_tflops": round(tf, 1),
@@ -54,6 +90,8 @@ def fusion_step():
 
 
 line("MultiViewFusion fwd+bwd", timed(fusion_step), 6.0 * B * (2 * D * D + D * D), B * D * (8 + 2 + 4 + 4 + 8) * 1.0)
+line("MultiViewFusion fwd+bwd (CUDA graph)", timed_graph(fusion_step), 6.0 * B * (2 * D * D + D * D), B * D * (8 + 2 + 4 + 4 + 8) * 1.0)
+kernels(fusion_step, "MultiViewFusion")
 
 # ---- MultiModalAttention fwd+bwd: GEMMs 6 B (2 D*D) flop (+ 2 passes of B*C*D tanh); bytes: x, ip f32 w+r, e bf16 w+r, out, d_out, d_e w+r, d_ip w+r, dx
 att = b200clip.MultiModalAttention().to(dev)
@@ -70,6 +108,8 @@ def attn_step():
 
 
 line("MultiModalAttention fwd+bwd", timed(attn_step), 6.0 * B * (2 * D * D), B * D * (4 + 8 + 4 + 4 + 4 + 8 + 4 + 4) * 1.0)
+line("MultiModalAttention fwd+bwd (CUDA graph)", timed_graph(attn_step), 6.0 * B * (2 * D * D), B * D * (4 + 8 + 4 + 4 + 4 + 8 + 4 + 4) * 1.0)
+kernels(attn_step, "MultiModalAttention")
 
 # ---- ASL fwd+bwd on [B, C] logits: HBM-bound, 4 * B*C*4 bytes (logits + targets read twice, gradient written)
 lg = (torch.randn(B, C, generator=g) * 3).to(dev).requires_grad_(True)
@@ -82,3 +122,5 @@ def asl_step():
 
 
 line("multilabel_asymmetric_loss fwd+bwd", timed(asl_step), 0.0, B * C * 4 * 5.0)
+line("multilabel_asymmetric_loss fwd+bwd (CUDA graph)", timed_graph(asl_step), 0.0, B * C * 4 * 5.0)
+kernels(asl_step, "ASL")
