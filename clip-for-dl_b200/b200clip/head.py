@@ -135,10 +135,10 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
         # loss kernel queued behind the backward kernels' CTAs would hold this all-reduce, and with it the reduce-scatter of
         # dT issued after it (measured at 2 ranks: reduce-scatter start 570 us late).  So the loss kernel stays on the main
         # stream in front of the backward pass (6-17 us) and only the all-reduce is asynchronous.
-        if small:
-            main.wait_stream(heads_side)
-            heads_side = None
         _, rinvh, cinvh = ops.infonce_forward(ihat, that_all, tau_nce, row0=row0, group=group, sums_out=sums6[:3])
+        if small:
+            main.wait_stream(heads_side)                   # after the InfoNCE forward is enqueued: the heads run beside it
+            heads_side = None
         sums_work = dp.sum_across_async(sums6, group)
 
     def finish():
