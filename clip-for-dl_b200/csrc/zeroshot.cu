@@ -17,7 +17,7 @@
 
 namespace b200 {
 
-constexpr int ZS_D = 512;
+// embedding width: template parameter of the kernels (ZsCfg<DD>, 512 or 768)
 
 constexpr int ZS_MAXP = 32;
 
@@ -99,15 +99,23 @@ __device__ void emit_row_fp64(const ZsParams& p, long long row, const double* sc
 // path switched off): 3 warps per scheduler cannot hide LDS / HMMA / shuffle latencies.  The ring needs one stage per consumer
 // (see the static_assert), so more warps means smaller blocks: 24 consumers x 8-row (8 KB) stages = the same 192 KB in flight.
 constexpr int ZS_ROWS = 8;                              // rows per block = per stage
-constexpr int ZS_CONSUMERS = 24;                        // consumer warps (6 per SM sub-partition); the last warp is the bulk-copy producer
-constexpr int ZS_THREADS2 = (ZS_CONSUMERS + 1) * 32;
-constexpr int ZS_PITCH = ZS_D * 2;                      // dense rows: ONE 8 KB bulk copy per block (small copies cost ~75 clk each)
-constexpr int ZS_STAGE_BYTES = ZS_ROWS * ZS_PITCH;      // one 8-row block
-constexpr int ZS_STAGES = 24;
-// a consumer may hold a claim at most ZS_CONSUMERS-1 blocks ahead of the oldest unconsumed block; with fewer stages than
-// consumers a claim could be two fills ahead of its stage's barrier and the parity wait would alias
-static_assert(ZS_STAGES >= ZS_CONSUMERS, "ring must have at least as many stages as consumer warps");
-constexpr int ZS_SMEM_BYTES = 16 * 4 * 32 * 16 + ZS_STAGES * ZS_STAGE_BYTES + 2 * ZS_STAGES * 8 + 128;
+// Per embedding width (512 = 0426/config.py:30 default, 768 = BASELINE.json configs[4]'s other width): the prompt fragment table
+// (32 prompts x DD bf16) and the ring share the 227 KB of shared memory, so the wider rows get fewer, larger stages.
+template <int DD> struct ZsCfg {
+  static_assert(DD == 512 || DD == 768, "zero-shot kernel widths");
+  static constexpr int KS = DD / 32;                    // 32-element steps per row (two k16 MMAs each)
+  static constexpr int EPL = DD / 32;                   // elements per lane in the exact re-evaluation
+  static constexpr int FRAG_BYTES = KS * 4 * 32 * 16;   // 32 KB / 48 KB
+  static constexpr int CONSUMERS = DD == 512 ? 24 : 14; // consumer warps; the last warp of the CTA is the bulk-copy producer
+  static constexpr int THREADS = (CONSUMERS + 1) * 32;
+  static constexpr int PITCH = DD * 2;                  // dense rows: ONE bulk copy per block (small copies cost ~75 clk each)
+  static constexpr int STAGE_BYTES = ZS_ROWS * PITCH;   // one 8-row block: 8 KB / 12 KB
+  // a consumer may hold a claim at most CONSUMERS-1 blocks ahead of the oldest unconsumed block; with fewer stages than
+  // consumers a claim could be two fills ahead of its stage's barrier and the parity wait would alias
+  static constexpr int STAGES = CONSUMERS;
+  static constexpr int SMEM_BYTES = FRAG_BYTES + STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
 
 __device__ __forceinline__ void bulk_load_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -119,20 +127,23 @@ __device__ __forceinline__ void bulk_load_g2s(uint32_t smem_dst, const void* gsr
 // a 10-stage ring, so ~160 KB of loads are in flight per SM independent of the consumers' registers and occupancy;
 // the 8 consumer warps take 16-row blocks round-robin and read their MMA fragments from the padded rows.
 // Exact re-evaluation of ONE row by a whole warp (rows whose fast-path decision margin was inside the guard band).
-template <bool PAIR>
+template <bool PAIR, int DD>
 __device__ __forceinline__ void reevaluate_row(const ZsParams& p, long long row, int lane) {
+  constexpr int EPL = ZsCfg<DD>::EPL, NW = EPL / 2, NV = EPL / 8;      // elements, 32-bit words, 16-byte loads per lane
   const int L = p.nlabels;
-  // lane owns k in [16*lane, 16*lane+16)
-  const uint4* px = reinterpret_cast<const uint4*>(p.x + row * p.ldx) + lane * 2;
-  const uint4 x0 = __ldg(px), x1 = __ldg(px + 1);
-  const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-  double xs[16];
+  // lane owns k in [EPL*lane, EPL*lane + EPL)
+  const uint4* px = reinterpret_cast<const uint4*>(p.x + row * p.ldx) + lane * NV;
+  uint32_t xw[NW];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const uint4 q = __ldg(px + v);
+    xw[4 * v] = q.x; xw[4 * v + 1] = q.y; xw[4 * v + 2] = q.z; xw[4 * v + 3] = q.w;
+  }
   double ss = 0.0;
 #pragma unroll
-  for (int jx = 0; jx < 8; ++jx) {
-    xs[2 * jx] = static_cast<double>(bf16_lo(xw[jx]));
-    xs[2 * jx + 1] = static_cast<double>(bf16_hi(xw[jx]));
-    ss += xs[2 * jx] * xs[2 * jx] + xs[2 * jx + 1] * xs[2 * jx + 1];
+  for (int jx = 0; jx < NW; ++jx) {
+    const double a = static_cast<double>(bf16_lo(xw[jx])), b = static_cast<double>(bf16_hi(xw[jx]));
+    ss += a * a + b * b;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -141,21 +152,25 @@ __device__ __forceinline__ void reevaluate_row(const ZsParams& p, long long row,
   // cost ~50 us of a 270 us kernel at 0.4 % flagged rows).  bf16 x bf16 products are EXACT in fp32 (8 + 8 significand
   // bits), and Knuth's TwoSum keeps the rounding error of every addition, so (hi, lo) carries the sum to ~2^-45: the
   // decisions made from it are those of the fp64 evaluation unless a margin is below ~1e-13 of the score scale.
-  float xf[16];
+  float xf[EPL];
 #pragma unroll
-  for (int jx = 0; jx < 8; ++jx) { xf[2 * jx] = bf16_lo(xw[jx]); xf[2 * jx + 1] = bf16_hi(xw[jx]); }
+  for (int jx = 0; jx < NW; ++jx) { xf[2 * jx] = bf16_lo(xw[jx]); xf[2 * jx + 1] = bf16_hi(xw[jx]); }
   double l[ZS_MAXP];
   // 4 prompts per trip: their TwoSum chains (16 dependent additions each) and L2 round trips are independent, so one row
   // costs ~7 chain latencies instead of 28 (the fix-up kernel's duration IS one row's latency: every warp has 1-2 rows)
 #pragma unroll 4
   for (int c = 0; c < p.np; ++c) {
     // the prompts themselves (28 KB, L1/L2-resident) -- the fragment table is in MMA register order
-    const uint4* pp = reinterpret_cast<const uint4*>(p.prompts + static_cast<long long>(c) * ZS_D) + lane * 2;
-    const uint4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
-    const uint32_t pw[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    const uint4* pp = reinterpret_cast<const uint4*>(p.prompts + static_cast<long long>(c) * DD) + lane * NV;
+    uint32_t pw[NW];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const uint4 q = __ldg(pp + v);
+      pw[4 * v] = q.x; pw[4 * v + 1] = q.y; pw[4 * v + 2] = q.z; pw[4 * v + 3] = q.w;
+    }
     float hi = 0.f, lo = 0.f;
 #pragma unroll
-    for (int jx = 0; jx < 16; ++jx) {
+    for (int jx = 0; jx < EPL; ++jx) {
       const float pv = (jx & 1) ? bf16_hi(pw[jx >> 1]) : bf16_lo(pw[jx >> 1]);
       const float prod = __fmul_rn(xf[jx], pv);                         // exact
       const float s = __fadd_rn(hi, prod);                              // TwoSum(hi, prod)
@@ -184,12 +199,12 @@ __device__ __forceinline__ void reevaluate_row(const ZsParams& p, long long row,
 // Second pass: one warp per listed row.  Inline, the re-evaluation cost 43 us of a 263 us kernel at 0.4 % flagged rows (28
 // dependent L2 round trips per row on ONE warp of an SM whose other warps wait on the same instruction cache); here the
 // rows are independent work items of a full grid.
-template <bool PAIR>
+template <bool PAIR, int DD>
 __global__ void __launch_bounds__(256) zeroshot_fixup_kernel(const ZsParams p) {
   const int lane = threadIdx.x & 31;
   const unsigned int nfix = min(*p.fix_count, p.fix_cap);
   for (unsigned int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < nfix; i += gridDim.x * 8)
-    reevaluate_row<PAIR>(p, static_cast<long long>(p.fix_rows[i]), lane);
+    reevaluate_row<PAIR, DD>(p, static_cast<long long>(p.fix_rows[i]), lane);
 }
 
 // PAIR / TOPK are compile-time: the decision code below is branch-heavy and the common call (pair mode or plain labels, no
@@ -209,19 +224,22 @@ __global__ void __launch_bounds__(256) zeroshot_fixup_kernel(const ZsParams p) {
 //     c2/c3 = prompt 16mt+2g+1 x the same rows.
 //   * row norms: diagonal of the Gram blocks X[0..15] . X[0..7]^T and X[0..15] . X[8..15]^T (one extra MMA pair per k16 with X
 //     as BOTH operands; the A quad of rows (r, r+8) costs 4 moves per k16, the only ones left).
-template <bool PAIR, bool TOPK>
-__global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams p) {
+template <bool PAIR, bool TOPK, int DD>
+__global__ void __launch_bounds__(ZsCfg<DD>::THREADS, 1) zeroshot_kernel(const ZsParams p) {
+  using Cfg = ZsCfg<DD>;
+  constexpr int ZS_STAGES = Cfg::STAGES, ZS_STAGE_BYTES = Cfg::STAGE_BYTES, ZS_PITCH = Cfg::PITCH, ZS_CONSUMERS = Cfg::CONSUMERS;
+  constexpr int ZS_THREADS2 = Cfg::THREADS, ZS_D = DD;
   extern __shared__ __align__(128) uint8_t zs_smem[];
   // A fragments in consumption order: frag[((s*2 + mt)*2 + j)*32 + lane] = {P[pr0][kb..+1], P[pr1][kb..+1], P[pr0][kb+2..+3],
   // P[pr1][kb+2..+3]}, pr0 = 16mt + 2(lane/4), pr1 = pr0 + 1, kb = 32s + 8(lane%4) + 4j
   uint4* s_frag = reinterpret_cast<uint4*>(zs_smem);
-  uint8_t* ring = zs_smem + 16 * 4 * 32 * 16;
+  uint8_t* ring = zs_smem + Cfg::FRAG_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + ZS_STAGES * ZS_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + ZS_STAGES;
   int* next_claim = reinterpret_cast<int*>(empty_bar + ZS_STAGES);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t = lane & 3, g = lane >> 2;
-  for (int i = threadIdx.x; i < 16 * 4 * 32; i += ZS_THREADS2) {
+  for (int i = threadIdx.x; i < Cfg::KS * 4 * 32; i += ZS_THREADS2) {
     const int l = i & 31, j = (i >> 5) & 1, mt = (i >> 6) & 1, s = i >> 7;
     const int pr0 = 16 * mt + 2 * (l >> 2), kb = 32 * s + 8 * (l & 3) + 4 * j;
     uint2 v0 = make_uint2(0u, 0u), v1 = make_uint2(0u, 0u);
@@ -309,7 +327,7 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
       for (int i = 0; i < 4; ++i) acc[mt][i] = 0.f;
     float na[4] = {0.f, 0.f, 0.f, 0.f};                   // Gram block X . X^T for the row norms (A rows 8..15 are zero)
 #pragma unroll 4
-    for (int s = 0; s < 16; ++s) {
+    for (int s = 0; s < Cfg::KS; ++s) {
       const uint4 xa = pa[s * 4];
       if (normalize) {
         mma_bf16_16816(na, xa.x, 0u, xa.y, 0u, xa.x, xa.y);
@@ -467,7 +485,7 @@ __global__ void __launch_bounds__(ZS_THREADS2, 1) zeroshot_kernel(const ZsParams
           continue;
         }
       }
-      reevaluate_row<PAIR>(p, row, lane);                 // no list (or list full): re-evaluate in place
+      reevaluate_row<PAIR, DD>(p, row, lane);             // no list (or list full): re-evaluate in place
     }
   }
 }
@@ -487,7 +505,7 @@ extern "C" int b200clip_zeroshot_score(const void* x_bf16, long long ldx, long l
                                        int value_mode, uint8_t* argmax, void* mask, int mask_is_u32, uint8_t* topk_idx,
                                        float* topk_val, float* scores, unsigned long long* guard_count, void* workspace,
                                        size_t workspace_bytes, void* stream) {
-  B200_REQUIRE(D == ZS_D, "zeroshot: D=%d unsupported (kernel is built for D=%d)", D, ZS_D);
+  B200_REQUIRE(D == 512 || D == 768, "zeroshot: D=%d unsupported (the kernel is built for D = 512 and 768)", D);
   B200_REQUIRE(n >= 0 && np > 0 && np <= ZS_MAXP, "zeroshot: need 0 < np <= %d", ZS_MAXP);
   B200_REQUIRE(!pair_mode || np % 2 == 0, "zeroshot: pair mode needs an even number of prompts");
   B200_REQUIRE(temperature > 0.f && guard >= 0.f && topk >= 0 && topk <= 4, "zeroshot: bad scalar arguments");
@@ -514,22 +532,31 @@ extern "C" int b200clip_zeroshot_score(const void* x_bf16, long long ldx, long l
   }
   const long long nblk = (n + ZS_ROWS - 1) / ZS_ROWS;
   const int grid = static_cast<int>(std::min<long long>(nblk, static_cast<long long>(num_sms())));
-  static SmemAttrOnce attr[4];
-#define B200_ZS_CASE(PAIR, TOPK, IDX)                                                         \
-  if ((pair_mode != 0) == PAIR && (topk > 0) == TOPK) {                                       \
-    B200_CHECK_CUDA(attr[IDX].ensure(zeroshot_kernel<PAIR, TOPK>, ZS_SMEM_BYTES));            \
-    zeroshot_kernel<PAIR, TOPK><<<grid, ZS_THREADS2, ZS_SMEM_BYTES, s>>>(p);                  \
+  static SmemAttrOnce attr[8];
+#define B200_ZS_CASE(PAIR, TOPK, DD, IDX)                                                                       \
+  if ((pair_mode != 0) == PAIR && (topk > 0) == TOPK && D == DD) {                                              \
+    B200_CHECK_CUDA(attr[IDX].ensure(zeroshot_kernel<PAIR, TOPK, DD>, ZsCfg<DD>::SMEM_BYTES));                  \
+    zeroshot_kernel<PAIR, TOPK, DD><<<grid, ZsCfg<DD>::THREADS, ZsCfg<DD>::SMEM_BYTES, s>>>(p);                 \
   }
-  B200_ZS_CASE(false, false, 0)
-  B200_ZS_CASE(false, true, 1)
-  B200_ZS_CASE(true, false, 2)
-  B200_ZS_CASE(true, true, 3)
+  B200_ZS_CASE(false, false, 512, 0)
+  B200_ZS_CASE(false, true, 512, 1)
+  B200_ZS_CASE(true, false, 512, 2)
+  B200_ZS_CASE(true, true, 512, 3)
+  B200_ZS_CASE(false, false, 768, 4)
+  B200_ZS_CASE(false, true, 768, 5)
+  B200_ZS_CASE(true, false, 768, 6)
+  B200_ZS_CASE(true, true, 768, 7)
 #undef B200_ZS_CASE
   B200_LAUNCH_CHECK();
   if (p.fix_count != nullptr) {
     const int fgrid = 2 * num_sms();
-    if (pair_mode) zeroshot_fixup_kernel<true><<<fgrid, 256, 0, s>>>(p);
-    else zeroshot_fixup_kernel<false><<<fgrid, 256, 0, s>>>(p);
+    if (D == 512) {
+      if (pair_mode) zeroshot_fixup_kernel<true, 512><<<fgrid, 256, 0, s>>>(p);
+      else zeroshot_fixup_kernel<false, 512><<<fgrid, 256, 0, s>>>(p);
+    } else {
+      if (pair_mode) zeroshot_fixup_kernel<true, 768><<<fgrid, 256, 0, s>>>(p);
+      else zeroshot_fixup_kernel<false, 768><<<fgrid, 256, 0, s>>>(p);
+    }
     B200_LAUNCH_CHECK();
   }
   return B200_OK;

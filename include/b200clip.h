@@ -249,7 +249,8 @@ int b200clip_predict_multilabel(const float* image_features, long long ldx, cons
  * 14 x (pos,neg) prompt shape.  thr_logit_host: HOST array of nlabels floats, a label passes when its score
  * (cos/tau, or l+ - l- in pair mode) is > (or >= if thr_inclusive) the value, i.e. logit(threshold). */
 size_t b200clip_zeroshot_workspace_bytes(long long n);
-/* workspace (optional, b200clip_zeroshot_workspace_bytes): rows whose decision margin is inside the guard band are listed
+/* D = 512 or 768 (the two widths BASELINE.json names; np <= 32 prompts).
+ * workspace (optional, b200clip_zeroshot_workspace_bytes): rows whose decision margin is inside the guard band are listed
  * there and re-evaluated exactly by a second kernel; without it they are re-evaluated in place (same results, slower). */
 int b200clip_zeroshot_score(const void* x_bf16, long long ldx, long long n, const void* prompts_bf16, int np, int D,
                             int pair_mode, int normalize_x, float temperature, const float* thr_logit_host,

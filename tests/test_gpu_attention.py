@@ -37,7 +37,7 @@ def test_attention_matches_reference_golden(golden):
     np.testing.assert_allclose(w.detach().sum(1).cpu().numpy(), np.ones(6), atol=1e-5)
 
 
-@pytest.mark.parametrize("B,C", [(64, 16), (1000, 14), (4096, 16)])
+@pytest.mark.parametrize("B,C", [(64, 16), (1000, 14), (4096, 16), (1001, 3), (1, 16), (20001, 14)])   # odd B: the row-pair tail
 def test_attention_forward_backward(B, C):
     d = dev()
     rnd = synth.bf16_round

@@ -10,9 +10,9 @@ import synth
 pytestmark = gpu
 
 
-def _data(N, NP, seed=51):
-    X = synth.bf16_round(synth.randn(seed, N, 512) * 3.0)
-    P = synth.bf16_round(synth.unit_rows(seed + 1, NP, 512))
+def _data(N, NP, seed=51, D=512):
+    X = synth.bf16_round(synth.randn(seed, N, D) * 3.0)
+    P = synth.bf16_round(synth.unit_rows(seed + 1, NP, D))
     return X, P
 
 
@@ -77,3 +77,33 @@ def test_guard_band_rows_are_rare_and_counted():
                              thresholds=[0.5], count_guard=True)
     frac = out["guard_rows"].item() / 20000
     assert 0 < frac < 0.1
+
+
+@pytest.mark.parametrize("N", [1, 9, 4000, 100003])
+def test_width_768_all_modes_exact(N):
+    """shared_embedding_size = 768 (0426/config.py:30 is a knob; BASELINE.json configs[4] names 512 and 768): 14-stage ring of
+    12 KB blocks, 24 k32 steps per row, 24 elements per lane in the exact re-evaluation."""
+    import b200clip
+    D = 768
+    X, P = _data(N, 28, seed=71, D=D)
+    am_ref, mask_ref, _ = R.zero_shot_posneg(X.double(), P.double().reshape(14, 2, D), 0.07, 0.5)
+    am, mask = b200clip.zero_shot_posneg(X.to(dev()).to(torch.bfloat16), P.to(dev()).to(torch.bfloat16).reshape(14, 2, D))
+    assert torch.equal(am.cpu().long(), am_ref)
+    assert torch.equal(b200clip.unpack_mask(mask, 14).cpu(), mask_ref)
+    X, P = _data(N, 16, seed=73, D=D)
+    k = 3
+    idx_ref, val_ref = R.zero_shot_softmax_topk(X.double(), P.double(), k, 0.07)
+    idx, val = b200clip.zero_shot_topk(X.to(dev()), P.to(dev()), k, 0.07)
+    assert torch.equal(idx.cpu().long(), idx_ref)
+    assert torch.allclose(val.cpu().double(), val_ref, rtol=2e-4, atol=1e-6)
+    mask_ref, _, am_ref = R.zero_shot_sigmoid_threshold(X.double(), P.double(), [0.45 + 0.01 * i for i in range(16)], 0.5)
+    mask, am = b200clip.zero_shot_threshold(X.to(dev()), P.to(dev()), [0.45 + 0.01 * i for i in range(16)], 0.5)
+    assert torch.equal(b200clip.unpack_mask(mask, 16).cpu(), mask_ref)
+    assert torch.equal(am.cpu().long(), am_ref)
+
+
+def test_rejects_other_widths():
+    import b200clip
+    X, P = _data(64, 28, D=640)
+    with pytest.raises(RuntimeError):
+        b200clip.zero_shot_posneg(X.to(dev()).to(torch.bfloat16), P.to(dev()).to(torch.bfloat16).reshape(14, 2, 640))

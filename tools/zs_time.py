@@ -5,8 +5,9 @@ from b200clip import ops
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(1234)
 N = 1_000_000
-X = torch.randn(N, 512, generator=g).to(torch.bfloat16).to(dev)
-P = torch.nn.functional.normalize(torch.randn(28, 512, generator=g), dim=1).to(torch.bfloat16).to(dev)
+D = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+X = torch.randn(N, D, generator=g).to(torch.bfloat16).to(dev)
+P = torch.nn.functional.normalize(torch.randn(28, D, generator=g), dim=1).to(torch.bfloat16).to(dev)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 for guard in (None, 0.0):
     for _ in range(3):
@@ -17,4 +18,4 @@ for guard in (None, 0.0):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); out = ops.zeroshot_score(X, P, pair_mode=True, temperature=0.07, thresholds=[0.5], guard=guard, count_guard=True); e1.record()
         torch.cuda.synchronize(); tot += e0.elapsed_time(e1)
-    print("guard", guard, "ms", tot / 10, "guard_rows", int(out["guard_rows"]))
+    print("D", D, "GB/s", round(N * (D * 2 + 3) / (tot / 10) / 1e6, 1), "guard", guard, "ms", tot / 10, "guard_rows", int(out["guard_rows"]))
