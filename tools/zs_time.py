@@ -19,3 +19,13 @@ for guard in (None, 0.0):
         e0.record(); out = ops.zeroshot_score(X, P, pair_mode=True, temperature=0.07, thresholds=[0.5], guard=guard, count_guard=True); e1.record()
         torch.cuda.synchronize(); tot += e0.elapsed_time(e1)
     print("D", D, "GB/s", round(N * (D * 2 + 3) / (tot / 10) / 1e6, 1), "guard", guard, "ms", tot / 10, "guard_rows", int(out["guard_rows"]))
+from torch.profiler import ProfilerActivity, profile
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for guard in (None, 0.0):
+        flush.zero_()
+        ops.zeroshot_score(X, P, pair_mode=True, temperature=0.07, thresholds=[0.5], guard=guard, count_guard=True)
+    torch.cuda.synchronize()
+evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
+t0 = evs[0].time_range.start
+for e in evs:
+    print(f"{e.time_range.start - t0:9.1f} {e.time_range.end - e.time_range.start:8.1f} us  {e.name[:80]}")
