@@ -327,14 +327,18 @@ def measure_head(args, cfg, rank, world, dev, steps, warmup, eager=False, want_e
     if want_e2e:
         # ---- e2e: same step through the public API with HOST buffers (pinned H2D in, loss D2H out, every step) ----------
         # Input pipeline as a training loop runs it: while step i computes, a copy stream moves step i+1's batch from pinned
-        # host memory into the other of two device buffer sets.  Every step's H2D copy and its loss read-back (with a
-        # stream synchronize: the user reads the loss every step) are inside the timed region.
+        # host memory into the other of two device buffer sets.  Every step's H2D copy and its loss read-back are inside the
+        # timed region.  The loss of EVERY step is copied to pinned host memory and read by the host, one step late: the host
+        # enqueues step i, then waits for step i-1's loss (an event, not a stream synchronize), so the GPU never idles while
+        # the host turns around (a logging loop that does not need the value before launching the next step).
         hx_img, hx_txt, hlab, _ = synth_inputs(cfg, b_loc, rank, dev, pinned=True)
         bufs = []
         for _ in range(2):
             bufs.append((torch.empty_like(hx_img, device=dev).requires_grad_(True),
                          torch.empty_like(hx_txt, device=dev).requires_grad_(True), torch.empty_like(hlab, device=dev)))
-        host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+        host_loss = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        seen = []
         copy_stream = torch.cuda.Stream(device=dev)
         copied = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
@@ -355,27 +359,37 @@ def measure_head(args, cfg, rank, world, dev, steps, warmup, eager=False, want_e
             d_img, d_txt, d_lab = bufs[slot]
             l = step(d_img, d_txt, d_lab)                      # graph mode: D2D into the static inputs, then one replay
             consumed[slot].record(cur)
-            host_loss.copy_(l.detach(), non_blocking=True)
+            host_loss[slot].copy_(l.detach(), non_blocking=True)
+            loss_ready[slot].record(cur)
             prefetch(slot ^ 1)                                  # next step's batch: enqueued while this step computes
-            cur.synchronize()                                   # the user reads the loss every step
-            return float(host_loss)
+            if i > 0:
+                read_loss(slot ^ 1)                             # step i-1's loss, while step i runs
+
+        def read_loss(slot):
+            loss_ready[slot].synchronize()
+            seen.append(float(host_loss[slot]))
 
         for slot in range(2):
             consumed[slot].record(torch.cuda.current_stream())
         prefetch(0)
         for i in range(4):
             e2e_step(i)
+        read_loss(3 & 1)
         barrier()
+        seen.clear()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
         for i in range(steps):
             e2e_step(i)                                         # `steps` H2D batches are copied inside the region
+        read_loss((steps - 1) & 1)                              # the last step's loss: inside the region too
         s1.record()
         barrier()
+        assert len(seen) == steps and all(v == v for v in seen), "e2e: every step's loss must have been read"
         t2 = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         out["e2e"] = {"value": B / (t2.item() / steps / 1e3), "unit": "pairs/s",
+                      "loss_readback": "every step's loss is copied to pinned host memory and read by the host inside the timed region, one step late (event wait, no stream synchronize)",
                       "h2d_bytes_per_step": world * (hx_img.numel() * 2 + hx_txt.numel() * 2 + hlab.numel() * 4),
                       "d2h_bytes_per_step": world * 4}
 
