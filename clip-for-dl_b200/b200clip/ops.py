@@ -671,12 +671,12 @@ def bce_heads(image_features, class_text, fc_weight, fc_bias, labels, temperatur
 
 
 def heads_mma_supported(D: int, c1: int, c2: int) -> bool:
-    return D == 512 and c1 == 16 and c2 == 16
+    return D in (512, 768) and c1 == 16 and c2 == 16
 
 
 def bce_heads_mma(yhat_bf16, inv_norm, class_text, fc_weight, fc_bias, labels, temperature, *, label_sum, total_elems_text,
                   total_elems_fc, sums_out, want_grad=True):
-    """Both BCE heads on tensor cores from the normalised bf16 features (head step fast path, D=512, 16+16 classes).
+    """Both BCE heads on tensor cores from the normalised bf16 features (head step fast path, D = 512 or 768, 16+16 classes).
     Returns (d_y [B,D] f32 for upstream gradient 1, coefn [B,16] bf16, db_raw [16] f32); sums_out receives 3 doubles."""
     lib = load()
     B, D = yhat_bf16.shape

@@ -24,14 +24,19 @@
 
 namespace b200 {
 
-constexpr int HM_D = 512;
+constexpr int HM_MAXD = 768;                             // widths: 512 (0426/config.py:30) and 768 (BASELINE.json configs[4])
 constexpr int HM_C = 16;                                 // classes per head (class texts | FC rows)
 constexpr int HM_THREADS = 256;
 constexpr int HM_WARPS = HM_THREADS / 32;
-// shared memory: class fragments for the score product (32 KB) + transposed class matrices for the gradient product (32 KB)
-constexpr int HM_FRAG_BYTES = 16 * 4 * 32 * 16;
-constexpr int HM_CT_BYTES = 2 * HM_D * HM_C * 2;
-constexpr int HM_SMEM = HM_FRAG_BYTES + HM_CT_BYTES;
+// shared memory: class fragments for the score product (32 / 48 KB) + transposed class matrices for the gradient product
+// (32 / 48 KB): two CTAs per SM at either width
+template <int DD> struct HmCfg {
+  static_assert(DD == 512 || DD == 768, "heads_mma widths");
+  static constexpr int KS = DD / 32;                     // 32-element steps per row (two k16 MMAs each)
+  static constexpr int FRAG_BYTES = KS * 4 * 32 * 16;
+  static constexpr int CT_BYTES = 2 * DD * HM_C * 2;
+  static constexpr int SMEM = FRAG_BYTES + CT_BYTES;
+};
 
 __device__ __forceinline__ void hmma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                            uint32_t b1) {
@@ -60,7 +65,9 @@ struct HeadsParams {
   float* db;                          // [16] sum_rows d loss / d z (unscaled) or null
 };
 
+template <int HM_D>
 __global__ void __launch_bounds__(HM_THREADS, 2) bce_heads_mma_kernel(const HeadsParams p) {
+  constexpr int HM_FRAG_BYTES = HmCfg<HM_D>::FRAG_BYTES, KS = HmCfg<HM_D>::KS;
   extern __shared__ __align__(128) uint8_t hm_smem[];
   // frag[(s*4 + t)*32 + lane] = V[8t + lane/4][32s + 8(lane%4) .. +7]   (V = 16 normalised class texts, then 16 FC rows)
   uint4* s_frag = reinterpret_cast<uint4*>(hm_smem);
@@ -82,7 +89,7 @@ __global__ void __launch_bounds__(HM_THREADS, 2) bce_heads_mma_kernel(const Head
     if (lane == 0) s_cinv[c] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 16 * 4 * 32; i += HM_THREADS) {
+  for (int i = threadIdx.x; i < KS * 4 * 32; i += HM_THREADS) {
     const int l = i & 31, t = (i >> 5) & 3, s = i >> 7;
     const int n = 8 * t + (l >> 2), k0 = 32 * s + 8 * (l & 3);
     const float* src = (n < HM_C) ? p.cls + n * HM_D + k0 : p.w + (n - HM_C) * HM_D + k0;
@@ -94,7 +101,7 @@ __global__ void __launch_bounds__(HM_THREADS, 2) bce_heads_mma_kernel(const Head
   // pairs of classes; consecutive threads take consecutive columns of one class pair so that the global reads coalesce (with
   // the class pair fastest every load was a separate 32-byte sector: ~20 us of this kernel's 35 us at B = 4096)
   for (int i = threadIdx.x; i < 2 * HM_D * HM_C / 2; i += HM_THREADS) {
-    const int col = i & (HM_D - 1), cp = (i >> 9) & 7, h = i >> 12;
+    const int col = i % HM_D, cp = (i / HM_D) & 7, h = i / (8 * HM_D);
     const int c0 = 2 * cp;
     float a, b;
     if (h == 0) {
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(HM_THREADS, 2) bce_heads_mma_kernel(const Head
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
 #pragma unroll 8
-    for (int s = 0; s < 16; ++s) {
+    for (int s = 0; s < KS; ++s) {
       const uint4 xa = __ldg(pa + s * 4), xb = __ldg(pb + s * 4);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -273,48 +280,52 @@ __global__ void __launch_bounds__(HM_THREADS, 2) bce_heads_mma_kernel(const Head
 // dW[16, 512] partials: out[c][d] = sum_rows coefn[row][c] * yhat[row][d].   One CTA per slab of rows, 8 warps x 64
 // columns; per 16-row step a warp issues 4 ldmatrix.x4.trans (A = y_hat^T: m = column, k = row) and 8 MMAs.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int SO2_ROWS = 32;                             // rows staged per iteration (2 k16 steps; static smem < 48 KB)
-constexpr int SO2_PITCH = HM_D * 2 + 16;                 // padded row pitch (bytes): ldmatrix rows 16 B apart in bank space
+constexpr int SO2_ROWS = 32;                             // slab granularity (rows per CTA are a multiple of it)
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
+// 8 warps x HM_D/8 columns (4 or 6 m-tiles of 16); rows staged per iteration: 32 at D = 512, 16 at D = 768 (static smem < 48 KB)
+template <int HM_D>
 __global__ void __launch_bounds__(HM_THREADS, 2) skinny_outer_mma_kernel(const __nv_bfloat16* __restrict__ coefn,
                                                                          const __nv_bfloat16* __restrict__ yhat, int rows,
-                                                                         int rows_per_cta, float* __restrict__ partial /*[grid][16*512]*/) {
-  __shared__ __align__(128) uint8_t s_y[SO2_ROWS * SO2_PITCH];          // [64 rows][512 bf16 + pad]
-  __shared__ __align__(16) __nv_bfloat16 s_c[HM_C][SO2_ROWS + 8];        // transposed coefficients [class][row]
+                                                                         int rows_per_cta, float* __restrict__ partial /*[grid][16*D]*/) {
+  constexpr int STG = HM_D == 512 ? 32 : 16;             // rows staged per iteration
+  constexpr int MT = HM_D / 128;                         // m-tiles (16 columns) per warp
+  constexpr int SO2_PITCH = HM_D * 2 + 16;               // padded row pitch (bytes): ldmatrix rows 16 B apart in bank space
+  __shared__ __align__(128) uint8_t s_y[STG * SO2_PITCH];               // [rows][D bf16 + pad]
+  __shared__ __align__(16) __nv_bfloat16 s_c[HM_C][STG + 8];            // transposed coefficients [class][row]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane & 3, r = lane >> 2;
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(rows, r0 + rows_per_cta);
-  float acc[4][2][4];                                     // [m-tile (16 columns)][n-tile (8 classes)][4]
+  float acc[MT][2][4];                                    // [m-tile (16 columns)][n-tile (8 classes)][4]
 #pragma unroll
-  for (int m = 0; m < 4; ++m)
+  for (int m = 0; m < MT; ++m)
 #pragma unroll
     for (int n = 0; n < 2; ++n)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[m][n][i] = 0.f;
   const uint32_t sy = smem_u32(s_y);
-  for (int base = r0; base < r1; base += SO2_ROWS) {
+  for (int base = r0; base < r1; base += STG) {
     __syncthreads();
     // stage y_hat rows (zero beyond the slab) and the transposed coefficients
-    for (int i = threadIdx.x; i < SO2_ROWS * (HM_D / 8); i += HM_THREADS) {
-      const int rr = i >> 6, ch = i & 63;
+    for (int i = threadIdx.x; i < STG * (HM_D / 8); i += HM_THREADS) {
+      const int rr = i / (HM_D / 8), ch = i % (HM_D / 8);
       const int row = base + rr;
       const uint4 v = row < r1 ? __ldg(reinterpret_cast<const uint4*>(yhat + static_cast<long long>(row) * HM_D) + ch) : make_uint4(0u, 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(s_y + rr * SO2_PITCH + ch * 16) = v;
     }
-    for (int i = threadIdx.x; i < SO2_ROWS * HM_C; i += HM_THREADS) {
+    for (int i = threadIdx.x; i < STG * HM_C; i += HM_THREADS) {
       const int rr = i >> 4, c = i & 15;   // HM_C == 16
       const int row = base + rr;
       s_c[c][rr] = row < r1 ? coefn[static_cast<long long>(row) * HM_C + c] : __float2bfloat16(0.f);
     }
     __syncthreads();
 #pragma unroll
-    for (int ks = 0; ks < SO2_ROWS / 16; ++ks) {
+    for (int ks = 0; ks < STG / 16; ++ks) {
       // B fragments: (k = row 16ks + 2q, +1 ; n = class r) and rows +8 ; second n-tile: class 8 + r
       uint32_t bfr[2][2];
 #pragma unroll
@@ -323,11 +334,11 @@ __global__ void __launch_bounds__(HM_THREADS, 2) skinny_outer_mma_kernel(const _
         bfr[n][1] = *reinterpret_cast<const uint32_t*>(&s_c[8 * n + r][16 * ks + 8 + 2 * q]);
       }
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        // A = y_hat^T tile: m = column (warp*64 + 16m ..+16), k = row (16ks ..+16).  Stored [row][col]: four 8x8 blocks
+      for (int m = 0; m < MT; ++m) {
+        // A = y_hat^T tile: m = column (warp*16MT + 16m ..+16), k = row (16ks ..+16).  Stored [row][col]: four 8x8 blocks
         // (rows 0-7 | cols 0-7), (rows 0-7 | cols 8-15), (rows 8-15 | cols 0-7), (rows 8-15 | cols 8-15), transposed on load
         // -> a0 = (m 0-7, k 0-7), a1 = (m 8-15, k 0-7), a2 = (m 0-7, k 8-15), a3 = (m 8-15, k 8-15)
-        const int col0 = warp * 64 + 16 * m;
+        const int col0 = warp * (16 * MT) + 16 * m;
         const int lrow = 16 * ks + (lane & 7) + ((lane >> 4) << 3);       // lanes 0-15: rows 0-7 ; 16-31: rows 8-15
         const int lcol = col0 + (((lane >> 3) & 1) << 3);                 // lanes 8-15, 24-31: cols +8
         uint32_t a[4];
@@ -340,10 +351,10 @@ __global__ void __launch_bounds__(HM_THREADS, 2) skinny_outer_mma_kernel(const _
   // acc[m][n] = {(col 16m + r, class 8n + 2q), (col .., class +1), (col 16m + r + 8, class ..), (.., +1)}
   float* out = partial + static_cast<long long>(blockIdx.x) * (HM_C * HM_D);
 #pragma unroll
-  for (int m = 0; m < 4; ++m)
+  for (int m = 0; m < MT; ++m)
 #pragma unroll
     for (int n = 0; n < 2; ++n) {
-      const int col = warp * 64 + 16 * m + r, c = 8 * n + 2 * q;
+      const int col = warp * (16 * MT) + 16 * m + r, c = 8 * n + 2 * q;
       out[c * HM_D + col] = acc[m][n][0];
       out[(c + 1) * HM_D + col] = acc[m][n][1];
       out[c * HM_D + col + 8] = acc[m][n][2];
@@ -384,7 +395,7 @@ using namespace b200;
 extern "C" size_t b200clip_bce_heads_mma_workspace_bytes(long long rows) {
   const size_t a = static_cast<size_t>(hm_grid(rows)) * (3 + HM_C) * sizeof(double) + 256;
   const int per = so2_rows_per_cta(rows);
-  const size_t b = static_cast<size_t>((rows + per - 1) / per) * HM_C * HM_D * sizeof(float);
+  const size_t b = static_cast<size_t>((rows + per - 1) / per) * HM_C * HM_MAXD * sizeof(float);
   return a + b + 256;
 }
 
@@ -394,8 +405,8 @@ extern "C" int b200clip_bce_heads_mma_fwd(const void* yhat_bf16, const float* in
                                           const float* label_sum, double total_elems_text, double total_elems_fc, float* d_y,
                                           void* coefn_bf16, float* db_fc, double* sums, void* workspace, size_t workspace_bytes,
                                           void* stream) {
-  if (D != HM_D || c1 != HM_C || c2 != HM_C)
-    return fail(B200_ERR_UNSUPPORTED, "bce_heads_mma: built for D=512 and 16+16 classes (got D=%d, %d+%d); use b200clip_bce_heads_fwd_bwd", D, c1, c2);
+  if ((D != 512 && D != 768) || c1 != HM_C || c2 != HM_C)
+    return fail(B200_ERR_UNSUPPORTED, "bce_heads_mma: built for D=512/768 and 16+16 classes (got D=%d, %d+%d); use b200clip_bce_heads_fwd_bwd", D, c1, c2);
   B200_REQUIRE(B > 0 && yhat_bf16 && inv_norm && class_text && fc_weight && labels && label_sum && sums && temperature > 0.f,
                "bce_heads_mma: missing arguments");
   B200_REQUIRE(aligned16(yhat_bf16) && aligned16(class_text) && aligned16(fc_weight) && aligned16(d_y) && aligned16(coefn_bf16),
@@ -411,10 +422,15 @@ extern "C" int b200clip_bce_heads_mma_fwd(const void* yhat_bf16, const float* in
   p.dy = d_y; p.coefn = static_cast<__nv_bfloat16*>(coefn_bf16); p.db = db_fc; p.sums = sums;
   p.partial = static_cast<double*>(workspace);
   p.counter = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(workspace) + static_cast<size_t>(grid) * (3 + HM_C) * sizeof(double));
-  static SmemAttrOnce attr;
-  B200_CHECK_CUDA(attr.ensure(bce_heads_mma_kernel, HM_SMEM));
+  static SmemAttrOnce attr512, attr768;
   B200_CHECK_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), s));
-  bce_heads_mma_kernel<<<grid, HM_THREADS, HM_SMEM, s>>>(p);
+  if (D == 512) {
+    B200_CHECK_CUDA(attr512.ensure(bce_heads_mma_kernel<512>, HmCfg<512>::SMEM));
+    bce_heads_mma_kernel<512><<<grid, HM_THREADS, HmCfg<512>::SMEM, s>>>(p);
+  } else {
+    B200_CHECK_CUDA(attr768.ensure(bce_heads_mma_kernel<768>, HmCfg<768>::SMEM));
+    bce_heads_mma_kernel<768><<<grid, HM_THREADS, HmCfg<768>::SMEM, s>>>(p);
+  }
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -423,7 +439,7 @@ extern "C" int b200clip_bce_heads_mma_fwd(const void* yhat_bf16, const float* in
 extern "C" int b200clip_skinny_outer_mma(const void* coefn_bf16, const void* yhat_bf16, long long rows, int D, int C,
                                          const float* out_scale, float* out_w, const float* db_raw, float* db_out,
                                          void* workspace, size_t workspace_bytes, void* stream) {
-  if (D != HM_D || C != HM_C) return fail(B200_ERR_UNSUPPORTED, "skinny_outer_mma: built for D=512, C=16 (got D=%d C=%d)", D, C);
+  if ((D != 512 && D != 768) || C != HM_C) return fail(B200_ERR_UNSUPPORTED, "skinny_outer_mma: built for D=512/768, C=16 (got D=%d C=%d)", D, C);
   B200_REQUIRE(rows > 0 && coefn_bf16 && yhat_bf16 && out_w, "skinny_outer_mma: missing arguments");
   B200_REQUIRE(aligned16(yhat_bf16) && aligned16(coefn_bf16), "skinny_outer_mma: pointers must be 16-byte aligned");
   if (workspace_bytes < b200clip_bce_heads_mma_workspace_bytes(rows)) return fail(B200_ERR_WORKSPACE, "skinny_outer_mma: workspace too small");
@@ -431,11 +447,15 @@ extern "C" int b200clip_skinny_outer_mma(const void* coefn_bf16, const void* yha
   const int per = so2_rows_per_cta(rows);
   const int grid = static_cast<int>((rows + per - 1) / per);
   float* partial = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + static_cast<size_t>(hm_grid(rows)) * (3 + HM_C) * sizeof(double) + 256);
-  skinny_outer_mma_kernel<<<grid, HM_THREADS, 0, s>>>(static_cast<const __nv_bfloat16*>(coefn_bf16),
-                                                      static_cast<const __nv_bfloat16*>(yhat_bf16), static_cast<int>(rows), per, partial);
+  if (D == 512)
+    skinny_outer_mma_kernel<512><<<grid, HM_THREADS, 0, s>>>(static_cast<const __nv_bfloat16*>(coefn_bf16),
+                                                             static_cast<const __nv_bfloat16*>(yhat_bf16), static_cast<int>(rows), per, partial);
+  else
+    skinny_outer_mma_kernel<768><<<grid, HM_THREADS, 0, s>>>(static_cast<const __nv_bfloat16*>(coefn_bf16),
+                                                             static_cast<const __nv_bfloat16*>(yhat_bf16), static_cast<int>(rows), per, partial);
   B200_LAUNCH_CHECK();
-  so2_reduce_kernel<<<(HM_C * HM_D + 255) / 256, 256, 0, s>>>(partial, grid, HM_C * HM_D, out_w, out_scale, db_raw,
-                                                              (db_raw && db_out) ? db_out : nullptr, HM_C);
+  so2_reduce_kernel<<<(HM_C * D + 255) / 256, 256, 0, s>>>(partial, grid, HM_C * D, out_w, out_scale, db_raw,
+                                                           (db_raw && db_out) ? db_out : nullptr, HM_C);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

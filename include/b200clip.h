@@ -188,7 +188,7 @@ int b200clip_skinny_outer(const float* coef, int C, const float* x, long long ld
                           int D, float* out_w, float* out_b, int accumulate, const float* out_scale, void* workspace,
                           size_t workspace_bytes, void* stream);
 
-/* a-B + a-A on warp-level tensor cores (head step, D = 512, 16 class texts + 16 FC rows): reads the L2-normalised bf16
+/* a-B + a-A on warp-level tensor cores (head step, D = 512 or 768, 16 class texts + 16 FC rows): reads the L2-normalised bf16
  * features and 1/||y||; writes sums[3] as above, d_y [B,D] = d(text BCE + FC BCE)/dy for upstream gradient 1, the FC
  * coefficients times ||y|| in bf16 (coefn [B,16], feeds b200clip_skinny_outer_mma) and db_fc[16] = sum_rows dL/dz. */
 size_t b200clip_bce_heads_mma_workspace_bytes(long long rows);

@@ -87,14 +87,15 @@ def test_predict_multilabel(B, thr):
     assert safe.float().mean() > 0.999
 
 
-@pytest.mark.parametrize("B,tau", [(1000, 1.0), (4096, 0.07), (37, 1.0)])
-def test_bce_heads_tensor_core_path_vs_oracle(B, tau):
+@pytest.mark.parametrize("B,tau,D", [(1000, 1.0, 512), (4096, 0.07, 512), (37, 1.0, 512), (1000, 1.0, 768), (4100, 0.07, 768),
+                                      (37, 1.0, 768)])
+def test_bce_heads_tensor_core_path_vs_oracle(B, tau, D):
     """heads_mma.cu (both BCE heads on mma.sync from the bf16 normalised features) vs the reference ops in fp32/autograd
     on the same bf16-rounded normalised features: F.normalize + class-text BCE (0426/train.py:178-230) and
     Linear(512,16) + BCEWithLogits (NB02 c28:50-52)."""
     from b200clip import ops
     d = dev()
-    C, D = 16, 512
+    C = 16
     y = synth.randn(31, B, D) * 1.7
     ct = synth.randn(32, C, D)
     W = synth.uniform(33, -0.044, 0.044, C, D)

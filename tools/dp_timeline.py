@@ -1,5 +1,5 @@
 """Kernel timeline of one graphed head step on rank 0 (torch.profiler/CUPTI), for the multi-GPU overlap analysis.
-   torchrun --nproc-per-node N tools/dp_timeline.py [global_B] [E_img]"""
+   torchrun --nproc-per-node N tools/dp_timeline.py [global_B] [E_img] [D]"""
 import os
 import sys
 
@@ -20,6 +20,8 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 cfg = dict(bench.CFG["cfg3"], B=B)
 if len(sys.argv) > 2:
     cfg["E_img"] = int(sys.argv[2])
+if len(sys.argv) > 3:
+    cfg["D"] = int(sys.argv[3])
 b_loc = B // world
 torch.manual_seed(0)
 head = b200clip.ClipHead(cfg["E_img"], cfg["E_txt"], cfg["D"], cfg["C"], 0.07, 1.0).to(dev)
