@@ -77,8 +77,10 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
     with torch.cuda.stream(side if side is not None else main):
         xt = ops.cast_bf16(x_txt)
         tw1b, tw2b = ops.cast_bf16(tw1), ops.cast_bf16(tw2)
+        # the fp32 LayerNorm output is never read on this path (InfoNCE and the heads consume y_hat bf16 + 1/||y||): not written
         y_txt, that_loc, inv_txt, saved_t = ops.proj_fwd(xt, tw1b, f(tb1), tw2b, f(tb2), f(tg), f(tbeta), want_yhat=True,
-                                                         drop_p=drop_p, drop_seed=drop_seed + 1, drop_seed_dev=drop_seed_dev)
+                                                         drop_p=drop_p, drop_seed=drop_seed + 1, drop_seed_dev=drop_seed_dev,
+                                                         want_y=False)
         if W > 1 and side is not None:
             # data parallel: the image chain starts when the text chain has finished, so the text chain gets the whole GPU and
             # the all-gather of T_hat (81 us at 8 ranks, RING_LL) starts ~25 us earlier, hidden behind the image chain + heads
@@ -92,10 +94,12 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
     iw1b, iw2b = ops.cast_bf16(iw1), ops.cast_bf16(iw2)
     if W > 1 and side is not None:
         main.wait_event(text_done)
-    y_img, ihat, inv_img, saved_i = ops.proj_fwd(xi, iw1b, f(ib1), iw2b, f(ib2), f(ig), f(ibeta), want_yhat=True,
-                                                 drop_p=drop_p, drop_seed=drop_seed, drop_seed_dev=drop_seed_dev)
     C = class_text.shape[0]
     Cf = fw.shape[0]
+    fast_heads = ops.heads_mma_supported(iw2.shape[0], C, Cf)          # tensor-core heads read y_hat; the fp32 heads read y
+    y_img, ihat, inv_img, saved_i = ops.proj_fwd(xi, iw1b, f(ib1), iw2b, f(ib2), f(ig), f(ibeta), want_yhat=True,
+                                                 drop_p=drop_p, drop_seed=drop_seed, drop_seed_dev=drop_seed_dev,
+                                                 want_y=not fast_heads)
     sums6 = torch.empty((6,), dtype=torch.float64, device=x_img.device)   # rank-local loss numerators (NCE 3 | BCE 3)
     # one pass over y_img serves both BCE heads, forward AND backward: the input gradient d_bce (for upstream grad 1)
     # and the FC coefficients are produced here; backward only scales them by the incoming gradient.  The heads do not
@@ -104,7 +108,6 @@ def head_forward(x_img, x_txt, class_text, labels, tau_nce, tau_bce, group, drop
         heads_side.wait_stream(main)                       # the heads branch: label count (above), then the image features
     with torch.cuda.stream(heads_side if small else main):
         dp.wait(lsum_work)
-        fast_heads = ops.heads_mma_supported(y_img.shape[1], C, Cf)
         if fast_heads:        # tensor-core path: reads the bf16 normalised features LayerNorm wrote for InfoNCE
             d_bce, coef, db_raw = ops.bce_heads_mma(ihat, inv_img, class_text, fw, fb, labels_f, tau_bce, label_sum=lsum,
                                                     total_elems_text=float(b_glob) * C, total_elems_fc=float(b_glob) * Cf,
@@ -173,7 +176,7 @@ def head_backward(tensors, meta, g):
     seed_dev = meta.get("drop_seed_dev")
     g = ops._f32c(g).reshape(())
     W = meta["W"]
-    b_loc = y_txt.shape[0]
+    b_loc = ihat.shape[0]
     main = torch.cuda.current_stream()
     side = _side_stream(ihat.device) if (b_loc <= TWO_STREAM_MAX_ROWS or W > 1) else None
     nce_side = None

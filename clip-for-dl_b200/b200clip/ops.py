@@ -152,15 +152,16 @@ def new_dropout_seed() -> int:
 # a-P1 / a-P2 projection block
 # --------------------------------------------------------------------------------------------------------------
 def proj_fwd(x_bf16, w1_bf16, b1, w2_bf16, b2, gamma, beta, want_yhat: bool, drop_p: float = 0.0, drop_seed: int = 0,
-             drop_seed_dev: Optional[torch.Tensor] = None):
-    """drop_seed_dev: optional device int32 word added to drop_seed inside the kernels (GraphedHeadStep's per-replay seed)."""
+             drop_seed_dev: Optional[torch.Tensor] = None, want_y: bool = True):
+    """drop_seed_dev: optional device int32 word added to drop_seed inside the kernels (GraphedHeadStep's per-replay seed).
+    want_y=False skips the fp32 LayerNorm output (the fused head only consumes the normalised bf16 copy and 1/||y||)."""
     B, E = x_bf16.shape
     D = w1_bf16.shape[0]
     dev = x_bf16.device
     p = torch.empty((B, D), dtype=torch.bfloat16, device=dev)
     h = torch.empty((B, D), dtype=torch.bfloat16, device=dev)
     z = torch.empty((B, D), dtype=torch.float32, device=dev)
-    y = torch.empty((B, D), dtype=torch.float32, device=dev)
+    y = torch.empty((B, D), dtype=torch.float32, device=dev) if want_y else None
     mean = torch.empty((B,), dtype=torch.float32, device=dev)
     rstd = torch.empty((B,), dtype=torch.float32, device=dev)
     yhat = torch.empty((B, D), dtype=torch.bfloat16, device=dev) if want_yhat else None
