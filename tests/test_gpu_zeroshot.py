@@ -107,3 +107,20 @@ def test_rejects_other_widths():
     X, P = _data(64, 28, D=640)
     with pytest.raises(RuntimeError):
         b200clip.zero_shot_posneg(X.to(dev()).to(torch.bfloat16), P.to(dev()).to(torch.bfloat16).reshape(14, 2, 640))
+
+
+def test_posneg_at_benchmark_size_against_chunked_fp64_oracle():
+    """BASELINE.json configs[3] at its full size: 1 000 000 embeddings x 14 (positive, negative) prompt pairs, D = 512.  The
+    fp64 oracle is evaluated in 8 chunks of 125 000 rows on the host; arg-max and label sets must be identical for every row."""
+    import b200clip
+    d = dev()
+    N = 1_000_000
+    g = torch.Generator(device=d).manual_seed(5)
+    X = (torch.randn(N, 512, device=d, generator=g) * 3.0).to(torch.bfloat16)
+    P = synth.bf16_round(synth.unit_rows(52, 28, 512))
+    am, mask = b200clip.zero_shot_posneg(X, P.to(d).to(torch.bfloat16).reshape(14, 2, 512))
+    am, sets = am.cpu().long(), b200clip.unpack_mask(mask, 14).cpu()
+    for s in range(0, N, 125_000):
+        am_ref, mask_ref, _ = R.zero_shot_posneg(X[s:s + 125_000].cpu().double(), P.double().reshape(14, 2, 512), 0.07, 0.5)
+        assert torch.equal(am[s:s + 125_000], am_ref)
+        assert torch.equal(sets[s:s + 125_000], mask_ref)
