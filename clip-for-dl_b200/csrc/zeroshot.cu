@@ -123,9 +123,9 @@ __device__ __forceinline__ void bulk_load_g2s(uint32_t smem_dst, const void* gsr
                : "memory");
 }
 
-// Rows are staged by a producer warp with asynchronous bulk copies (one 16 KB copy per 16-row block) into
-// a 10-stage ring, so ~160 KB of loads are in flight per SM independent of the consumers' registers and occupancy;
-// the 8 consumer warps take 16-row blocks round-robin and read their MMA fragments from the padded rows.
+// Rows are staged by a producer warp with asynchronous bulk copies (ONE copy per 8-row block: 8 KB at D = 512, 12 KB at 768)
+// into a ring with one stage per consumer warp, so 170-190 KB of loads are in flight per SM independent of the consumers'
+// registers and occupancy; the consumer warps claim blocks dynamically and read their MMA fragments straight from the rows.
 // Exact re-evaluation of ONE row by a whole warp (rows whose fast-path decision margin was inside the guard band).
 template <bool PAIR, int DD>
 __device__ __forceinline__ void reevaluate_row(const ZsParams& p, long long row, int lane) {
