@@ -5,13 +5,18 @@
 // (SURVEY.md 8a-N):   loss = m + (sum_i log r_i + sum_j log c_j)/(2B) - (sum_i S_ii)/B
 //                      G    = E (1/r_i + 1/c_j)/(2B) - I/B ;  dI = G T / tau ;  dT = G^T I / tau
 //
-// Pass 1  nce_fwd_kernel : persistent CTAs walk 128x128 S tiles (X row block stationary in smem, Y streamed by TMA,
-//                          tcgen05.mma into double-buffered TMEM); two epilogue warpgroups turn tiles into
-//                          row sums (in-thread) and column sums (warp butterfly) -> r_part / c_part.
-// Pass 2  nce_bwd_kernel : one CTA per (direction, 128-row block, D-half).  Per 32-column tile: recompute S
-//                          (tcgen05, N=32), epilogue forms G (bf16) in swizzled smem, a second tcgen05.mma chain
-//                          accumulates dX[:, half] += G * Y[:, half] in TMEM (Y tile reused as MN-major operand).
+// Pass 1  nce_fwd2_kernel (round 2): a CTA PAIR (cluster 2x1x1) owns two stacked 128-row blocks and issues one
+//                          tcgen05.mma.cta_group::2 of M = 256, N = 256 per k16 step; each CTA supplies its own rows of X and
+//                          half of the Y tile, 16 epilogue warps per CTA turn the 128 x 256 fp32 tile into row sums
+//                          (in-thread) and column sums (31-shuffle exchange) -> r_part / c_part.  D = 512: X stationary in
+//                          smem; any other D = 64k <= 1024: X chunks streamed with Y.
+//         nce_fwd_kernel : round 1's one-CTA-per-SM kernel (128 x 128 tiles), kept behind B200CLIP_FWD_VARIANT=1.
+// Pass 2  nce_bwdc_kernel<NC> (infonce_bwd.cuh): cluster of NC = D/256 CTAs per (direction, 128-row block, column split); the
+//                          CTAs own 256-wide slices of dX.  Per 32-column tile the owner CTA recomputes S (tcgen05, N = 32,
+//                          X in TMEM), forms G (bf16) and sends it to its peers; every CTA accumulates
+//                          dX[:, slice] += G * Y[:, slice] in TMEM (Y tile reused as MN-major operand).
 //                          Direction 0: X=I (rows), Y=T;  direction 1: X=T, Y=I  (G is symmetric under r<->c).
+//         nce_bwd4_kernel: round 1's D = 512 pair kernel, kept behind B200CLIP_BWD_VARIANT=4 (tests/test_gpu_variants.py).
 // Data-parallel use: I is the rank's local row block [b_loc, D] (global rows row0..), T holds all b_glob rows; column
 // sums and dT are per-rank partials that the host combines (all-reduce / reduce-scatter).
 #include <stdlib.h>
